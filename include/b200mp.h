@@ -1,0 +1,169 @@
+/* b200mp.h -- C ABI of the B200-native batched vehicle-dynamics / lattice-evaluation engine.
+ *
+ * This is the drop-in boundary for the one data-parallel hot path of earasteh/Python-Motionplanning:
+ *   VehicleModel.planar_model / planar_model_RK4   (reference libs/vehicle_model/vehicle_model.py:220-445)
+ *   CollisionChecker.collision_check               (reference libs/motionplanner/collision_checker.py:32-117)
+ *   CollisionChecker.select_best_path_index        (reference libs/motionplanner/collision_checker.py:134-203)
+ *   the multiprocessing fan-out they are called through (reference libs/motionplanner/local_planner.py:369-374)
+ * The reference is pure Python and has no FFI of its own; these are the entry points a ctypes binding
+ * on the reference side calls (INTEGRATION.md shows that binding).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  No C++ or torch types cross this boundary.
+ *   - "dev" pointers are device memory on `device`, allocated and owned by the CALLER (cudaMalloc or a
+ *     framework tensor); the library never frees them and keeps no reference after the call returns.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream)
+ *     unless stated otherwise.  Host scalars / small host arrays are consumed before the call returns.
+ *   - Return value: 0 = OK, > 0 = a cudaError_t, < 0 = argument error (B200MP_E_*).  A message for the
+ *     calling thread is available from b200mp_last_error().  No exception crosses the ABI.
+ *   - Numerical exceptional values (NaN/Inf from a wheel speed of exactly 0) are not errors; they
+ *     propagate exactly like the reference's numpy scalars.
+ *   - Arrays are structure-of-arrays with the rollout / path index fastest, so that a warp touches
+ *     32 consecutive elements per component.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef B200MP_H
+#define B200MP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MP_VERSION 100
+
+#define B200MP_E_ARG (-1)      /* bad argument (NULL pointer, negative size, unsupported channel count) */
+#define B200MP_E_PARAMS (-2)   /* no parameter table uploaded for this device / set index out of range */
+#define B200MP_E_NODEVICE (-3) /* no usable CUDA device */
+
+#define B200MP_N_STATE 10   /* [U, V, wz, wFL, wFR, wRL, wRR, yaw, x, y]            vehicle_model.py:224 */
+#define B200MP_N_CARRY 12   /* the 10 states + ax_prev, ay_prev carried step to step  drive.py:141        */
+#define B200MP_N_OUTPUTS 18 /* [fx(4) fy(4) Fz(4) s(4) fxtFL fytFL]                   vehicle_model.py:420 */
+#define B200MP_N_AUX 28     /* RK4-averaged state_dot(10) + outputs(18)               vehicle_model.py:440-441 */
+#define B200MP_N_MISC 6     /* [vx, vy, ax, ay, axc, ayc]                             vehicle_model.py:410-416 */
+
+/* np.linalg.norm([v0, v1]) closed forms (host-BLAS dependent) */
+#define B200MP_NORM2_NOFMA 0  /* sqrt(fl(v0*v0) + fl(v1*v1))    */
+#define B200MP_NORM2_FMA_V1 1 /* sqrt(fma(v1, v1, fl(v0*v0)))    */
+#define B200MP_NORM2_FMA_V0 2 /* sqrt(fma(v0, v0, fl(v1*v1)))    */
+
+/* Parameter block: the attributes of the reference's VehicleParameters that the planar model reads
+ * (vehicle_model.py:17-61).  Wheel order FL, FR, RL, RR.  D is the Pacejka peak used when no mu_max
+ * array is supplied (the reference overwrites D with mu_max on every call, vehicle_model.py:232-235). */
+typedef struct B200mpVehicleParams {
+    double m, a, b, Izz, Jw, hg, T, wL, wR, rw;
+    double B[4], C[4], D[4];
+} B200mpVehicleParams;
+
+/* Arguments of one batched RK4 rollout launch (replaces the per-vehicle loop of drive.py:141-143
+ * around VehicleModel.planar_model_RK4, vehicle_model.py:427-445).  All pointers are dev pointers of
+ * the launch's element type (double for _f64, float for _f32).
+ *   state0     [12][B]   states + ax_prev, ay_prev
+ *   delta      [n_seg][delta_ch][Bc]   delta_ch = 1: front steer on FL = FR, rear 0 (drive.py:143); 4: per wheel
+ *   torque     [n_seg][torque_ch][Bc]  torque_ch = 1: equal on 4 wheels (stanley_controller.py:159); 4: per wheel
+ *              Bc = B, or 1 when ctrl_broadcast != 0 (one control sequence for every rollout)
+ *              segment index of step n = (step0 + n) / hold   (zero-order hold, drive.py:128)
+ *   mu         [4][B] mu_max per wheel, or NULL -> parameter-set D
+ *   param_set  [B] int index into the table of b200mp_set_params, or NULL -> set 0
+ *   traj       [n_steps/store_stride][10][B] state after every store_stride-th step, or NULL (store_stride 0)
+ *   aux        [n_steps/store_stride][28][B] RK4-averaged state_dot + outputs at the same steps, or NULL
+ *   state_end  [12][B]  (may alias state0)
+ *   cost       [B] or NULL: J = sum_n (x-xr_n)^2 + (y-yr_n)^2 + w_u (U-u_ref)^2 accumulated in step order
+ *   cost_ref   [n_total][2] (xr, yr) indexed by step0 + n;  cost_in [B] or NULL = J carried in from a previous launch
+ */
+typedef struct B200mpRolloutArgs {
+    int B;
+    int n_steps;
+    int step0;
+    int hold;
+    double dt;
+    const void *state0;
+    const void *delta;
+    const void *torque;
+    int delta_ch;
+    int torque_ch;
+    int ctrl_broadcast;
+    int store_stride;
+    const void *mu;
+    const int *param_set;
+    void *traj;
+    void *aux;
+    void *state_end;
+    void *cost;
+    const void *cost_in;
+    const void *cost_ref;
+    double w_u;
+    double u_ref;
+} B200mpRolloutArgs;
+
+int b200mp_version(void);
+const char *b200mp_last_error(void);
+
+/* Number of CUDA devices, or a negative error. */
+int b200mp_device_count(void);
+
+/* Upload n_sets parameter sets for `device` (synchronous; must not race with rollouts in flight on
+ * that device).  Replaces constructing VehicleParameters (vehicle_model.py:17-61, drive.py:37). */
+int b200mp_set_params(int device, const B200mpVehicleParams *host_sets, int n_sets);
+
+/* Batched RK4 rollouts, one thread per rollout.  vehicle_model.py:427-445 looped as drive.py:141-143. */
+int b200mp_rk4_rollout_f64(int device, void *stream, const B200mpRolloutArgs *args);
+int b200mp_rk4_rollout_f32(int device, void *stream, const B200mpRolloutArgs *args);
+
+/* Batched single right-hand-side evaluation, VehicleModel.planar_model (vehicle_model.py:220-425).
+ *   state [10][B], torque [4][B], mu [4][B] or NULL, delta [4][B], axay [2][B] (ax_prev, ay_prev),
+ *   outputs: state_dot [10][B], misc [6][B] = (vx, vy, ax, ay, axc, ayc), outputs [18][B] (each may be NULL). */
+int b200mp_planar_model_f64(int device, void *stream, int B, const double *state, const double *torque,
+                            const double *mu, const double *delta, const double *axay, const int *param_set,
+                            double *state_dot, double *misc, double *outputs);
+
+/* Sampling-MPC control sequences (BASELINE.json config 4):
+ *   delta[seg][0][r]  = clip(delta_mean + delta_sigma * eps,  +-delta_clip)
+ *   torque[seg][0][r] = torque_mean + torque_sigma * eps'
+ * eps, eps' iid N(0,1) from Philox4x32-10 keyed by seed with counter (rollout0 + r, seg): a shard that
+ * passes its global offset in rollout0 reproduces the unsharded sequences. */
+int b200mp_mpc_sample_controls_f64(int device, void *stream, int B, int n_seg, unsigned long long seed,
+                                   long long rollout0, double delta_mean, double delta_sigma, double delta_clip,
+                                   double torque_mean, double torque_sigma, double *delta, double *torque);
+
+/* argmin over cost[n] with lowest-index tie-break (the convention of collision_checker.py:199); NaN
+ * counts as +inf.  Writes min_out[0] (dev double) and idx_out[0] (dev long long, index_offset added;
+ * -1 when nothing is finite). */
+int b200mp_argmin_f64(int device, void *stream, long long n, const double *cost, long long index_offset,
+                      double *min_out, long long *idx_out);
+
+/* Circle-offset collision test for P paths at once: replaces Pool.starmap(collision_check, ...)
+ * (local_planner.py:369-372) over CollisionChecker.collision_check (collision_checker.py:32-117).
+ *   off, rad   HOST arrays [n_circ] (n_circ <= 8)
+ *   px, py     dev [P][n_pts]
+ *   pcos, psin dev [P][n_pts] cos / sin of path[2][j] computed by the caller on the host (numpy), which is
+ *              what makes the booleans bit-exact; or NULL with pyaw dev [P][yaw_stride] (first n_pts of
+ *              each row used) to evaluate sincos on the device (<= 1-2 ulp from libm)
+ *   obs        dev [M][2]
+ *   free_out   dev [P] bytes, 1 = collision-free (the reference's polarity)
+ *   min_clear  dev [P] min over all tests of (distance - radius), or NULL
+ * Distances follow scipy cdist bit for bit: sqrt(fl(dx*dx) + fl(dy*dy)), no FMA; d == r is free. */
+int b200mp_collision_check_f64(int device, void *stream, int P, int n_pts, int n_circ, const double *off,
+                               const double *rad, const double *px, const double *py, const double *pcos,
+                               const double *psin, const double *pyaw, int yaw_stride, int M, const double *obs,
+                               unsigned char *free_out, double *min_clear);
+
+/* select_best_path_index on the path end points (collision_checker.py:134-203):
+ *   score_i = norm([ex_i-gx, ey_i-gy]) + sum over colliding j (ascending) of weight*norm([ex_i-ex_j, ey_i-ey_j])
+ * colliding i -> +inf; first strict minimum wins; best_out[0] = -1 for the reference's None.
+ * norm_mode picks the closed form of np.linalg.norm the host follows (B200MP_NORM2_*).
+ * scores_out dev [P] or NULL. */
+int b200mp_select_best_f64(int device, void *stream, int P, const double *ex, const double *ey,
+                           const unsigned char *free_in, double gx, double gy, double weight, int norm_mode,
+                           double *scores_out, int *best_out);
+
+/* Measured pipe peak for the roofline denominator: runs a register-resident FMA chain kernel
+ * (dtype_bits 64 or 32) `reps` times, synchronises, and returns the best TFLOP/s (FMA = 2 flop). */
+int b200mp_fma_peak(int device, int dtype_bits, int reps, double *tflops_out);
+
+/* Free library-owned device state (parameter tables, reduction scratch) on every device. */
+int b200mp_shutdown(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MP_H */

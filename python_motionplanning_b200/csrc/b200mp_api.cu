@@ -1,0 +1,253 @@
+// C-ABI entry points of libb200mp.so (declared in include/b200mp.h).
+//
+// Thin, exception-free shims: validate, make the device current, launch on the caller's stream.
+// Ownership: callers own every buffer they pass; the library owns only the per-device parameter
+// table and a reduction scratch area, both released by b200mp_shutdown().
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "b200mp_internal.h"
+
+namespace b200mp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+static DeviceState g_states[kMaxDevices];
+static std::mutex g_mutex;
+
+DeviceState &dev_state(int device) { return g_states[(device >= 0 && device < kMaxDevices) ? device : 0]; }
+
+int ensure_scratch(int device, size_t bytes, void **out)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceState &ds = dev_state(device);
+    if (bytes < 4096) bytes = 4096;
+    if (ds.scratch_bytes < bytes) {
+        if (ds.scratch) {
+            // a larger area is needed: wait for work that may still use the old one
+            B200MP_CUDA(cudaDeviceSynchronize());
+            B200MP_CUDA(cudaFree(ds.scratch));
+            ds.scratch = nullptr;
+            ds.scratch_bytes = 0;
+        }
+        const size_t want = bytes + bytes / 2;
+        B200MP_CUDA(cudaMalloc(&ds.scratch, want));
+        ds.scratch_bytes = want;
+    }
+    *out = ds.scratch;
+    return 0;
+}
+
+DeviceGuard::DeviceGuard(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1) {
+        set_error("no usable CUDA device (%s); libb200mp has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        status_ = B200MP_E_NODEVICE;
+        return;
+    }
+    if (device < 0 || device >= n || device >= kMaxDevices) {
+        set_error("device %d out of range (have %d)", device, n);
+        status_ = B200MP_E_ARG;
+        return;
+    }
+    e = cudaGetDevice(&prev_);
+    if (e != cudaSuccess) prev_ = -1;
+    if (prev_ != device) {
+        e = cudaSetDevice(device);
+        if (e != cudaSuccess) status_ = cuda_fail(e, "cudaSetDevice");
+    }
+}
+
+DeviceGuard::~DeviceGuard()
+{
+    if (status_ == 0 && prev_ >= 0) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != prev_) (void)cudaSetDevice(prev_);
+    }
+}
+
+}  // namespace b200mp
+
+using namespace b200mp;
+
+#define B200MP_ENTER(device)          \
+    g_err[0] = 0;                     \
+    DeviceGuard guard__(device);      \
+    if (guard__.status() != 0) return guard__.status()
+
+extern "C" {
+
+int b200mp_version(void) { return B200MP_VERSION; }
+
+const char *b200mp_last_error(void) { return g_err; }
+
+int b200mp_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return B200MP_E_NODEVICE;
+    }
+    return n;
+}
+
+int b200mp_set_params(int device, const B200mpVehicleParams *host_sets, int n_sets)
+{
+    B200MP_ENTER(device);
+    if (!host_sets || n_sets < 1) {
+        set_error("set_params: need at least one parameter set");
+        return B200MP_E_ARG;
+    }
+    static_assert(sizeof(HostParams) == sizeof(B200mpVehicleParams), "parameter struct layout");
+    DevParams<double> *h64 = new DevParams<double>[n_sets];
+    DevParams<float> *h32 = new DevParams<float>[n_sets];
+    for (int i = 0; i < n_sets; ++i) {
+        HostParams hp;
+        memcpy(&hp, &host_sets[i], sizeof(hp));
+        h64[i] = derive_params<double>(hp);
+        h32[i] = derive_params<float>(hp);
+    }
+    int rc = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        DeviceState &ds = dev_state(device);
+        cudaError_t e = cudaDeviceSynchronize();   // rollouts in flight may still read the old table
+        if (e == cudaSuccess && ds.table64) e = cudaFree(ds.table64);
+        if (e == cudaSuccess && ds.table32) e = cudaFree(ds.table32);
+        ds.table64 = nullptr;
+        ds.table32 = nullptr;
+        ds.n_sets = 0;
+        if (e == cudaSuccess) e = cudaMalloc((void **)&ds.table64, sizeof(DevParams<double>) * n_sets);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&ds.table32, sizeof(DevParams<float>) * n_sets);
+        if (e == cudaSuccess) e = cudaMemcpy(ds.table64, h64, sizeof(DevParams<double>) * n_sets, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(ds.table32, h32, sizeof(DevParams<float>) * n_sets, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            memcpy(&ds.set0, &host_sets[0], sizeof(HostParams));
+            ds.n_sets = n_sets;
+        } else {
+            rc = cuda_fail(e, "set_params");
+        }
+    }
+    delete[] h64;
+    delete[] h32;
+    return rc;
+}
+
+int b200mp_rk4_rollout_f64(int device, void *stream, const B200mpRolloutArgs *args)
+{
+    B200MP_ENTER(device);
+    if (!args) {
+        set_error("rk4_rollout: args is NULL");
+        return B200MP_E_ARG;
+    }
+    return launch_rollout_f64(device, (cudaStream_t)stream, *args);
+}
+
+int b200mp_rk4_rollout_f32(int device, void *stream, const B200mpRolloutArgs *args)
+{
+    B200MP_ENTER(device);
+    if (!args) {
+        set_error("rk4_rollout: args is NULL");
+        return B200MP_E_ARG;
+    }
+    return launch_rollout_f32(device, (cudaStream_t)stream, *args);
+}
+
+int b200mp_planar_model_f64(int device, void *stream, int B, const double *state, const double *torque,
+                            const double *mu, const double *delta, const double *axay, const int *param_set,
+                            double *state_dot, double *misc, double *outputs)
+{
+    B200MP_ENTER(device);
+    return launch_planar_model_f64(device, (cudaStream_t)stream, B, state, torque, mu, delta, axay, param_set, state_dot,
+                                   misc, outputs);
+}
+
+int b200mp_mpc_sample_controls_f64(int device, void *stream, int B, int n_seg, unsigned long long seed,
+                                   long long rollout0, double delta_mean, double delta_sigma, double delta_clip,
+                                   double torque_mean, double torque_sigma, double *delta, double *torque)
+{
+    B200MP_ENTER(device);
+    return launch_mpc_sample_f64((cudaStream_t)stream, B, n_seg, seed, rollout0, delta_mean, delta_sigma, delta_clip,
+                                 torque_mean, torque_sigma, delta, torque);
+}
+
+int b200mp_argmin_f64(int device, void *stream, long long n, const double *cost, long long index_offset,
+                      double *min_out, long long *idx_out)
+{
+    B200MP_ENTER(device);
+    return launch_argmin_f64(device, (cudaStream_t)stream, n, cost, index_offset, min_out, idx_out);
+}
+
+int b200mp_collision_check_f64(int device, void *stream, int P, int n_pts, int n_circ, const double *off,
+                               const double *rad, const double *px, const double *py, const double *pcos,
+                               const double *psin, const double *pyaw, int yaw_stride, int M, const double *obs,
+                               unsigned char *free_out, double *min_clear)
+{
+    B200MP_ENTER(device);
+    return launch_collision_f64(device, (cudaStream_t)stream, P, n_pts, n_circ, off, rad, px, py, pcos, psin, pyaw,
+                                yaw_stride, M, obs, free_out, min_clear);
+}
+
+int b200mp_select_best_f64(int device, void *stream, int P, const double *ex, const double *ey,
+                           const unsigned char *free_in, double gx, double gy, double weight, int norm_mode,
+                           double *scores_out, int *best_out)
+{
+    B200MP_ENTER(device);
+    return launch_select_best_f64(device, (cudaStream_t)stream, P, ex, ey, free_in, gx, gy, weight, norm_mode, scores_out,
+                                  best_out);
+}
+
+int b200mp_fma_peak(int device, int dtype_bits, int reps, double *tflops_out)
+{
+    B200MP_ENTER(device);
+    return run_fma_peak(dtype_bits, reps, tflops_out);
+}
+
+int b200mp_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    int prev = -1;
+    (void)cudaGetDevice(&prev);
+    for (int d = 0; d < n && d < kMaxDevices; ++d) {
+        DeviceState &ds = g_states[d];
+        if (!ds.table64 && !ds.table32 && !ds.scratch) continue;
+        if (cudaSetDevice(d) != cudaSuccess) continue;
+        (void)cudaDeviceSynchronize();
+        if (ds.table64) (void)cudaFree(ds.table64);
+        if (ds.table32) (void)cudaFree(ds.table32);
+        if (ds.scratch) (void)cudaFree(ds.scratch);
+        ds = DeviceState{};
+    }
+    if (prev >= 0) (void)cudaSetDevice(prev);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Internal glue shared by the translation units of libb200mp.so (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "../../include/b200mp.h"
+#include "vehicle_rhs.cuh"
+
+namespace b200mp {
+
+constexpr int kMaxDevices = 64;
+
+// printf-style message for b200mp_last_error() (thread-local)
+void set_error(const char *fmt, ...);
+// records the CUDA error text and returns it as the ABI return code
+int cuda_fail(cudaError_t e, const char *what);
+
+#define B200MP_CUDA(call)                                         \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return ::b200mp::cuda_fail(e__, #call); \
+    } while (0)
+
+// Library-owned per-device state: the uploaded parameter table and reduction scratch.
+struct DeviceState {
+    int n_sets = 0;
+    HostParams set0{};
+    DevParams<double> *table64 = nullptr;
+    DevParams<float> *table32 = nullptr;
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+DeviceState &dev_state(int device);
+int ensure_scratch(int device, size_t bytes, void **out);
+
+// Sets `device` current for the scope of an ABI call and restores the caller's device afterwards.
+class DeviceGuard {
+  public:
+    explicit DeviceGuard(int device);
+    ~DeviceGuard();
+    int status() const { return status_; }
+
+  private:
+    int prev_ = -1;
+    int status_ = 0;
+};
+
+// kernel launchers (defined next to their kernels)
+int launch_rollout_f64(int device, cudaStream_t st, const B200mpRolloutArgs &a);
+int launch_rollout_f32(int device, cudaStream_t st, const B200mpRolloutArgs &a);
+int launch_planar_model_f64(int device, cudaStream_t st, int B, const double *state, const double *torque,
+                            const double *mu, const double *delta, const double *axay, const int *param_set,
+                            double *state_dot, double *misc, double *outputs);
+int launch_collision_f64(int device, cudaStream_t st, int P, int n_pts, int n_circ, const double *off,
+                         const double *rad, const double *px, const double *py, const double *pcos,
+                         const double *psin, const double *pyaw, int yaw_stride, int M, const double *obs,
+                         unsigned char *free_out, double *min_clear);
+int launch_select_best_f64(int device, cudaStream_t st, int P, const double *ex, const double *ey,
+                           const unsigned char *free_in, double gx, double gy, double weight, int norm_mode,
+                           double *scores_out, int *best_out);
+int launch_argmin_f64(int device, cudaStream_t st, long long n, const double *cost, long long index_offset,
+                      double *min_out, long long *idx_out);
+// two-phase argmin (lowest index wins ties, NaN = +inf); scratch must hold argmin_scratch_bytes(n)
+size_t argmin_scratch_bytes(long long n);
+int argmin_launch(cudaStream_t st, long long n, const double *cost, long long index_offset, void *scratch,
+                  double *min_out, long long *idx_out, int *idx32_out);
+int launch_mpc_sample_f64(cudaStream_t st, int B, int n_seg, unsigned long long seed, long long rollout0,
+                          double delta_mean, double delta_sigma, double delta_clip, double torque_mean,
+                          double torque_sigma, double *delta, double *torque);
+int run_fma_peak(int dtype_bits, int reps, double *tflops_out);
+
+}  // namespace b200mp

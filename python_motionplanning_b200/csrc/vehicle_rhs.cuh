@@ -1,0 +1,230 @@
+// 7-DoF planar vehicle model: right-hand side and classic RK4 step, one rollout per thread.
+//
+// Computes what the reference's VehicleModel.planar_model (libs/vehicle_model/vehicle_model.py:220-425)
+// and VehicleModel.planar_model_RK4 (:427-445) compute, re-derived for a register-resident thread
+// program rather than transcribed:
+//   * parameter-only sub-expressions (static loads, load-transfer gains, 1/m, 1/Izz, 1/Jw, T/2) are
+//     folded on the host into DevParams, which reaches the kernel as a by-value argument (constant
+//     bank operands, no registers);
+//   * sin/cos of the steer angles are hoisted out of the four stages (controls are frozen across a
+//     step, :429-436) and out of every step of a zero-order-hold segment (drive.py:128);
+//   * normal loads depend only on ax_prev, ay_prev and are formed once per step (:255-258);
+//   * each wheel needs one reciprocal (1/vx serves both slips, :284-293) and one reciprocal square
+//     root (sqrt(q) = q*rsqrt(q) and mu/s = mu*rsqrt(q), :296-348);
+//   * x and y never feed back into the right-hand side, so stage states carry 8 components;
+//   * RK4 is kept in running-sum form (acc += w_s * K_s) so only y, acc, ys and one K are live.
+// Quirks of the reference that are reproduced on purpose: mu_max replaces Pacejka D;
+// rear wheel-spin uses the chassis-frame force; lateral slip divides by |vx|; zero combined slip gives
+// zero friction; yaw is never wrapped; ax_prev/ay_prev are the RK4-averaged axc/ayc of the previous step.
+#pragma once
+
+#include "b200mp_math.cuh"
+
+namespace b200mp {
+
+constexpr double kGravity = 9.81;  // vehicle_model.py:230
+
+// Device-ready parameter set (derived on the host in double, reference operator order).
+template <typename R> struct DevParams {
+    R inv_m, inv_Izz, inv_Jw, a, b, halfT, rw;
+    R Fz0F, Fz0R, DfzxL, DfzxR, DfzyF, DfzyR;
+    R Bc[4], Cc[4], Dc[4];
+};
+
+// Plain-double mirror of B200mpVehicleParams (kept layout-identical; see b200mp.h)
+struct HostParams {
+    double m, a, b, Izz, Jw, hg, T, wL, wR, rw;
+    double B[4], C[4], D[4];
+};
+
+template <typename R> inline DevParams<R> derive_params(const HostParams &p)
+{
+    const double g = kGravity;
+    DevParams<R> d;
+    d.inv_m = (R)(1 / p.m);
+    d.inv_Izz = (R)(1 / p.Izz);
+    d.inv_Jw = (R)(1 / p.Jw);
+    d.a = (R)p.a;
+    d.b = (R)p.b;
+    d.halfT = (R)(p.T / 2);
+    d.rw = (R)p.rw;
+    d.Fz0F = (R)(p.b / (p.a + p.b) * p.m * g / 2);                      // :245-248
+    d.Fz0R = (R)(p.a / (p.a + p.b) * p.m * g / 2);
+    d.DfzxL = (R)(p.m * p.hg * p.wR / ((p.a + p.b) * (p.wL + p.wR)));   // :250-253
+    d.DfzxR = (R)(p.m * p.hg * p.wL / ((p.a + p.b) * (p.wL + p.wR)));
+    d.DfzyF = (R)(p.m * p.hg * p.b / ((p.a + p.b) * (p.wL + p.wR)));
+    d.DfzyR = (R)(p.m * p.hg * p.a / ((p.a + p.b) * (p.wL + p.wR)));
+    for (int i = 0; i < 4; ++i) {
+        d.Bc[i] = (R)p.B[i];
+        d.Cc[i] = (R)p.C[i];
+        d.Dc[i] = (R)p.D[i];
+    }
+    return d;
+}
+
+// Controls of one zero-order-hold segment, with the steer trigonometry already evaluated.
+template <typename R> struct WheelCtrl {
+    R cd[4], sd[4], tq[4];
+};
+
+template <typename R, bool REAR0>
+B200MP_HD void set_steer(WheelCtrl<R> &c, const R delta[4])
+{
+    Math<R>::sincos(delta[0], &c.sd[0], &c.cd[0]);
+    if (REAR0) {
+        // front-steer layout: FL = FR, rear wheels straight (drive.py:143)
+        c.sd[1] = c.sd[0];
+        c.cd[1] = c.cd[0];
+        c.sd[2] = c.sd[3] = (R)0;
+        c.cd[2] = c.cd[3] = (R)1;
+    } else {
+        for (int i = 1; i < 4; ++i) Math<R>::sincos(delta[i], &c.sd[i], &c.cd[i]);
+    }
+}
+
+template <typename R>
+B200MP_HD void normal_loads(const DevParams<R> &P, R ax_prev, R ay_prev, R Fz[4])
+{
+    Fz[0] = P.Fz0F - P.DfzxL * ax_prev - P.DfzyF * ay_prev;   // :255-258
+    Fz[1] = P.Fz0F - P.DfzxR * ax_prev + P.DfzyF * ay_prev;
+    Fz[2] = P.Fz0R + P.DfzxL * ax_prev - P.DfzyR * ay_prev;
+    Fz[3] = P.Fz0R + P.DfzxR * ax_prev + P.DfzyR * ay_prev;
+}
+
+// Tyre of wheel I: slips -> combined-slip Pacejka friction -> forces in the chassis frame.
+template <typename R, int I, bool REAR0>
+B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd, R sd, R Fz,
+                            R &fx, R &fy, R &fxt, R &fyt, R &s)
+{
+    typedef Math<R> M;
+    R vx, vy;
+    if (REAR0 && I >= 2) {
+        vx = vxc;
+        vy = vyc;
+    } else {
+        vx = vxc * cd + vyc * sd;        // :274-281
+        vy = vyc * cd - vxc * sd;
+    }
+    const R r = M::rcp(vx);
+    const R sx = (P.rw * w) * r - (R)1;  // :284-287
+    const R sy = -vy * M::abs(r);        // :290-293
+    const R q = sx * sx + sy * sy;       // :296-299
+    const R rs = M::rsqrt(q);
+    s = q * rs;
+    const R mu = D * M::sin(P.Cc[I] * M::atan(P.Bc[I] * s));   // :303-306
+    const R g = (q != (R)0) ? mu * rs : (R)0;                  // :309-348 (zero slip -> zero friction)
+    fxt = (sx * g) * Fz;                 // :351-360
+    fyt = (sy * g) * Fz;
+    if (REAR0 && I >= 2) {
+        fx = fxt;
+        fy = fyt;
+    } else {
+        fx = fxt * cd - fyt * sd;        // :363-373
+        fy = fxt * sd + fyt * cd;
+    }
+}
+
+// y8 = [U V wz wFL wFR wRL wRR yaw].  k[10] receives the derivative of the full 10-state
+// (k[7] = wz, k[8] = x_dot, k[9] = y_dot).  out (AUX only) = the reference's 18 "outputs".
+template <typename R, bool REAR0, bool AUX>
+B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], const WheelCtrl<R> &c,
+                          const R Fz[4], R k[10], R &axc, R &ayc, R *out)
+{
+    typedef Math<R> M;
+    const R U = y8[0], V = y8[1], wz = y8[2];
+    const R hw = P.halfT * wz;                       // :261-271
+    const R vxL = U - hw, vxR = U + hw;
+    const R vyF = V + P.a * wz, vyR = V - P.b * wz;
+    R fx[4], fy[4], fxt[4], fyt[4], s[4];
+    wheel_forces<R, 0, REAR0>(P, D[0], vxL, vyF, y8[3], c.cd[0], c.sd[0], Fz[0], fx[0], fy[0], fxt[0], fyt[0], s[0]);
+    wheel_forces<R, 1, REAR0>(P, D[1], vxR, vyF, y8[4], c.cd[1], c.sd[1], Fz[1], fx[1], fy[1], fxt[1], fyt[1], s[1]);
+    wheel_forces<R, 2, REAR0>(P, D[2], vxL, vyR, y8[5], c.cd[2], c.sd[2], Fz[2], fx[2], fy[2], fxt[2], fyt[2], s[2]);
+    wheel_forces<R, 3, REAR0>(P, D[3], vxR, vyR, y8[6], c.cd[3], c.sd[3], Fz[3], fx[3], fy[3], fxt[3], fyt[3], s[3]);
+
+    const R Vwz = V * wz, Uwz = U * wz;
+    const R U_dot = P.inv_m * (fx[0] + fx[1] + fx[2] + fx[3]) + Vwz;     // :376-378
+    const R V_dot = P.inv_m * (fy[0] + fy[1] + fy[2] + fy[3]) - Uwz;
+    k[0] = U_dot;
+    k[1] = V_dot;
+    k[2] = P.inv_Izz * (P.a * (fy[0] + fy[1]) - P.b * (fy[2] + fy[3]) + P.halfT * (fx[1] - fx[0] + fx[3] - fx[2]));
+    k[3] = (c.tq[0] - P.rw * fxt[0]) * P.inv_Jw;                          // :379-382
+    k[4] = (c.tq[1] - P.rw * fxt[1]) * P.inv_Jw;
+    k[5] = (c.tq[2] - P.rw * fx[2]) * P.inv_Jw;   // chassis-frame force on the rear axle, as the reference
+    k[6] = (c.tq[3] - P.rw * fx[3]) * P.inv_Jw;
+    k[7] = wz;                                                            // :383-385
+    R sy, cy;
+    M::sincos(y8[7], &sy, &cy);
+    k[8] = U * cy - V * sy;
+    k[9] = U * sy + V * cy;
+    axc = U_dot - Vwz;                                                    // :413-414
+    ayc = V_dot + Uwz;
+    if (AUX) {
+        for (int i = 0; i < 4; ++i) {                                     // :420-423
+            out[i] = fx[i];
+            out[4 + i] = fy[i];
+            out[8 + i] = Fz[i];
+            out[12 + i] = s[i];
+        }
+        out[16] = fxt[0];
+        out[17] = fyt[0];
+    }
+}
+
+// One classic RK4 step (:427-445).  y[10] is advanced in place; ax, ay hold ax_prev, ay_prev on entry
+// and the RK4-averaged axc, ayc on exit (the next step's ax_prev, ay_prev, drive.py:141).
+// With AUX, sdot[10] and outs[18] receive the RK4-weighted means the reference returns (:440-441).
+template <typename R, bool REAR0, bool AUX>
+B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> &c, R h, R y[10], R &ax, R &ay,
+                        R *sdot, R *outs)
+{
+    R Fz[4];
+    normal_loads(P, ax, ay, Fz);
+    R acc[10], ys[8], k[10], o[AUX ? 18 : 1], axc, ayc, sax, say;
+    const R h2 = h * (R)0.5;
+
+    planar_rhs<R, REAR0, AUX>(P, D, y, c, Fz, k, axc, ayc, o);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] = k[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ys[i] = y[i] + h2 * k[i];
+    sax = axc;
+    say = ayc;
+    if (AUX)
+        for (int i = 0; i < 18; ++i) outs[i] = o[i];
+
+    planar_rhs<R, REAR0, AUX>(P, D, ys, c, Fz, k, axc, ayc, o);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] += (R)2 * k[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ys[i] = y[i] + h2 * k[i];
+    sax += (R)2 * axc;
+    say += (R)2 * ayc;
+    if (AUX)
+        for (int i = 0; i < 18; ++i) outs[i] += (R)2 * o[i];
+
+    planar_rhs<R, REAR0, AUX>(P, D, ys, c, Fz, k, axc, ayc, o);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] += (R)2 * k[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ys[i] = y[i] + h * k[i];
+    sax += (R)2 * axc;
+    say += (R)2 * ayc;
+    if (AUX)
+        for (int i = 0; i < 18; ++i) outs[i] += (R)2 * o[i];
+
+    planar_rhs<R, REAR0, AUX>(P, D, ys, c, Fz, k, axc, ayc, o);
+    const R h6 = (R)(1.0 / 6) * h;       // :438  state + 1/6*h*(K1+2K2+2K3+K4)
+    const R sixth = (R)(1.0 / 6);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const R sum = acc[i] + k[i];
+        y[i] = y[i] + h6 * sum;
+        if (AUX) sdot[i] = sum * sixth;
+    }
+    ax = (sax + axc) * sixth;            // :442-443
+    ay = (say + ayc) * sixth;
+    if (AUX)
+        for (int i = 0; i < 18; ++i) outs[i] = (outs[i] + o[i]) * sixth;
+}
+
+}  // namespace b200mp
