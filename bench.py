@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- 7-DoF RK4 rollout-steps/s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one batch: BASELINE.json config 2 on every GPU -- 65,536
+open-loop rollouts x 500 RK4 steps, FP64, the full trajectory (2.62 GB) written to HBM.  Rollouts are
+independent, so N GPUs run N such batches with no data-path collective (weak scaling).
+
+One JSON line is printed by rank 0.  ``value`` is timed with CUDA events around each step with the inputs
+resident in HBM; ``e2e`` goes through the public host-buffer API (H2D of the inputs, time-chunked kernels,
+D2H of the whole trajectory, overlapped) and is the number to hold against the CPU reference arm.
+``--impl reference`` times the CPU port of the reference's path (the plain-C oracle, all host threads) on a
+bounded sample of the same workload.  The reference itself is pure Python and cannot travel to the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "7-DoF RK4 rollout-steps/sec"
+UNIT = "rollout-steps/s"
+B, N_STEPS, HOLD, DT = 65536, 500, 10, 1e-4
+ALG_FLOP_PER_STEP = 854          # 806 add/mul/div/sqrt flops + 48 transcendental values
+ALG_BYTES_PER_STEP = 80          # 10 states x 8 B written per rollout-step
+ALG_FLOP_PER_TEST = 8            # one circle-vs-point test
+WORKLOAD = f"config2: {B} rollouts x {N_STEPS} steps, FP64, dt=1e-4, ZOH-{HOLD} controls, full trajectory stored"
+
+
+def _host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------- CPU reference
+def cpu_port_run(threads: int, rollouts_per_thread: int = 2048, repeats: int = 1):
+    """Time the plain-C port of the reference's RK4 path on `threads` host threads (bounded sample)."""
+    import numpy as np
+
+    from oracle import c_oracle, planar_numpy
+    from python_motionplanning_b200 import workloads as wl
+    nb = min(B, threads * rollouts_per_thread)
+    s0, d, t = wl.config2_rollouts(B=B, n_steps=N_STEPS)
+    s0, d, t = (np.ascontiguousarray(a[..., :nb]) for a in (s0, d, t))
+    par = c_oracle.make_params(planar_numpy.VehicleParams())
+    par[0].D[:] = (1.0,) * 4
+    c_oracle.rollout(s0[:, :64], d[:, :, :64], t[:, :, :64], par, DT, 50, hold=HOLD, nthreads=threads)   # warm
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        c_oracle.rollout(s0, d, t, par, DT, N_STEPS, hold=HOLD, store_stride=1, nthreads=threads)
+        times.append(time.perf_counter() - t0)
+    sample = f"first {nb} rollouts of config 2 x {N_STEPS} steps, full trajectory, {threads} OpenMP threads"
+    return nb * N_STEPS, times, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = _host_threads()
+    for _ in range(args.warmup):
+        cpu_port_run(threads, rollouts_per_thread=256)
+    units, times, sample = cpu_port_run(threads, repeats=args.steps)
+    total = sum(times)
+    value = units * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "note": "plain-C restatement of vehicle_model.py:220-445 (oracle/csrc/oracle.c); the reference "
+                                 "is pure Python (~2e3 steps/s/core, tests/golden/rollout_cfg2_sub.npz) and cannot "
+                                 "travel to the GPU box"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.tmp = None
+
+    def start(self):
+        try:
+            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = []
+        with open(self.tmp.name) as f:
+            for ln in f:
+                parts = [p.strip() for p in ln.split(",")]
+                if len(parts) >= 7:
+                    try:
+                        rows.append((float(parts[0]), float(parts[1]), float(parts[2]), parts[3:7]))
+                    except ValueError:
+                        pass
+        os.unlink(self.tmp.name)
+        if not rows:
+            return out
+        loaded = [r for r in rows if r[2] > 0.5 * max(x[2] for x in rows)] or rows
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[3][i].lower().startswith("active")})
+        out.update(sm_mhz=statistics.median(r[0] for r in loaded), sm_max_mhz=max(r[1] for r in rows), reasons=reasons,
+                   samples=len(rows), power_w_max=max(r[2] for r in rows))
+        return out
+
+
+# ---------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import python_motionplanning_b200 as mp
+    from python_motionplanning_b200 import workloads as wl
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = mp.Engine(local_rank)
+    dev = eng.tdev
+    p = mp.VehicleParameters()
+    p.DFL = p.DFR = p.DRL = p.DRR = 1.0          # mu_max = [1, 1, 1, 1] (drive.py:142) folded into the set
+    eng.set_params(p)
+
+    # each rank gets its own seeded batch (weak scaling; same distribution)
+    s0_h, d_h, t_h = wl.config2_rollouts(B=B, n_steps=N_STEPS, seed=wl.SEED + rank)
+    s0, dl, tq = eng.dev(s0_h), eng.dev(d_h), eng.dev(t_h)
+    traj = eng.empty(N_STEPS, 10, B)
+    end = eng.empty(12, B)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
+
+    def step():
+        eng.rollout(s0, dl, tq, DT, N_STEPS, hold=HOLD, store_stride=1, traj_out=traj, state_out=end)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    def timed_region():
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        t0 = time.perf_counter()
+        for e0, e1 in evs:
+            flush.fill_(1)                      # evict L2 between timed iterations (untimed)
+            e0.record()
+            step()
+            e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+        return ms, wall, clocks
+
+    ms, wall, clocks = timed_region()
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    remeasured = False
+    if bad & set(clocks["reasons"]):
+        remeasured = True
+        ms, wall, clocks = timed_region()
+    dev_ms = sum(ms)
+    t_all = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    max_ms = float(t_all.item())
+    units_per_step = B * N_STEPS
+    value = world * units_per_step * args.steps / (max_ms * 1e-3)
+
+    # ---- end to end through the public host-buffer API (pinned host <-> device copies inside the timed region)
+    hs, hd, ht = (torch.from_numpy(a).pin_memory() for a in (s0_h, d_h, t_h))
+    traj_host = torch.empty(N_STEPS, 10, B, dtype=torch.float64).pin_memory()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        eng.rollout_to_host(hs, hd, ht, DT, N_STEPS, HOLD, traj_host, chunk_steps=50)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.rollout_to_host(hs, hd, ht, DT, N_STEPS, HOLD, traj_host, chunk_steps=50)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * units_per_step * e2e_steps / float(t_e.item())
+    h2d = int(hs.numel() + hd.numel() + ht.numel()) * 8
+    d2h = int(traj_host.numel()) * 8
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (rk4_rollout_kernel<double,...>), measured live on this GPU
+        peak64 = eng.fma_peak(64, reps=5)
+        kernel_ms = statistics.mean(ms)
+        steps_per_s_gpu = units_per_step / (kernel_ms * 1e-3)
+        achieved_tf = steps_per_s_gpu * ALG_FLOP_PER_STEP * 1e-12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        prof = {}
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_inputs.json")))
+            traffic = prof.get("rk4_rollout_f64_dram_bytes_per_launch")
+        except Exception:
+            pass
+        roofline = {
+            "bound": "fp64", "kernel": "rk4_rollout_kernel<double,front-steer>", "achieved": achieved_tf, "peak": peak64,
+            "unit": "TFLOP/s", "frac": achieved_tf / peak64 if peak64 else None, "traffic": traffic,
+            "peak_source": "measured live: register-resident DFMA chains (b200mp_fma_peak), FMA = 2 flop; "
+                           "MEASURED_PEAKS.json has no FP64 entry",
+            "algorithmic_flop_per_step": ALG_FLOP_PER_STEP, "kernel_ms": kernel_ms,
+            "fp64_pipe_util_ncu": prof.get("rk4_rollout_f64_fp64_pipe_pct"),
+            "hbm": {"achieved": steps_per_s_gpu * ALG_BYTES_PER_STEP * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": steps_per_s_gpu * ALG_BYTES_PER_STEP * 1e-9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
+        }
+        cpu_baseline = None
+        if world == 1:
+            threads = _host_threads()
+            units, times, sample = cpu_port_run(threads)
+            cpu_baseline = {"value": units / times[0], "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        extras = secondary_metrics(eng, wl, np, torch) if world == 1 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "n_steps": N_STEPS, "parallelism": f"dp{world} (independent rollouts, no data-path collective)",
+                       "l2": "256 MiB buffer written between timed iterations (untimed); each step also streams 2.62 GB of output through the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "Engine.rollout_to_host: pinned host inputs -> H2D, 10 time-chunks of 50 steps, D2H of the full trajectory overlapped on a copy stream"},
+            "gpu_launches": args.steps * world,
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                       "samples": clocks["samples"], "power_w_max": clocks.get("power_w_max"), "remeasured": remeasured},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_s_timed_region": wall,
+        }
+        if extras:
+            line["secondary"] = extras
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def secondary_metrics(eng, wl, np, torch):
+    """The metric's second half (lattice collision checks/s, config 3) and the other configs, N = 1 only."""
+    out = {}
+    w = wl.config3_lattice()
+    P, n = w["px"].shape
+    M = len(w["obstacles"])
+    tests = P * n * 3 * M
+    px, py = eng.dev(w["px"]), eng.dev(w["py"])
+    obs = eng.dev(w["obstacles"])
+
+    def run(clear):
+        return eng.collision_check_batch(px, py, w["pyaw"], obs, w["offsets"], w["radii"], want_clearance=clear)
+
+    for name, clear in (("collision_flags", False), ("collision_min_clearance", True)):
+        for _ in range(3):
+            run(clear)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            r = run(clear)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        free = r[0] if clear else r
+        sec = statistics.median(ts)
+        out[name] = {"metric": "lattice collision checks/sec", "value": tests / sec, "unit": "circle-point tests/s (nominal P*49*3*M)",
+                     "ms": sec * 1e3, "paths_per_s": P / sec, "free_fraction": float(free.float().mean().item()),
+                     "includes": "host numpy cos/sin of 200k yaws + H2D of them + kernel(s) + sync",
+                     "algorithmic_tflops": tests * ALG_FLOP_PER_TEST / sec * 1e-12}
+    t0 = time.perf_counter()
+    best = eng.select_best_path_index_batch(px[:, -1].contiguous(), py[:, -1].contiguous(), free, w["goal"], w["weight"])
+    out["select_best"] = {"P": P, "ms": (time.perf_counter() - t0) * 1e3, "best_index": best}
+    # FP32 twin of the headline kernel on the same batch
+    s0_h, d_h, t_h = wl.config2_rollouts(B=B, n_steps=N_STEPS)
+    s32, d32, t32 = (eng.dev(a, torch.float32) for a in (s0_h, d_h, t_h))
+    tr32 = eng.empty(N_STEPS, 10, B, dtype=torch.float32)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for k in range(4):
+        if k == 3:
+            ev0.record()
+        eng.rollout(s32, d32, t32, DT, N_STEPS, hold=HOLD, store_stride=1, dtype="f32", traj_out=tr32)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms32 = ev0.elapsed_time(ev1)
+    peak32 = eng.fma_peak(32, reps=3)
+    out["rollout_f32"] = {"value": B * N_STEPS / (ms32 * 1e-3), "unit": UNIT, "ms": ms32, "fp32_peak_tflops": peak32,
+                          "frac_of_fp32_peak": B * N_STEPS / (ms32 * 1e-3) * ALG_FLOP_PER_STEP * 1e-12 / peak32}
+    del tr32
+    # end-state-only FP64 (no trajectory writeback): separates compute from writeback
+    s0, dl, tq = eng.dev(s0_h), eng.dev(d_h), eng.dev(t_h)
+    for k in range(4):
+        if k == 3:
+            ev0.record()
+        eng.rollout(s0, dl, tq, DT, N_STEPS, hold=HOLD, store_stride=0)
+    ev1.record()
+    torch.cuda.synchronize()
+    out["rollout_f64_endstate_only"] = {"value": B * N_STEPS / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT,
+                                        "ms": ev0.elapsed_time(ev1)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.steps < 1:
+        raise SystemExit("--steps must be >= 1")
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

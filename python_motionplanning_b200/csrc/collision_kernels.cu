@@ -143,11 +143,11 @@ int launch_collision_f64(int device, cudaStream_t st, int P, int n_pts, int n_ci
         set_error("collision_check: bad sizes P=%d n_pts=%d n_circ=%d (1..%d) M=%d", P, n_pts, n_circ, kMaxCircles, M);
         return B200MP_E_ARG;
     }
+    if (P == 0) return 0;
     if (!off || !rad || !free_out) {
         set_error("collision_check: off, rad and free_out must be non-NULL");
         return B200MP_E_ARG;
     }
-    if (P == 0) return 0;
     // every path starts collision-free (empty path or empty obstacle list -> True, as the reference)
     B200MP_CUDA(cudaMemsetAsync(free_out, 1, (size_t)P, st));
     if (n_pts == 0 || M == 0) {

@@ -1,0 +1,134 @@
+"""Multi-GPU glue: one process per GPU (``torchrun``), ``torch.distributed`` with NCCL over NVLink.
+
+The hot path shards trivially -- rollouts are independent (no cross-vehicle term anywhere in
+vehicle_model.py:220-445) and ``collision_check`` touches one path (collision_checker.py:63) -- so each
+rank takes a contiguous block and the data path needs no collective.  The only exchanges are the two
+tiny ones BASELINE.json names: gather the per-rank winners (16 B per rank) or the per-path flags, and
+broadcast the chosen control sequence / path from its owner.  They are latency-bound, so they are
+issued with NCCL right after the local kernels rather than fused into them.
+
+The communication helpers work on whatever device the tensors live on, which is how the world_size-2
+``gloo`` tests exercise them on CPU; the compute they combine always comes from the CUDA engine.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block ``[lo, hi)`` of ``n`` items for ``rank``; sizes differ by at most one."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sets(n_sets: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Config-5 style sharding: whole tyre sets per rank (each set stays on one GPU)."""
+    return shard_range(n_sets, rank, world_size)
+
+
+def global_argmin(local_min: torch.Tensor, local_idx: torch.Tensor, group=None) -> Tuple[float, int, int]:
+    """Combine per-rank ``(min cost, GLOBAL index)`` pairs into the global winner.
+
+    All-gathers one (f64, i64) pair per rank and takes the replicated lowest-index argmin -- the tie
+    convention of collision_checker.py:199.  ``local_idx < 0`` means the rank had nothing finite.
+    Returns ``(cost, global_index, owner_rank)``; ``(inf, -1, -1)`` when no rank had a finite cost.
+    """
+    rank, ws = world()
+    pair = torch.stack([local_min.reshape(1).to(torch.float64),
+                        local_idx.reshape(1).to(torch.float64)]).reshape(2)   # idx < 2^53: exact in f64
+    if ws == 1:
+        allp = pair.reshape(1, 2)
+    else:
+        buf = [torch.empty_like(pair) for _ in range(ws)]
+        dist.all_gather(buf, pair, group=group)
+        allp = torch.stack(buf)
+    allp = allp.cpu()
+    best_cost, best_idx, owner = float("inf"), -1, -1
+    for r in range(allp.shape[0]):
+        c, i = float(allp[r, 0]), int(allp[r, 1])
+        if i < 0 or c != c:
+            continue
+        if c < best_cost or (c == best_cost and i < best_idx):
+            best_cost, best_idx, owner = c, i, r
+    return best_cost, best_idx, owner
+
+
+def broadcast_from(t: torch.Tensor, owner: int, group=None) -> torch.Tensor:
+    """Broadcast ``t`` (same shape on every rank) from ``owner``; in place."""
+    _, ws = world()
+    if ws > 1 and owner >= 0:
+        dist.broadcast(t, src=owner, group=group)
+    return t
+
+
+def gather_flags(local_flags: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gather per-path flags of contiguous shards into one ``[n_total]`` uint8 tensor."""
+    rank, ws = world()
+    if ws == 1:
+        return local_flags
+    sizes = [shard_range(n_total, r, ws) for r in range(ws)]
+    width = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros(width, dtype=local_flags.dtype, device=local_flags.device)
+    pad[: local_flags.numel()] = local_flags
+    buf = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(buf, pad, group=group)
+    return torch.cat([buf[r][: hi - lo] for r, (lo, hi) in enumerate(sizes)])
+
+
+def mpc_plan(engine, cfg: dict, n_total: Optional[int] = None, hold: int = 1, dt: float = 1e-4, group=None):
+    """Sampling-MPC step of BASELINE.json config 4, sharded over the ranks of the process group.
+
+    Each rank draws the control sequences of its block (Philox keyed by GLOBAL rollout index, so the result
+    is independent of the number of ranks), rolls them out from the shared start state with the running
+    cost, takes its local argmin, then: all-gather of the (cost, index) pairs, replicated lowest-index
+    argmin, broadcast of the winner's control sequence from the owning rank.
+    Returns ``dict(cost, index, owner, delta[n_seg], torque[n_seg], local_cost[B_local])``.
+    """
+    rank, ws = world()
+    Btot = int(n_total if n_total is not None else cfg["B"])
+    lo, hi = shard_range(Btot, rank, ws)
+    Bl = hi - lo
+    n_steps = int(cfg["n_steps"])
+    n_seg = -(-n_steps // hold)
+    delta, torque = engine.mpc_sample_controls(Bl, n_seg, cfg["seed"], rollout0=lo, delta_mean=cfg["delta_mean"],
+                                               delta_sigma=cfg["delta_sigma"], delta_clip=cfg["delta_clip"],
+                                               torque_mean=cfg["torque_mean"], torque_sigma=cfg["torque_sigma"])
+    s0 = engine.dev(cfg["state0"]).reshape(12, 1).expand(12, Bl).contiguous()
+    res = engine.rollout(s0, delta, torque, dt, n_steps, hold=hold, cost_ref=cfg["cost_ref"], w_u=cfg["w_u"],
+                         u_ref=cfg["u_ref"])
+    mn, ix = engine.argmin(res.cost, index_offset=lo)
+    cost, index, owner = global_argmin(mn, ix, group=group)
+    win_d = engine.empty(n_seg)
+    win_t = engine.empty(n_seg)
+    if owner == rank and index >= 0:
+        win_d.copy_(delta[:, 0, index - lo])
+        win_t.copy_(torque[:, 0, index - lo])
+    broadcast_from(win_d, owner, group=group)
+    broadcast_from(win_t, owner, group=group)
+    return dict(cost=cost, index=index, owner=owner, delta=win_d, torque=win_t, local_cost=res.cost, shard=(lo, hi))
+
+
+def collision_select_sharded(engine, px, py, pyaw, obstacles, offsets, radii, goal_xy, weight, group=None):
+    """Config 3 sharded by paths: local flags -> all-gather -> replicated ``select_best_path_index``.
+
+    ``px, py, pyaw`` are the FULL ``[P, n]`` host arrays on every rank; rank r evaluates rows ``shard_range(P, r, G)``.
+    Returns ``(free[P] uint8 device tensor, best index or None)`` -- identical on every rank.
+    """
+    rank, ws = world()
+    P = px.shape[0]
+    lo, hi = shard_range(P, rank, ws)
+    local = engine.collision_check_batch(px[lo:hi], py[lo:hi], pyaw[lo:hi], obstacles, offsets, radii)
+    free = gather_flags(local, P, group=group)
+    best = engine.select_best_path_index_batch(engine.dev(px[:, -1].copy()), engine.dev(py[:, -1].copy()), free,
+                                               goal_xy, weight)
+    return free, best

@@ -1,0 +1,321 @@
+"""Batch entry points of the B200 engine: thin Python over the C ABI (``include/b200mp.h``).
+
+PyTorch appears here only as plumbing: CUDA tensors are the device buffers (``.data_ptr()``), the
+current torch stream is the launch stream, pinned tensors are the host staging areas.  Every result is
+computed by the hand-written kernels in ``csrc/``; there is no CPU fallback.
+
+Array layouts are structure-of-arrays with the rollout / path index last (fastest):
+``state[12, B]``, ``delta[n_seg, ch, B]``, ``traj[n_out, 10, B]``, ``px[P, n_pts]`` ...
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import B200mpError, RolloutArgsC, VehicleParamsC, check
+from .host_numerics import host_norm2_mode
+
+_PARAM_SCALARS = ("m", "a", "b", "Izz", "Jw", "hg", "T", "wL", "wR", "rw")
+_WHEELS = ("FL", "FR", "RL", "RR")
+
+
+def pack_params(p, n_sets: Optional[int] = None):
+    """Pack objects carrying the reference's ``VehicleParameters`` attribute names into the C struct array.
+
+    ``p`` may be one object (its ``B**/C**/D**`` scalars, or ``[n_sets]`` arrays for a tyre sweep) or a
+    sequence of objects (one set each).
+    """
+    if isinstance(p, (list, tuple)):
+        arr = (VehicleParamsC * len(p))()
+        for k, q in enumerate(p):
+            arr[k] = pack_params(q)[0]
+        return arr
+    cols = {}
+    n = 1
+    for w in _WHEELS:
+        for c in "BCD":
+            v = np.atleast_1d(np.asarray(getattr(p, c + w), dtype=np.float64))
+            cols[c + w] = v
+            n = max(n, len(v))
+    n = n_sets or n
+    arr = (VehicleParamsC * n)()
+    for s in range(n):
+        q = arr[s]
+        for name in _PARAM_SCALARS:
+            setattr(q, name, float(getattr(p, name)))
+        for i, w in enumerate(_WHEELS):
+            for c in "BCD":
+                v = cols[c + w]
+                getattr(q, c)[i] = float(v[s] if len(v) > 1 else v[0])
+    return arr
+
+
+@dataclass
+class RolloutResult:
+    state_end: torch.Tensor                 # [12, B]
+    traj: Optional[torch.Tensor] = None     # [n_out, 10, B]
+    aux: Optional[torch.Tensor] = None      # [n_out, 28, B]  state_dot(10) + outputs(18)
+    cost: Optional[torch.Tensor] = None     # [B]
+
+
+class Engine:
+    """One CUDA device's view of libb200mp.  Construct one per GPU (one process per GPU under torchrun)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        n = self.lib.b200mp_device_count()
+        if n <= 0 or not torch.cuda.is_available():
+            raise B200mpError("no CUDA device is visible: python_motionplanning_b200 has no CPU fallback "
+                              f"(b200mp_device_count() = {n})")
+        if not 0 <= device < n:
+            raise ValueError(f"device {device} out of range (have {n})")
+        self.device = int(device)
+        self.tdev = torch.device("cuda", self.device)
+        self._param_sig = None
+        self._norm2_mode = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.tdev).cuda_stream
+
+    def dev(self, x, dtype=torch.float64) -> torch.Tensor:
+        """A contiguous device tensor of ``dtype`` holding ``x`` (numpy / list / tensor); no copy when possible."""
+        if isinstance(x, torch.Tensor):
+            if x.device != self.tdev or x.dtype != dtype or not x.is_contiguous():
+                x = x.to(device=self.tdev, dtype=dtype).contiguous()
+            return x
+        a = np.ascontiguousarray(x, dtype={torch.float64: np.float64, torch.float32: np.float32,
+                                           torch.int32: np.int32, torch.uint8: np.uint8}[dtype])
+        return torch.from_numpy(a).to(self.tdev)
+
+    def empty(self, *shape, dtype=torch.float64) -> torch.Tensor:
+        return torch.empty(*shape, dtype=dtype, device=self.tdev)
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    # ---------------------------------------------------------------- parameters
+    def set_params(self, p) -> int:
+        """Upload parameter set(s) (reference ``VehicleParameters`` objects); returns the number of sets."""
+        arr = p if isinstance(p, C.Array) else pack_params(p)
+        sig = bytes(arr)
+        if sig != self._param_sig:
+            check(self.lib.b200mp_set_params(self.device, arr, len(arr)), "b200mp_set_params")
+            self._param_sig = sig
+        return len(arr)
+
+    # ------------------------------------------------------------------ rollouts
+    def rollout(self, state0, delta, torque, dt: float, n_steps: int, hold: int = 1, mu=None, param_set=None,
+                store_stride: int = 0, want_aux: bool = False, dtype: str = "f64", ctrl_broadcast: bool = False,
+                cost_ref=None, cost_in=None, w_u: float = 0.1, u_ref: float = 25.0, step0: int = 0,
+                traj_out: Optional[torch.Tensor] = None, state_out: Optional[torch.Tensor] = None) -> RolloutResult:
+        """Batched open-loop RK4 rollouts (``b200mp_rk4_rollout_f64/_f32``), asynchronous on the current stream.
+
+        state0 ``[12,B]`` (or ``[10,B]``: ax_prev = ay_prev = 0, drive.py:60-61); delta ``[n_seg,1|4,B]``;
+        torque ``[n_seg,1|4,B]`` (``[n_seg,ch,1]`` with ``ctrl_broadcast``); segment of step n = (step0+n)//hold.
+        """
+        td = torch.float64 if dtype == "f64" else torch.float32
+        fn = self.lib.b200mp_rk4_rollout_f64 if dtype == "f64" else self.lib.b200mp_rk4_rollout_f32
+        s0 = self.dev(state0, td)
+        if s0.dim() != 2 or s0.shape[0] not in (10, 12):
+            raise ValueError(f"state0 must be [12,B] or [10,B], got {tuple(s0.shape)}")
+        B = s0.shape[1]
+        if s0.shape[0] == 10:
+            s0 = torch.cat([s0, torch.zeros(2, B, dtype=td, device=self.tdev)])
+        dl, tq = self.dev(delta, td), self.dev(torque, td)
+        if dl.dim() != 3 or tq.dim() != 3:
+            raise ValueError("delta and torque must be [n_seg, channels, B]")
+        need_seg = -(-(step0 + n_steps) // hold) if n_steps else 0
+        cb = 1 if ctrl_broadcast else B
+        if dl.shape[0] < need_seg or tq.shape[0] < need_seg or dl.shape[2] != cb or tq.shape[2] != cb:
+            raise ValueError(f"controls must cover {need_seg} segments x {cb} rollouts; got delta {tuple(dl.shape)}, "
+                             f"torque {tuple(tq.shape)}")
+        n_out = n_steps // store_stride if store_stride else 0
+        traj = aux = None
+        if n_out:
+            traj = traj_out if traj_out is not None else self.empty(n_out, 10, B, dtype=td)
+            if traj.shape != (n_out, 10, B) or traj.dtype != td or not traj.is_contiguous():
+                raise ValueError("traj_out has the wrong shape/dtype")
+            if want_aux:
+                aux = self.empty(n_out, 28, B, dtype=td)
+        end = state_out if state_out is not None else self.empty(12, B, dtype=td)
+        mu_t = None if mu is None else self.dev(mu, td)
+        ps_t = None if param_set is None else self.dev(param_set, torch.int32)
+        cref = cost = cin = None
+        if cost_ref is not None:
+            cref = self.dev(cost_ref, td)
+            if cref.shape[0] < step0 + n_steps:
+                raise ValueError("cost_ref must have one (x, y) row per step")
+            cost = self.empty(B, dtype=td)
+            cin = None if cost_in is None else self.dev(cost_in, td)
+        a = RolloutArgsC(B=B, n_steps=int(n_steps), step0=int(step0), hold=int(hold), dt=float(dt),
+                         state0=s0.data_ptr(), delta=dl.data_ptr(), torque=tq.data_ptr(),
+                         delta_ch=int(dl.shape[1]), torque_ch=int(tq.shape[1]), ctrl_broadcast=int(bool(ctrl_broadcast)),
+                         store_stride=int(store_stride if n_out else 0),
+                         mu=None if mu_t is None else mu_t.data_ptr(),
+                         param_set=None if ps_t is None else ps_t.data_ptr(),
+                         traj=None if traj is None else traj.data_ptr(), aux=None if aux is None else aux.data_ptr(),
+                         state_end=end.data_ptr(), cost=None if cost is None else cost.data_ptr(),
+                         cost_in=None if cin is None else cin.data_ptr(),
+                         cost_ref=None if cref is None else cref.data_ptr(), w_u=float(w_u), u_ref=float(u_ref))
+        check(fn(self.device, self._stream(), C.byref(a)), "b200mp_rk4_rollout_" + dtype)
+        return RolloutResult(state_end=end, traj=traj, aux=aux, cost=cost)
+
+    def rollout_to_host(self, state0_host: torch.Tensor, delta_host: torch.Tensor, torque_host: torch.Tensor,
+                        dt: float, n_steps: int, hold: int, traj_host: torch.Tensor, chunk_steps: int = 50,
+                        dtype: str = "f64", state_end_host: Optional[torch.Tensor] = None):
+        """End-to-end rollout with HOST buffers: H2D of the inputs, time-chunked kernels, D2H of the full
+        trajectory overlapped with the next chunk (two device slabs, two streams).
+
+        ``*_host`` are pinned CPU tensors; ``traj_host`` is ``[n_steps, 10, B]``.  Rollouts are resumable
+        (``state_end`` of one chunk is ``state0`` of the next), which is what makes the time split exact.
+        Returns after the last byte has landed in ``traj_host``.
+        """
+        td = torch.float64 if dtype == "f64" else torch.float32
+        B = state0_host.shape[1]
+        if chunk_steps % hold != 0 and n_steps > chunk_steps:
+            raise ValueError("chunk_steps must be a multiple of hold")
+        compute = torch.cuda.current_stream(self.tdev)
+        copy = self._copy_stream()
+        s = state0_host.to(self.tdev, non_blocking=True)
+        dl = delta_host.to(self.tdev, non_blocking=True)
+        tq = torque_host.to(self.tdev, non_blocking=True)
+        slabs = self._slabs(min(chunk_steps, n_steps), B, td)
+        slab_free = [None, None]
+        n0, k = 0, 0
+        while n0 < n_steps:
+            nc = min(chunk_steps, n_steps - n0)
+            slab = slabs[k & 1][:nc]
+            if slab_free[k & 1] is not None:
+                compute.wait_event(slab_free[k & 1])            # D2H of the chunk that used this slab is done
+            res = self.rollout(s, dl, tq, dt, nc, hold=hold, store_stride=1, dtype=dtype, step0=n0, traj_out=slab)
+            s = res.state_end
+            done = torch.cuda.Event()
+            done.record(compute)
+            copy.wait_event(done)
+            with torch.cuda.stream(copy):
+                traj_host[n0:n0 + nc].copy_(slab, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            slab_free[k & 1] = ev
+            n0 += nc
+            k += 1
+        if state_end_host is not None:
+            state_end_host.copy_(s, non_blocking=True)
+        copy.synchronize()
+        compute.synchronize()
+        return s
+
+    def _copy_stream(self):
+        if not hasattr(self, "_cstream"):
+            self._cstream = torch.cuda.Stream(self.tdev)
+        return self._cstream
+
+    def _slabs(self, steps, B, td):
+        key = (steps, B, td)
+        if getattr(self, "_slab_key", None) != key:
+            self._slab = [self.empty(steps, 10, B, dtype=td) for _ in range(2)]
+            self._slab_key = key
+        return self._slab
+
+    def planar_model_batch(self, state, torque, mu, delta, ax_prev, ay_prev, param_set=None):
+        """Batched ``VehicleModel.planar_model``: returns ``(state_dot[10,B], misc[6,B], outputs[18,B])``."""
+        st = self.dev(state)
+        B = st.shape[1]
+        tq, dl = self.dev(torque), self.dev(delta)
+        mu_t = None if mu is None else self.dev(mu)
+        axay = torch.stack([self.dev(ax_prev).reshape(B), self.dev(ay_prev).reshape(B)]).contiguous()
+        ps = None if param_set is None else self.dev(param_set, torch.int32)
+        sd, misc, out = self.empty(10, B), self.empty(6, B), self.empty(18, B)
+        check(self.lib.b200mp_planar_model_f64(self.device, self._stream(), B, self._ptr(st), self._ptr(tq),
+                                               self._ptr(mu_t), self._ptr(dl), self._ptr(axay), self._ptr(ps),
+                                               self._ptr(sd), self._ptr(misc), self._ptr(out)), "b200mp_planar_model_f64")
+        return sd, misc, out
+
+    # ------------------------------------------------------------- sampling MPC
+    def mpc_sample_controls(self, B: int, n_seg: int, seed: int, rollout0: int = 0, delta_mean=0.0, delta_sigma=0.02,
+                            delta_clip=0.5235987755982988, torque_mean=0.0, torque_sigma=50.0):
+        delta, torque = self.empty(n_seg, 1, B), self.empty(n_seg, 1, B)
+        check(self.lib.b200mp_mpc_sample_controls_f64(self.device, self._stream(), B, n_seg, int(seed), int(rollout0),
+                                                      delta_mean, delta_sigma, delta_clip, torque_mean, torque_sigma,
+                                                      self._ptr(delta), self._ptr(torque)), "b200mp_mpc_sample_controls_f64")
+        return delta, torque
+
+    def argmin(self, cost: torch.Tensor, index_offset: int = 0):
+        """Device-side lowest-index argmin; returns device tensors ``(min[1] f64, idx[1] i64)`` (async)."""
+        cost = self.dev(cost)
+        mn, ix = self.empty(1), self.empty(1, dtype=torch.int64)
+        check(self.lib.b200mp_argmin_f64(self.device, self._stream(), cost.numel(), self._ptr(cost), int(index_offset),
+                                         self._ptr(mn), self._ptr(ix)), "b200mp_argmin_f64")
+        return mn, ix
+
+    # ---------------------------------------------------------------- collision
+    def collision_check_batch(self, px, py, pyaw, obstacles, offsets: Sequence[float], radii: Sequence[float],
+                              want_clearance: bool = False, device_trig: bool = False):
+        """``free[P]`` (uint8, 1 = collision-free) for P paths at once (``b200mp_collision_check_f64``).
+
+        px, py ``[P,n]``; pyaw ``[P,>=n]`` (first n used).  By default cos/sin of the yaws are evaluated on the
+        host with numpy -- exactly what the reference does (collision_checker.py:88-89) -- which makes the
+        booleans bit-exact; ``device_trig=True`` evaluates them in the kernel instead (<= 1-2 ulp).
+        """
+        pxt, pyt = self.dev(px), self.dev(py)
+        if pxt.dim() != 2:
+            raise ValueError("px, py must be [P, n_pts]")
+        P, n = pxt.shape
+        obs = self.dev(np.asarray(obstacles, dtype=np.float64).reshape(-1, 2) if not isinstance(obstacles, torch.Tensor)
+                       else obstacles)
+        M = obs.shape[0]
+        off = (C.c_double * len(offsets))(*[float(v) for v in offsets])
+        rad = (C.c_double * len(radii))(*[float(v) for v in radii])
+        if len(offsets) != len(radii):
+            raise ValueError("circle_offsets and circle_radii must have the same length")
+        pc = ps = yaw_t = None
+        stride = 0
+        if device_trig:
+            yaw_t = self.dev(pyaw)
+            stride = yaw_t.shape[1]
+        else:
+            if isinstance(pyaw, torch.Tensor):
+                pyaw = pyaw.detach().cpu().numpy()
+            yaw = np.asarray(pyaw, dtype=np.float64)[:, :n]
+            pc, ps = self.dev(np.cos(yaw)), self.dev(np.sin(yaw))
+        free = self.empty(P, dtype=torch.uint8)
+        clr = self.empty(P) if want_clearance else None
+        check(self.lib.b200mp_collision_check_f64(self.device, self._stream(), P, n, len(offsets), off, rad,
+                                                  self._ptr(pxt), self._ptr(pyt), self._ptr(pc), self._ptr(ps),
+                                                  self._ptr(yaw_t), stride, M, self._ptr(obs), self._ptr(free),
+                                                  self._ptr(clr)), "b200mp_collision_check_f64")
+        return (free, clr) if want_clearance else free
+
+    def select_best_path_index_batch(self, end_x, end_y, free, goal_xy, weight: float, norm_mode: Optional[int] = None,
+                                     want_scores: bool = False):
+        """``select_best_path_index`` on end points; returns ``int`` or ``None`` (synchronises)."""
+        ex, ey = self.dev(end_x), self.dev(end_y)
+        fr = self.dev(free, torch.uint8) if not (isinstance(free, torch.Tensor) and free.dtype == torch.bool) \
+            else free.to(self.tdev).to(torch.uint8)
+        P = ex.numel()
+        if norm_mode is None:
+            if self._norm2_mode is None:
+                self._norm2_mode = host_norm2_mode()
+            norm_mode = self._norm2_mode
+        best = self.empty(1, dtype=torch.int32)
+        scores = self.empty(P) if want_scores else None
+        check(self.lib.b200mp_select_best_f64(self.device, self._stream(), P, self._ptr(ex), self._ptr(ey), self._ptr(fr),
+                                              float(goal_xy[0]), float(goal_xy[1]), float(weight), int(norm_mode),
+                                              self._ptr(scores), self._ptr(best)), "b200mp_select_best_f64")
+        b = int(best.item())
+        b = None if b < 0 else b
+        return (b, scores) if want_scores else b
+
+    # -------------------------------------------------------------- measurement
+    def fma_peak(self, dtype_bits: int = 64, reps: int = 5) -> float:
+        """Measured FMA-pipe peak in TFLOP/s (register-resident chains), the rollout roofline denominator."""
+        out = C.c_double(0.0)
+        check(self.lib.b200mp_fma_peak(self.device, dtype_bits, reps, C.byref(out)), "b200mp_fma_peak")
+        return out.value

@@ -1,0 +1,153 @@
+"""GPU parity of the lattice evaluation: collision booleans and selected indices must be BIT-EXACT.
+
+Compared with the literal-reference golden vectors, with the bit-exact oracle on the full config-3
+batch (4,096 paths x 49 points x 3 circles vs 10,000 obstacle points), and through the reference-named
+classes / the pool seam.
+"""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, collision_numpy as cn
+from python_motionplanning_b200 import CollisionChecker, ThreadPool, workloads as wl
+from python_motionplanning_b200.host_numerics import host_norm2_mode
+
+pytestmark = pytest.mark.gpu
+OFF, RAD, W = list(wl.CIRCLE_OFFSETS), list(wl.CIRCLE_RADII), wl.PATH_SELECT_WEIGHT
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def test_collision_subsample_vs_literal(engine, golden):
+    g = golden("collision_cfg3_sub.npz")
+    free = engine.collision_check_batch(g["px"], g["py"], g["pyaw"], g["obstacles"], OFF, RAD)
+    assert np.array_equal(_np(free).astype(bool), g["free"])
+
+
+def test_collision_kat3_and_boundary_vs_literal(engine, golden):
+    g = golden("collision_cfg3_sub.npz")
+    cc = CollisionChecker(OFF, RAD, W, engine=engine)
+    path = [[float(i) for i in range(1, 50)], [0.0] * 49, [0.0] * 50]          # 50 yaws: only 49 are read
+    for obs, cnt, want in zip(g["kat3_obstacles"], g["kat3_counts"], g["kat3_free"]):
+        got = cc.collision_check(path, obs[:cnt].tolist())
+        assert isinstance(got, bool) and got == bool(want)
+    # obstacle points a few ulps either side of the radius (3,000 literal-reference verdicts)
+    n = len(g["bnd_x"])
+    got = np.zeros(n, dtype=bool)
+    for i in range(n):
+        f = engine.collision_check_batch(g["bnd_x"][i:i + 1, None], g["bnd_y"][i:i + 1, None], g["bnd_yaw"][i:i + 1, None],
+                                         np.array([[g["bnd_ox"][i], g["bnd_oy"][i]]]), OFF, RAD)
+        got[i] = bool(f.item())
+    assert np.array_equal(got, g["bnd_free"])
+
+
+def test_collision_cfg3_full_bit_exact(engine):
+    """Full config 3 against the bit-exact C oracle, plus min-clearance and the early-exit-free mode."""
+    w = wl.config3_lattice()
+    free = engine.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD)
+    ref, _, _ = c_oracle.collision_check(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD)
+    assert np.array_equal(_np(free).astype(bool), ref)
+    assert 0.2 <= ref.mean() <= 0.8
+    free2, clr = engine.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD, want_clearance=True)
+    ref2, clr_ref, _ = c_oracle.collision_check(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD, want_clearance=True)
+    assert np.array_equal(_np(free2).astype(bool), ref) and np.array_equal(ref2, ref)
+    assert np.array_equal(_np(clr), clr_ref)                     # same roundings -> identical doubles
+    # device-side sincos (<= 1-2 ulp from libm): report, and require agreement on this batch
+    free3 = engine.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD, device_trig=True)
+    mism = int((_np(free3).astype(bool) != ref).sum())
+    print(f"config 3: free fraction {ref.mean():.3f}; device-trig mismatches {mism}/{len(ref)}")
+    assert mism <= 2
+
+
+def test_collision_permutation_and_tiling_invariance(engine):
+    """The verdict does not depend on obstacle order / tile boundaries (1,024-point tiles)."""
+    w = wl.config3_lattice(P=512, M=3000)
+    base = _np(engine.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD))
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(len(w["obstacles"]))
+    assert np.array_equal(base, _np(engine.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"][perm], OFF, RAD)))
+    for M in (1, 1023, 1024, 1025, 2049):
+        ref, _, _ = c_oracle.collision_check(w["px"], w["py"], w["pyaw"], w["obstacles"][:M], OFF, RAD)
+        got = _np(engine.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"][:M], OFF, RAD)).astype(bool)
+        assert np.array_equal(got, ref), M
+    # other circle counts / radii
+    for off, rad in (([0.0], [2.0]), ([-1.0, 0.5, 2.0, 3.5, 5.0], [1.0, 1.2, 0.8, 1.5, 0.3])):
+        ref, _, _ = c_oracle.collision_check(w["px"], w["py"], w["pyaw"], w["obstacles"], off, rad)
+        got = _np(engine.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"], off, rad)).astype(bool)
+        assert np.array_equal(got, ref)
+
+
+def test_select_best_vs_literal_and_oracle(engine, golden):
+    g = golden("collision_cfg3_sub.npz")
+    w = wl.config3_lattice()
+    ex, ey = w["px"][:, -1].copy(), w["py"][:, -1].copy()
+    mode = host_norm2_mode()
+    free512 = g["sel_free512"]
+    if mode == int(g["norm2_mode"]):
+        for lo, n, best in g["sel_cases"]:      # literal reference results (same BLAS closed form as this host)
+            got = engine.select_best_path_index_batch(ex[lo:lo + n], ey[lo:lo + n], free512[lo:lo + n], g["goal"], W)
+            assert got == (None if best < 0 else int(best))
+    # full P = 4,096 against the C oracle in every rounding mode, scores bit for bit
+    free, _, _ = c_oracle.collision_check(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD)
+    for m in (0, 1, 2):
+        want, scores = c_oracle.select_best(ex, ey, free, w["goal"], W, m)
+        got, sc = engine.select_best_path_index_batch(ex, ey, free, w["goal"], W, norm_mode=m, want_scores=True)
+        assert got == want and np.array_equal(_np(sc), scores)
+    # host-mode result equals the literal-order NumPy oracle (which calls np.linalg.norm itself) on 512 paths
+    want = cn.select_best_path_index(ex[:512], ey[:512], free[:512], w["goal"], W)
+    assert engine.select_best_path_index_batch(ex[:512], ey[:512], free[:512], w["goal"], W) == want
+
+
+def test_select_best_kat4_ties(engine, golden):
+    g = golden("collision_cfg3_sub.npz")
+    cc = CollisionChecker(OFF, RAD, W, engine=engine)
+    paths = [[[float(i) for i in range(1, 50)], [yv] * 49, [0.0] * 49] for yv in (-4.0, -2.0, 0.0, 2.0, 4.0)]
+    for flags, best in zip(g["kat4_flags"], g["kat4_best"]):
+        got = cc.select_best_path_index(paths, [bool(f) for f in flags], [49, 0, 25])
+        assert got == (None if best < 0 else int(best))
+    assert cc.select_best_path_index([], [], [0, 0, 0]) is None
+
+
+def test_planner_seam_closed_loop_lattices(engine, golden):
+    """Config 1: the reference's own planner lattices through the pool seam, flags + index per frame."""
+    g = golden("closedloop_cfg1.npz")
+    cc = CollisionChecker(OFF, RAD, W, engine=engine)
+    obstacle = g["obstacle_xy"].tolist()
+    for k, f in enumerate(g["plan_path_frames"]):
+        paths = [[g["plan_paths"][k, i, 0].tolist(), g["plan_paths"][k, i, 1].tolist(), g["plan_paths"][k, i, 2].tolist()]
+                 for i in range(7)]
+        # exactly the call local_planner.py:370-372 makes
+        pool = ThreadPool(processes=len(paths))
+        flags = pool.starmap(cc.collision_check, zip(paths, itertools.repeat(obstacle)))
+        assert flags == [bool(x) for x in g["plan_flags"][f]], f
+        goal = list(g["plan_goal"][f]) + [25.0]
+        best = cc.select_best_path_index(paths, flags, goal)
+        assert (-1 if best is None else best) == int(g["plan_best"][f]), f
+    with pytest.raises(ValueError):
+        ThreadPool(processes=0)               # keeps the planner's `except ValueError -> [True]*7` path
+
+
+def test_collision_edge_cases(engine):
+    cc = CollisionChecker(OFF, RAD, W, engine=engine)
+    path = [[1.0, 2.0, 3.0], [0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0]]
+    assert cc.collision_check(path, []) is True                       # empty obstacle list
+    assert cc.collision_check([[], [], []], [[1.0, 0.0]]) is True     # empty path
+    assert cc.collision_check_paths([], [[1.0, 0.0]]) == []
+    # ragged lengths in one batch
+    long = [[float(i) for i in range(10)], [0.0] * 10, [0.0] * 10]
+    flags = cc.collision_check_paths([path, long, [[], [], []]], [[8.0, 0.5]])
+    assert flags == [True, False, True]
+    # dist == r is free, one ulp inside is a collision
+    assert cc.collision_check([[0.0], [0.0], [0.0]], [[4.5, 0.0]]) is True
+    assert cc.collision_check([[0.0], [0.0], [0.0]], [[np.nextafter(4.5, 0.0), 0.0]]) is False
+    # zero-size launches through the engine
+    z = np.zeros((0, 49))
+    assert engine.collision_check_batch(z, z, z, np.zeros((5, 2)), OFF, RAD).numel() == 0
+    f = engine.collision_check_batch(np.zeros((3, 4)), np.zeros((3, 4)), np.zeros((3, 4)), np.zeros((0, 2)), OFF, RAD)
+    assert _np(f).tolist() == [1, 1, 1]
+    with pytest.raises(ValueError):
+        engine.collision_check_batch(np.zeros((3, 4)), np.zeros((3, 4)), np.zeros((3, 4)), np.zeros((2, 2)), [0.0] * 9, [1.0] * 9)

@@ -1,0 +1,247 @@
+"""GPU parity of the 7-DoF RK4 path: CUDA kernels (through the C ABI) vs the oracle and the golden vectors.
+
+Contract (BASELINE.json north_star): FP64 within 1e-9 relative on every state component after N steps,
+evaluated as |gpu - ref| <= 1e-9 * max(|ref|, 1); FP32 within a measured drift bound.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import REL_TOL_F64, rel_err
+from oracle import c_oracle, mpc_numpy, planar_numpy as pn
+from python_motionplanning_b200 import VehicleModel, VehicleParameters, workloads as wl
+
+pytestmark = pytest.mark.gpu
+DT = 1e-4
+
+
+def _params(D=1.0):
+    p = VehicleParameters()
+    p.DFL = p.DFR = p.DRL = p.DRR = D
+    return p
+
+
+def _c_params(D=1.0):
+    par = c_oracle.make_params(pn.VehicleParams())
+    par[0].D[:] = (D,) * 4
+    return par
+
+
+def test_planar_model_vs_literal_golden(engine, golden):
+    g = golden("planar_model.npz")
+    engine.set_params(_params())
+    sd, misc, out = engine.planar_model_batch(g["states"].T, g["torque"].T, g["mu_max"].T, g["delta"].T,
+                                              g["ax_prev"], g["ay_prev"])
+    assert rel_err(sd.cpu().numpy().T, g["state_dot"]).max() < REL_TOL_F64
+    assert rel_err(misc.cpu().numpy().T, g["misc"]).max() < REL_TOL_F64
+    assert rel_err(out.cpu().numpy().T, g["outputs"]).max() < REL_TOL_F64
+    # zero-slip state: exactly zero forces (the s == 0 branch, vehicle_model.py:309-348)
+    assert list(sd.cpu().numpy()[:, 1]) == [0, 0, 0, 0, 0, 0, 0, 0, 25, 0]
+
+
+def test_rk4_single_step_vs_literal_golden(engine, golden):
+    g = golden("planar_model.npz")
+    engine.set_params(_params())
+    n = len(g["states"])
+    s0 = np.concatenate([g["states"].T, g["ax_prev"][None], g["ay_prev"][None]])
+    res = engine.rollout(s0, g["delta"].T[None], g["torque"].T[None], float(g["dt"]), 1, mu=g["mu_max"].T,
+                         store_stride=1, want_aux=True)
+    end = res.state_end.cpu().numpy()
+    aux = res.aux.cpu().numpy()[0]
+    assert rel_err(end[:10].T, g["rk4_state"]).max() < REL_TOL_F64
+    assert rel_err(end[10:].T, g["rk4_axay"]).max() < REL_TOL_F64
+    assert rel_err(aux[:10].T, g["rk4_state_dot"]).max() < REL_TOL_F64
+    assert rel_err(aux[10:].T, g["rk4_outputs"]).max() < REL_TOL_F64
+    assert np.array_equal(res.traj.cpu().numpy()[0], end[:10]) and n == end.shape[1]
+
+
+def test_rollout_cfg2_subsample_vs_literal(engine, golden):
+    """256 rollouts x 500 steps of config 2 against the literal reference."""
+    g = golden("rollout_cfg2_sub.npz")
+    engine.set_params(_params())
+    res = engine.rollout(g["state0"], g["delta"], g["torque"], float(g["dt"]), 500, hold=int(g["hold"]), store_stride=1)
+    traj = res.traj.cpu().numpy()
+    worst = 0.0
+    for k, n in enumerate(g["check_steps"]):
+        e = rel_err(traj[n - 1], g["states"][:, k, :10].T).max()
+        worst = max(worst, e)
+        assert e < REL_TOL_F64, (n, e)
+    assert rel_err(res.state_end.cpu().numpy()[10:], g["states"][:, -1, 10:].T).max() < REL_TOL_F64
+    print(f"config-2 subsample vs literal reference: worst rel err {worst:.3e}")
+
+
+def test_rollout_cfg2_full_vs_c_oracle(engine):
+    """Full config 2 (65,536 x 500, FP64) against the C oracle on identical inputs."""
+    B, N = 65536, 500
+    s0, d, t = wl.config2_rollouts(B=B, n_steps=N)
+    engine.set_params(_params())
+    res = engine.rollout(s0, d, t, DT, N, hold=wl.HOLD, store_stride=50)
+    ref = c_oracle.rollout(s0, d, t, _c_params(), DT, N, hold=wl.HOLD, store_stride=50)
+    e = rel_err(res.traj.cpu().numpy(), ref["traj"])
+    assert e.max() < REL_TOL_F64, e.max()
+    assert rel_err(res.state_end.cpu().numpy(), ref["state_end"]).max() < REL_TOL_F64
+    print(f"config 2 full: worst rel err {e.max():.3e}, per component {e.max(axis=(0, 2))}")
+
+
+def test_closed_loop_replay_cfg1(engine, golden):
+    """Config 1: replay the reference's recorded closed-loop controls (ZOH-10), all 40,000 steps."""
+    g = golden("closedloop_cfg1.npz")
+    engine.set_params(_params())
+    n = len(g["delta"]) * 10
+    res = engine.rollout(g["state0"][:, None], g["delta"][:, None, None], g["torque"][:, None, None], float(g["dt"]),
+                         n, hold=10, store_stride=10)
+    traj = res.traj.cpu().numpy()[:, :, 0]
+    e = rel_err(traj, g["state_every10"])
+    assert e.max() < REL_TOL_F64, e.max()
+    assert rel_err(res.state_end.cpu().numpy()[10:, 0], g["axay_every10"][-1]).max() < 1e-8
+    print(f"closed-loop replay 40,000 steps: worst rel err {e.max():.3e}")
+
+
+def test_scalar_vehicle_model_surface(golden):
+    """The reference-named scalar calls: return structure, p.D mutation, and values (first frame)."""
+    g = golden("closedloop_cfg1.npz")
+    vm = VehicleModel(2.906, np.deg2rad(30), float(g["dt"]))
+    p = VehicleParameters()
+    state = list(g["state0"][:10])
+    ax = ay = 0
+    for i in range(100):
+        d, t = g["delta"][i // 10], g["torque"][i // 10]
+        r = vm.planar_model_RK4(state, [t, t, t, t], [1.0, 1.0, 1.0, 1.0], [d, d, 0, 0], p, ax, ay)
+        assert len(r) == 9 and r[0].shape == (10,) and r[5].shape == (10,) and r[6].shape == (18,)
+        state, ax, ay = r[0], r[7], r[8]
+        assert r[1] == state[8] and r[2] == state[9] and r[3] == state[7] and r[4] == state[0]
+        assert rel_err(state, g["first_frame_states"][i]).max() < REL_TOL_F64
+        assert rel_err(r[5], g["first_frame_sdot"][i]).max() < REL_TOL_F64
+        assert rel_err(r[6], g["first_frame_outputs"][i]).max() < REL_TOL_F64
+    assert (p.DFL, p.DFR, p.DRL, p.DRR) == (1.0, 1.0, 1.0, 1.0)
+    k = golden("planar_model.npz")
+    r = vm.planar_model(list(k["states"][0]), list(k["torque"][0]), list(k["mu_max"][0]), list(k["delta"][0]), p,
+                        0.4, -0.7)
+    assert len(r) == 8 and r[0].shape == (10,) and r[5].shape == (18,)
+    assert rel_err(r[0], k["state_dot"][0]).max() < REL_TOL_F64
+    assert rel_err([r[1], r[2], r[3], r[4], r[6], r[7]], k["misc"][0]).max() < REL_TOL_F64
+    assert (p.DFL, p.DFR, p.DRL, p.DRR) == tuple(k["mu_max"][0])
+
+
+def test_rollout_is_resumable_bitwise(engine):
+    """Two launches of 250 steps (step0 = 0, 250) equal one launch of 500 bit for bit."""
+    s0, d, t = wl.config2_rollouts(B=4096, n_steps=500)
+    engine.set_params(_params())
+    one = engine.rollout(s0, d, t, DT, 500, hold=wl.HOLD, store_stride=10)
+    a = engine.rollout(s0, d, t, DT, 250, hold=wl.HOLD, store_stride=10)
+    b = engine.rollout(a.state_end, d, t, DT, 250, hold=wl.HOLD, store_stride=10, step0=250)
+    assert torch.equal(one.state_end, b.state_end)
+    assert torch.equal(one.traj, torch.cat([a.traj, b.traj]))
+
+
+def test_rollout_layout_variants_agree(engine):
+    """4-channel controls, per-rollout mu_max and param_set reproduce the front-steer fast path."""
+    B, N = 2048, 200
+    s0, d, t = wl.config2_rollouts(B=B, n_steps=N)
+    engine.set_params(_params())
+    fast = engine.rollout(s0, d, t, DT, N, hold=wl.HOLD, store_stride=0)
+    z = np.zeros_like(d)
+    d4 = np.concatenate([d, d, z, z], axis=1)
+    t4 = np.repeat(t, 4, axis=1)
+    gen = engine.rollout(s0, d4, t4, DT, N, hold=wl.HOLD)
+    mu = engine.rollout(s0, d, t, DT, N, hold=wl.HOLD, mu=np.ones((4, B)))
+    ps = engine.rollout(s0, d, t, DT, N, hold=wl.HOLD, param_set=np.zeros(B, dtype=np.int32))
+    for other in (gen, mu, ps):
+        assert rel_err(other.state_end.cpu().numpy(), fast.state_end.cpu().numpy()).max() < 1e-12
+    # broadcast controls: one sequence for every rollout
+    bc = engine.rollout(s0, d[:, :, :1], t[:, :, :1], DT, N, hold=wl.HOLD, ctrl_broadcast=True)
+    rep = engine.rollout(s0, np.repeat(d[:, :, :1], B, 2), np.repeat(t[:, :, :1], B, 2), DT, N, hold=wl.HOLD)
+    assert torch.equal(bc.state_end, rep.state_end)
+
+
+def test_param_sweep_cfg5_small_f64_and_f32_drift(engine):
+    """Config 5 (reduced: 16 tyre sets x 256 manoeuvres x 500 steps): FP64 parity + measured FP32 drift."""
+    n_sets, n_man, N = 16, 256, 500
+    sets, s0, d, t, pset = wl.config5_sweep(n_sets=n_sets, n_man=n_man)
+    p = VehicleParameters()
+    for w in ("FL", "FR", "RL", "RR"):
+        setattr(p, "B" + w, sets[:, 0])
+        setattr(p, "C" + w, sets[:, 1])
+        setattr(p, "D" + w, sets[:, 2])
+    assert engine.set_params(p) == n_sets
+    r64 = engine.rollout(s0, d, t, DT, N, hold=N, param_set=pset, store_stride=1)
+    op = pn.VehicleParams()
+    for w in ("FL", "FR", "RL", "RR"):
+        setattr(op, "B" + w, sets[:, 0])
+        setattr(op, "C" + w, sets[:, 1])
+        setattr(op, "D" + w, sets[:, 2])
+    ref = c_oracle.rollout(s0, d, t, c_oracle.make_params(op), DT, N, hold=N, param_set=pset, store_stride=1)
+    e = rel_err(r64.traj.cpu().numpy(), ref["traj"])
+    assert e.max() < REL_TOL_F64, e.max()
+    r32 = engine.rollout(s0, d, t, DT, N, hold=N, param_set=pset, store_stride=1, dtype="f32")
+    t32 = r32.traj.cpu().numpy().astype(np.float64)
+    drift = rel_err(t32, ref["traj"])
+    report = {n: float(drift[n - 1].max()) for n in (1, 10, 100, 500)}
+    print("FP32 drift (max rel, floor 1) at steps 1/10/100/500:", report)
+    # stated, measured bound: FP32 stays within 2e-3 of FP64 over 500 steps on this sweep
+    assert report[500] < 2e-3 and report[1] < 1e-5
+
+
+def test_mpc_controls_cost_argmin(engine):
+    """Config 4 (reduced): Philox control sampling, running cost and device argmin vs restatements."""
+    cfg = wl.config4_mpc(B=8192, n_steps=100)
+    B, N = cfg["B"], cfg["n_steps"]
+    engine.set_params(_params())
+    d, t = engine.mpc_sample_controls(B, N, cfg["seed"])
+    dn, tn = mpc_numpy.sample_controls(B, N, cfg["seed"])
+    assert np.abs(d.cpu().numpy() - dn).max() < 1e-15 and np.abs(t.cpu().numpy() - tn).max() < 1e-11
+    # sharded sampling (global rollout offset) reproduces the unsharded sequences bit for bit
+    d2, _ = engine.mpc_sample_controls(B // 2, N, cfg["seed"], rollout0=B // 2)
+    assert torch.equal(d2, d[:, :, B // 2:])
+    s0 = np.repeat(cfg["state0"][:, None], B, axis=1)
+    res = engine.rollout(s0, d, t, DT, N, hold=1, cost_ref=cfg["cost_ref"], w_u=cfg["w_u"], u_ref=cfg["u_ref"],
+                         store_stride=1)
+    ref = c_oracle.rollout(s0, d.cpu().numpy(), t.cpu().numpy(), _c_params(), DT, N, hold=1, store_stride=1,
+                           cost_ref=cfg["cost_ref"], w_u=cfg["w_u"], u_ref=cfg["u_ref"])
+    assert rel_err(res.traj.cpu().numpy(), ref["traj"]).max() < REL_TOL_F64
+    cost = res.cost.cpu().numpy()
+    assert rel_err(cost, ref["cost"], 1e-12).max() < 1e-8
+    # the cost equals the documented definition evaluated on the GPU's own trajectory
+    assert rel_err(cost, mpc_numpy.rollout_cost(res.traj.cpu().numpy(), cfg["cost_ref"], cfg["w_u"], cfg["u_ref"]),
+                   1e-300).max() < 1e-13
+    mn, ix = engine.argmin(res.cost, index_offset=1000)
+    assert int(ix.item()) == mpc_numpy.argmin_lowest(cost) + 1000 and float(mn.item()) == cost.min()
+    # ties -> lowest index; NaN -> +inf; nothing finite -> -1
+    c = torch.tensor([3.0, float("nan"), 1.0, 1.0, float("inf")], dtype=torch.float64)
+    assert int(engine.argmin(c)[1].item()) == 2
+    assert int(engine.argmin(torch.full((5000,), float("inf"), dtype=torch.float64))[1].item()) == -1
+    big = torch.rand(3_000_000, dtype=torch.float64, device="cuda")
+    big[2_345_678] = -1.0
+    big[2_999_999] = -1.0
+    assert int(engine.argmin(big)[1].item()) == 2_345_678
+
+
+def test_rollout_to_host_pipeline(engine):
+    """The end-to-end path (pinned host buffers, time-chunked, overlapped D2H) equals one device launch."""
+    B, N = 8192, 200
+    s0, d, t = wl.config2_rollouts(B=B, n_steps=N)
+    engine.set_params(_params())
+    dev = engine.rollout(s0, d, t, DT, N, hold=wl.HOLD, store_stride=1)
+    hs, hd, ht = (torch.from_numpy(a).pin_memory() for a in (s0, d, t))
+    out = torch.empty(N, 10, B, dtype=torch.float64).pin_memory()
+    end = engine.rollout_to_host(hs, hd, ht, DT, N, wl.HOLD, out, chunk_steps=50)
+    assert torch.equal(out, dev.traj.cpu()) and torch.equal(end, dev.state_end)
+
+
+def test_abi_error_behaviour(engine):
+    s0, d, t = wl.config2_rollouts(B=64, n_steps=20)
+    engine.set_params(_params())
+    with pytest.raises(ValueError):
+        engine.rollout(s0, d[:, :, :10], t, DT, 20, hold=wl.HOLD)          # controls do not cover the batch
+    with pytest.raises(ValueError):
+        engine.rollout(s0, np.repeat(d, 3, axis=1), t, DT, 20, hold=wl.HOLD)  # 3 steer channels
+    r = engine.rollout(s0, d, t, DT, 0, hold=wl.HOLD)                       # zero steps: state passes through
+    assert np.array_equal(r.state_end.cpu().numpy(), s0)
+    # NaN propagates like the reference's numpy scalars (vx == 0), no error
+    bad = s0.copy()
+    bad[0, 0] = 0.0
+    bad[1, 0] = 0.0
+    bad[2, 0] = 0.0
+    r = engine.rollout(bad, d, t, DT, 5, hold=wl.HOLD)
+    out = r.state_end.cpu().numpy()
+    assert np.isnan(out[0, 0]) and np.isfinite(out[:, 1:]).all()
