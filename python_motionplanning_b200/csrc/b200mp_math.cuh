@@ -60,6 +60,15 @@ template <> struct Math<double> {
         *c = ::cos(x);
 #endif
     }
+    // product rounded on its own (never contracted into a following add)
+    static B200MP_HD double mul_rn(double a, double b)
+    {
+#if defined(__CUDA_ARCH__)
+        return __dmul_rn(a, b);
+#else
+        return a * b;
+#endif
+    }
     static B200MP_HD double sin(double x) { return ::sin(x); }
     static B200MP_HD double atan(double x) { return ::atan(x); }
     static B200MP_HD double abs(double x) { return ::fabs(x); }
@@ -91,6 +100,14 @@ template <> struct Math<float> {
 #else
         *s = ::sinf(x);
         *c = ::cosf(x);
+#endif
+    }
+    static B200MP_HD float mul_rn(float a, float b)
+    {
+#if defined(__CUDA_ARCH__)
+        return __fmul_rn(a, b);
+#else
+        return a * b;
 #endif
     }
     static B200MP_HD float sin(float x) { return ::sinf(x); }

@@ -106,7 +106,9 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
         vy = vyc * cd - vxc * sd;
     }
     const R r = M::rcp(vx);
-    const R sx = (P.rw * w) * r - (R)1;  // :284-287
+    // (rw*w - vx)/vx instead of rw*w/vx - 1 (:284-287): same value, no cancellation after the divide,
+    // and exactly 0 when the rounded product equals vx (the reference's zero-slip equilibrium)
+    const R sx = (M::mul_rn(P.rw, w) - vx) * r;
     const R sy = -vy * M::abs(r);        // :290-293
     const R q = sx * sx + sy * sy;       // :296-299
     const R rs = M::rsqrt(q);
