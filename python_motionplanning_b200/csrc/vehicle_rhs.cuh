@@ -111,10 +111,11 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
     const R sx = (M::mul_rn(P.rw, w) - vx) * r;
     const R sy = -vy * M::abs(r);        // :290-293
     const R q = sx * sx + sy * sy;       // :296-299
+    const bool slipping = q != (R)0;
     const R rs = M::rsqrt(q);
-    s = q * rs;
+    s = slipping ? q * rs : (R)0;        // sqrt(q); rsqrt(0) = inf must not leak into s
     const R mu = D * M::sin(P.Cc[I] * M::atan(P.Bc[I] * s));   // :303-306
-    const R g = (q != (R)0) ? mu * rs : (R)0;                  // :309-348 (zero slip -> zero friction)
+    const R g = slipping ? mu * rs : (R)0;                     // :309-348 (zero slip -> zero friction)
     fxt = (sx * g) * Fz;                 // :351-360
     fyt = (sy * g) * Fz;
     if (REAR0 && I >= 2) {

@@ -55,6 +55,16 @@ def pack_params(p, n_sets: Optional[int] = None):
     return arr
 
 
+# The parameter table is library state per DEVICE (not per Engine object): remember what was uploaded
+# last so that several Engine / VehicleModel objects on one device never trust a stale table.
+_UPLOADED = {}      # device -> (signature bytes, upload counter)
+
+
+def uploaded_token(device: int) -> int:
+    """Counter that changes whenever a new parameter table is uploaded to ``device``."""
+    return _UPLOADED.get(device, (None, 0))[1]
+
+
 @dataclass
 class RolloutResult:
     state_end: torch.Tensor                 # [12, B]
@@ -76,7 +86,6 @@ class Engine:
             raise ValueError(f"device {device} out of range (have {n})")
         self.device = int(device)
         self.tdev = torch.device("cuda", self.device)
-        self._param_sig = None
         self._norm2_mode = None
 
     # ------------------------------------------------------------------ plumbing
@@ -105,9 +114,10 @@ class Engine:
         """Upload parameter set(s) (reference ``VehicleParameters`` objects); returns the number of sets."""
         arr = p if isinstance(p, C.Array) else pack_params(p)
         sig = bytes(arr)
-        if sig != self._param_sig:
+        old_sig, token = _UPLOADED.get(self.device, (None, 0))
+        if sig != old_sig:
             check(self.lib.b200mp_set_params(self.device, arr, len(arr)), "b200mp_set_params")
-            self._param_sig = sig
+            _UPLOADED[self.device] = (sig, token + 1)
         return len(arr)
 
     # ------------------------------------------------------------------ rollouts

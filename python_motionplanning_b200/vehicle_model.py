@@ -20,7 +20,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .engine import Engine
+from .engine import Engine, uploaded_token
 
 
 class VehicleParameters:
@@ -91,12 +91,11 @@ class VehicleModel:
         eng = self._buffers()
         # re-upload the parameter table only when a field the model reads has changed (D is replaced by
         # mu_max on every call and travels as the mu array instead)
-        sig = (p.m, p.a, p.b, p.Izz, p.Jw, p.hg, p.T, p.wL, p.wR, p.rw, p.BFL, p.BFR, p.BRL, p.BRR,
-               p.CFL, p.CFR, p.CRL, p.CRR)
+        sig = (uploaded_token(eng.device), p.m, p.a, p.b, p.Izz, p.Jw, p.hg, p.T, p.wL, p.wR, p.rw,
+               p.BFL, p.BFR, p.BRL, p.BRR, p.CFL, p.CFR, p.CRL, p.CRR)
         if sig != self._param_sig:
-            eng._param_sig = None
             eng.set_params(p)
-            self._param_sig = sig
+            self._param_sig = (uploaded_token(eng.device),) + sig[1:]
         a = self._np_in
         a[0:10] = state
         a[10] = ax_prev
