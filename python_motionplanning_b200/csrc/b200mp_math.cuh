@@ -1,24 +1,68 @@
 // Scalar math building blocks for the rollout kernels (sm_100a).
 //
-// FP64 division and square root are not single instructions on the GPU; the rollout needs, per wheel
-// and RK4 stage, 1/vx and both sqrt(q) and 1/sqrt(q).  We take the hardware seeds (MUFU.RCP64H /
-// MUFU.RSQ64H, ~2^-22 relative) and finish with two Newton steps on the FP64 pipe, which is 1-2 ulp --
-// three orders of magnitude inside the 1e-9 parity contract -- at a third of the instruction count of
-// the IEEE-rounded library routines and with no slow-path branches.
+// Why not the CUDA math library: per RK4 step the model needs 16 atan, 16 sin, 8 sincos, 32 divisions and
+// 16 square roots in FP64.  ncu on the first version of the kernel (profiles/r01_rollout_f64_v1.md)
+// showed that with libm only 45 % of the issued instructions were FP64-pipe instructions: the rest were
+// UMOV pairs materialising 64-bit polynomial coefficients, LDG loads of libm's coefficient tables,
+// FSEL/branch quadrant logic and slow-path scaffolding, which capped the FP64 pipe at 50 % busy and
+// overflowed the instruction cache.  The routines below
+//   * keep every polynomial coefficient in __constant__ memory, so it is a constant-bank operand of the
+//     DFMA itself (no UMOV, no load, no register),
+//   * are branch-free on their whole working range,
+//   * take the hardware seeds MUFU.RCP64H / MUFU.RSQ64H plus two Newton steps for 1/x and 1/sqrt(x)
+//     (1-2 ulp; no IEEE-rounding fix-up code),
+//   * use argument ranges the model guarantees (atan of a real, sin of C*atan(.), sincos of a heading).
+// Accuracy of each scheme is ~1-2 ulp (tools/gen_poly.py prints the measured bounds), three orders of
+// magnitude inside the 1e-9 parity contract.
 //
-// The same header compiles for the host (tests/hostsim) with plain libm so the algebra of the kernels
-// can be checked against the oracle without a GPU.
+// The same header compiles for the host (tests/hostsim, plain g++) so the polynomials and the algebra
+// of the kernels are checked against the oracle on a machine without a GPU.
 #pragma once
 
 #include <math.h>
+#include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define B200MP_HD __host__ __device__ __forceinline__
+#define B200MP_TABLE static __constant__
 #else
 #define B200MP_HD inline
+#define B200MP_TABLE static const
+#endif
+
+// custom polynomial paths: device code, and plain host compilers (hostsim); the host pass of nvcc
+// (which cannot read __constant__ tables) uses libm and is never executed
+#if defined(__CUDA_ARCH__) || !defined(__CUDACC__)
+#define B200MP_POLY 1
+#else
+#define B200MP_POLY 0
 #endif
 
 namespace b200mp {
+
+// ---- coefficient tables (tools/gen_poly.py; Chebyshev interpolants at 60 digits) -------------------
+// sin(r) = r + r*u*P(u), u = r*r, |r| <= pi/2                      max abs err 2.2e-16
+B200MP_TABLE double kSinHalfPi[8] = {-0.16666666666666666, 0.00833333333333331, -0.00019841269841251003,
+                                     2.7557319218112503e-06, -2.5052107485885176e-08, 1.6058968982311192e-10,
+                                     -7.643709637264542e-13, 2.728258980834901e-15};
+// atan(t) = t + t*u*Q(u), u = t*t, |t| <= tan(pi/8)                max rel err 2.9e-16
+B200MP_TABLE double kAtanPi8[10] = {-0.33333333333333226, 0.19999999999880183, -0.1428571426303133,
+                                    0.11111109439473953, -0.09090846249880491, 0.07690942354266835,
+                                    -0.06648434023802716, 0.05729171057606822, -0.04459975531678654,
+                                    0.022434044895340084};
+// scalar constants (uniform-register operands as well)
+B200MP_TABLE double kTrig[8] = {
+    0.3183098861837907,        // 0: 1/pi
+    3.141592653589793,         // 1: pi (hi)
+    1.2246467991473532e-16,    // 2: pi (lo)
+    1.5707963267948966,        // 3: pi/2 (hi)
+    6.123233995736766e-17,     // 4: pi/2 (lo)
+    0.41421356237309503,       // 5: tan(pi/8)
+    2.414213562373095,         // 6: tan(3 pi/8)
+    0.7853981633974483,        // 7: pi/4
+};
+constexpr double kRoundMagic = 6755399441055744.0;   // 1.5 * 2^52: low word zero -> an immediate operand
 
 template <typename R> struct Math;
 
@@ -51,15 +95,6 @@ template <> struct Math<double> {
         return 1.0 / ::sqrt(q);
 #endif
     }
-    static B200MP_HD void sincos(double x, double *s, double *c)
-    {
-#if defined(__CUDA_ARCH__)
-        ::sincos(x, s, c);
-#else
-        *s = ::sin(x);
-        *c = ::cos(x);
-#endif
-    }
     // product rounded on its own (never contracted into a following add)
     static B200MP_HD double mul_rn(double a, double b)
     {
@@ -69,9 +104,122 @@ template <> struct Math<double> {
         return a * b;
 #endif
     }
-    static B200MP_HD double sin(double x) { return ::sin(x); }
-    static B200MP_HD double atan(double x) { return ::atan(x); }
     static B200MP_HD double abs(double x) { return ::fabs(x); }
+
+    // bit helpers
+    static B200MP_HD int lo_word(double x)
+    {
+#if defined(__CUDA_ARCH__)
+        return __double2loint(x);
+#else
+        uint64_t b;
+        memcpy(&b, &x, 8);
+        return (int)(uint32_t)b;
+#endif
+    }
+    static B200MP_HD double xor_sign(double x, int bit0_source)
+    {
+        // flips the sign of x when bit 0 of bit0_source is set
+#if defined(__CUDA_ARCH__)
+        return __hiloint2double(__double2hiint(x) ^ (bit0_source << 31), __double2loint(x));
+#else
+        return (bit0_source & 1) ? -x : x;
+#endif
+    }
+
+    // odd polynomial for sin on [-pi/2, pi/2]
+    static B200MP_HD double sin_poly(double r)
+    {
+        const double u = r * r;
+        double p = kSinHalfPi[7];
+#pragma unroll
+        for (int i = 6; i >= 0; --i) p = fma(p, u, kSinHalfPi[i]);
+        return fma(r * u, p, r);
+    }
+
+    // sin(y) for moderate |y| (|y| < 2^30 pi): nearest multiple of pi removed with a two-term
+    // Cody-Waite reduction, one odd polynomial on [-pi/2, pi/2], sign from the parity of the multiple.
+    // The Pacejka argument C*atan(B*s) satisfies |y| < C*pi/2.
+    static B200MP_HD double sin(double y)
+    {
+#if B200MP_POLY
+        const double t = fma(y, kTrig[0], kRoundMagic);
+        const double kf = t - kRoundMagic;
+        double r = fma(-kf, kTrig[1], y);
+        r = fma(-kf, kTrig[2], r);
+        return xor_sign(sin_poly(r), lo_word(t));
+#else
+        return ::sin(y);
+#endif
+    }
+
+    // atan(x), any finite x: three-way argument reduction
+    //   |x| < tan(pi/8): t = |x|;  |x| > tan(3pi/8): t = -1/|x|, + pi/2;  else t = (|x|-1)/(|x|+1), + pi/4
+    // then one odd polynomial on |t| <= tan(pi/8).  One reciprocal, no branch.
+    static B200MP_HD double atan(double x)
+    {
+#if B200MP_POLY
+        const double ax = ::fabs(x);
+        const bool lo = ax < kTrig[5], hi = ax > kTrig[6];
+        const double num = lo ? ax : (hi ? -1.0 : ax - 1.0);
+        const double den = lo ? 1.0 : (hi ? ax : ax + 1.0);
+        const double off = lo ? 0.0 : (hi ? kTrig[3] : kTrig[7]);
+        const double t = num * rcp(den);
+        const double u = t * t;
+        double q = kAtanPi8[9];
+#pragma unroll
+        for (int i = 8; i >= 0; --i) q = fma(q, u, kAtanPi8[i]);
+        const double res = off + fma(t * u, q, t);
+        return ::copysign(res, x);
+#else
+        return ::atan(x);
+#endif
+    }
+
+    // sin and cos of a heading, |x| <= 1e5: nearest multiple of pi removed (two-term Cody-Waite), then
+    // sin(r) and cos(r) = sin(pi/2 - |r|) through the SAME polynomial as sin() above, so the per-step
+    // heading trigonometry adds no coefficient table to the kernel; the parity of the multiple flips
+    // both signs.  Larger or non-finite arguments fall back to the library.
+    static B200MP_HD void sincos(double x, double *s, double *c)
+    {
+#if B200MP_POLY
+        if (!(::fabs(x) <= 1.0e5)) {
+#if defined(__CUDA_ARCH__)
+            ::sincos(x, s, c);
+#else
+            *s = ::sin(x);
+            *c = ::cos(x);
+#endif
+            return;
+        }
+        const double t = fma(x, kTrig[0], kRoundMagic);
+        const double kf = t - kRoundMagic;
+        double r = fma(-kf, kTrig[1], x);
+        r = fma(-kf, kTrig[2], r);
+        const double a = (kTrig[3] - ::fabs(r)) + kTrig[4];
+        const int k = lo_word(t);
+        *s = xor_sign(sin_poly(r), k);
+        *c = xor_sign(sin_poly(a), k);
+#else
+        *s = ::sin(x);
+        *c = ::cos(x);
+#endif
+    }
+
+    // (sin, cos) of (a + e) from (sin a, cos a) for a small increment e: used for the RK4 stage headings,
+    // which differ from the step's heading by h/2*wz or h*wz.  sin e = e - e^3/6, cos e = 1 - e^2/2 + e^4/24
+    // (|e| <= 2^-10: truncation < 8e-18); returns false when e is too large for the series (the caller
+    // then evaluates sincos directly).
+    static B200MP_HD bool rotate_small(double sa, double ca, double e, double *s, double *c)
+    {
+        if (!(::fabs(e) <= 0.0009765625)) return false;
+        const double u = e * e;
+        const double se = fma(e * u, -1.0 / 6, e);
+        const double ce = fma(u, fma(u, 1.0 / 24, -0.5), 1.0);
+        *s = fma(sa, ce, ca * se);
+        *c = fma(ca, ce, -(sa * se));
+        return true;
+    }
 };
 
 template <> struct Math<float> {
@@ -86,9 +234,7 @@ template <> struct Math<float> {
     static B200MP_HD float rsqrt(float q)
     {
 #if defined(__CUDA_ARCH__)
-        // rsqrtf is 2 ulp; one Newton step brings s = q*rsqrt(q) to ~1 ulp
-        float y = rsqrtf(q);
-        return y;
+        return rsqrtf(q);
 #else
         return 1.0f / ::sqrtf(q);
 #endif
@@ -113,6 +259,16 @@ template <> struct Math<float> {
     static B200MP_HD float sin(float x) { return ::sinf(x); }
     static B200MP_HD float atan(float x) { return ::atanf(x); }
     static B200MP_HD float abs(float x) { return ::fabsf(x); }
+    static B200MP_HD bool rotate_small(float sa, float ca, float e, float *s, float *c)
+    {
+        if (!(::fabsf(e) <= 0.015625f)) return false;
+        const float u = e * e;
+        const float se = fmaf(e * u, -1.0f / 6, e);
+        const float ce = fmaf(u, fmaf(u, 1.0f / 24, -0.5f), 1.0f);
+        *s = fmaf(sa, ce, ca * se);
+        *c = fmaf(ca, ce, -(sa * se));
+        return true;
+    }
 };
 
 }  // namespace b200mp

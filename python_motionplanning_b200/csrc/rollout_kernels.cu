@@ -28,10 +28,24 @@ template <typename R> struct RolloutDev {
     R w_u, u_ref;
 };
 
-constexpr int kRolloutBlock = 64;
+// Launch shape.  65,536 rollouts (config 2) are 2,048 warps = 13.8 per SM: with <= 144 registers per
+// thread 14 warps fit on an SM and the batch is exactly one wave (no tail); above that the second wave
+// runs at 15 % occupancy.  Tunables are macros so tools/kbench can sweep them.
+#ifndef B200MP_ROLLOUT_BLOCK
+#define B200MP_ROLLOUT_BLOCK 64
+#endif
+#ifndef B200MP_ROLLOUT_MAXNREG
+#define B200MP_ROLLOUT_MAXNREG 0
+#endif
+constexpr int kRolloutBlock = B200MP_ROLLOUT_BLOCK;
+#if B200MP_ROLLOUT_MAXNREG > 0
+#define B200MP_ROLLOUT_BOUNDS __maxnreg__(B200MP_ROLLOUT_MAXNREG)
+#else
+#define B200MP_ROLLOUT_BOUNDS __launch_bounds__(B200MP_ROLLOUT_BLOCK)
+#endif
 
 template <typename R, bool REAR0, bool GENERIC, bool AUX>
-__global__ void __launch_bounds__(kRolloutBlock)
+__global__ void B200MP_ROLLOUT_BOUNDS
 rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constant__ DevParams<R> P0)
 {
     const int r = blockIdx.x * kRolloutBlock + threadIdx.x;
@@ -89,7 +103,7 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
 #pragma unroll 1
         for (; n < seg_end; ++n) {
             R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
-            rk4_step<R, REAR0, AUX>(P, D, c, a.dt, y, ax, ay, sdot, outs);
+            rk4_step<R, REAR0, AUX, !GENERIC>(P, D, c, a.dt, y, ax, ay, sdot, outs);
             if (a.cost) {
                 const size_t g = (size_t)(a.step0 + n);
                 const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;
@@ -179,7 +193,13 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
     const DevParams<R> P0 = derive_params<R>(ds.set0);
 
     const bool rear0 = g.delta_ch == 1;
-    const bool generic = g.mu != nullptr || g.param_set != nullptr;
+    // the constant-bank fast path assumes one (B, C, D) triple for the four tyres (the reference's
+    // VehicleParameters copies the FL values to every wheel, vehicle_model.py:41-54)
+    bool uniform_tyres = true;
+    for (int i = 1; i < 4; ++i)
+        uniform_tyres = uniform_tyres && ds.set0.B[i] == ds.set0.B[0] && ds.set0.C[i] == ds.set0.C[0] &&
+                        ds.set0.D[i] == ds.set0.D[0];
+    const bool generic = g.mu != nullptr || g.param_set != nullptr || !uniform_tyres;
     const bool aux = g.aux != nullptr;
     const dim3 grid((unsigned)((g.B + kRolloutBlock - 1) / kRolloutBlock)), block(kRolloutBlock);
     if (aux) {
@@ -228,12 +248,12 @@ planar_model_kernel(int B, const double *__restrict__ state, const double *__res
     }
     set_steer<double, false>(c, dl);
     normal_loads(P, axay[r], axay[Bs + r], Fz);
-    planar_rhs<double, false, true>(P, D, y, c, Fz, k, axc, ayc, out);
+    double sy, cy;
+    Math<double>::sincos(y[7], &sy, &cy);
+    planar_rhs<double, false, true, false>(P, D, y, sy, cy, c, Fz, k, axc, ayc, out);
     if (state_dot)
         for (int i = 0; i < 10; ++i) state_dot[i * Bs + r] = k[i];
     if (misc) {
-        double sy, cy;
-        sincos(y[7], &sy, &cy);
         misc[0 * Bs + r] = y[0] * cy - y[1] * sy;       // vx  :410
         misc[1 * Bs + r] = y[1] * sy + y[0] * cy;       // vy  :411 [sic], reproduced
         misc[2 * Bs + r] = axc * cy - ayc * sy;         // ax  :415

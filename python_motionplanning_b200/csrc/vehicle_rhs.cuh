@@ -92,10 +92,12 @@ B200MP_HD void normal_loads(const DevParams<R> &P, R ax_prev, R ay_prev, R Fz[4]
 }
 
 // Tyre of wheel I: slips -> combined-slip Pacejka friction -> forces in the chassis frame.
-template <typename R, int I, bool REAR0>
+// TY1: all four tyres share one (B, C) pair -- read entry 0 so the kernel carries 2 constants, not 8.
+template <typename R, int I, bool REAR0, bool TY1>
 B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd, R sd, R Fz,
                             R &fx, R &fy, R &fxt, R &fyt, R &s)
 {
+    constexpr int J = TY1 ? 0 : I;
     typedef Math<R> M;
     R vx, vy;
     if (REAR0 && I >= 2) {
@@ -114,7 +116,7 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
     const bool slipping = q != (R)0;
     const R rs = M::rsqrt(q);
     s = slipping ? q * rs : (R)0;        // sqrt(q); rsqrt(0) = inf must not leak into s
-    const R mu = D * M::sin(P.Cc[I] * M::atan(P.Bc[I] * s));   // :303-306
+    const R mu = D * M::sin(P.Cc[J] * M::atan(P.Bc[J] * s));   // :303-306
     const R g = slipping ? mu * rs : (R)0;                     // :309-348 (zero slip -> zero friction)
     fxt = (sx * g) * Fz;                 // :351-360
     fyt = (sy * g) * Fz;
@@ -127,22 +129,23 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
     }
 }
 
-// y8 = [U V wz wFL wFR wRL wRR yaw].  k[10] receives the derivative of the full 10-state
-// (k[7] = wz, k[8] = x_dot, k[9] = y_dot).  out (AUX only) = the reference's 18 "outputs".
-template <typename R, bool REAR0, bool AUX>
-B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], const WheelCtrl<R> &c,
+// y8 = [U V wz wFL wFR wRL wRR yaw]; sy, cy = sin / cos of the heading y8[7] (supplied by the caller,
+// which gets the four stage headings of a step from one sincos plus small-angle rotations).
+// k[10] receives the derivative of the full 10-state (k[7] = wz, k[8] = x_dot, k[9] = y_dot).
+// out (AUX only) = the reference's 18 "outputs".
+template <typename R, bool REAR0, bool AUX, bool TY1>
+B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R sy, R cy, const WheelCtrl<R> &c,
                           const R Fz[4], R k[10], R &axc, R &ayc, R *out)
 {
-    typedef Math<R> M;
     const R U = y8[0], V = y8[1], wz = y8[2];
     const R hw = P.halfT * wz;                       // :261-271
     const R vxL = U - hw, vxR = U + hw;
     const R vyF = V + P.a * wz, vyR = V - P.b * wz;
     R fx[4], fy[4], fxt[4], fyt[4], s[4];
-    wheel_forces<R, 0, REAR0>(P, D[0], vxL, vyF, y8[3], c.cd[0], c.sd[0], Fz[0], fx[0], fy[0], fxt[0], fyt[0], s[0]);
-    wheel_forces<R, 1, REAR0>(P, D[1], vxR, vyF, y8[4], c.cd[1], c.sd[1], Fz[1], fx[1], fy[1], fxt[1], fyt[1], s[1]);
-    wheel_forces<R, 2, REAR0>(P, D[2], vxL, vyR, y8[5], c.cd[2], c.sd[2], Fz[2], fx[2], fy[2], fxt[2], fyt[2], s[2]);
-    wheel_forces<R, 3, REAR0>(P, D[3], vxR, vyR, y8[6], c.cd[3], c.sd[3], Fz[3], fx[3], fy[3], fxt[3], fyt[3], s[3]);
+    wheel_forces<R, 0, REAR0, TY1>(P, D[TY1 ? 0 : 0], vxL, vyF, y8[3], c.cd[0], c.sd[0], Fz[0], fx[0], fy[0], fxt[0], fyt[0], s[0]);
+    wheel_forces<R, 1, REAR0, TY1>(P, D[TY1 ? 0 : 1], vxR, vyF, y8[4], c.cd[1], c.sd[1], Fz[1], fx[1], fy[1], fxt[1], fyt[1], s[1]);
+    wheel_forces<R, 2, REAR0, TY1>(P, D[TY1 ? 0 : 2], vxL, vyR, y8[5], c.cd[2], c.sd[2], Fz[2], fx[2], fy[2], fxt[2], fyt[2], s[2]);
+    wheel_forces<R, 3, REAR0, TY1>(P, D[TY1 ? 0 : 3], vxR, vyR, y8[6], c.cd[3], c.sd[3], Fz[3], fx[3], fy[3], fxt[3], fyt[3], s[3]);
 
     const R Vwz = V * wz, Uwz = U * wz;
     const R U_dot = P.inv_m * (fx[0] + fx[1] + fx[2] + fx[3]) + Vwz;     // :376-378
@@ -155,8 +158,6 @@ B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], co
     k[5] = (c.tq[2] - P.rw * fx[2]) * P.inv_Jw;   // chassis-frame force on the rear axle, as the reference
     k[6] = (c.tq[3] - P.rw * fx[3]) * P.inv_Jw;
     k[7] = wz;                                                            // :383-385
-    R sy, cy;
-    M::sincos(y8[7], &sy, &cy);
     k[8] = U * cy - V * sy;
     k[9] = U * sy + V * cy;
     axc = U_dot - Vwz;                                                    // :413-414
@@ -176,16 +177,21 @@ B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], co
 // One classic RK4 step (:427-445).  y[10] is advanced in place; ax, ay hold ax_prev, ay_prev on entry
 // and the RK4-averaged axc, ayc on exit (the next step's ax_prev, ay_prev, drive.py:141).
 // With AUX, sdot[10] and outs[18] receive the RK4-weighted means the reference returns (:440-441).
-template <typename R, bool REAR0, bool AUX>
+template <typename R, bool REAR0, bool AUX, bool TY1>
 B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> &c, R h, R y[10], R &ax, R &ay,
                         R *sdot, R *outs)
 {
+    typedef Math<R> M;
     R Fz[4];
     normal_loads(P, ax, ay, Fz);
     R acc[10], ys[8], k[10], o[AUX ? 18 : 1], axc, ayc, sax, say;
     const R h2 = h * (R)0.5;
+    // heading trigonometry: one sincos per step; the three later stage headings are yaw + e with
+    // e = h/2*wz or h*wz (tiny), obtained by a small-angle rotation of (s0, c0)
+    R s0, c0, sj, cj;
+    M::sincos(y[7], &s0, &c0);
 
-    planar_rhs<R, REAR0, AUX>(P, D, y, c, Fz, k, axc, ayc, o);
+    planar_rhs<R, REAR0, AUX, TY1>(P, D, y, s0, c0, c, Fz, k, axc, ayc, o);
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] = k[i];
 #pragma unroll
@@ -194,8 +200,9 @@ B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> 
     say = ayc;
     if (AUX)
         for (int i = 0; i < 18; ++i) outs[i] = o[i];
+    if (!M::rotate_small(s0, c0, h2 * k[7], &sj, &cj)) M::sincos(ys[7], &sj, &cj);
 
-    planar_rhs<R, REAR0, AUX>(P, D, ys, c, Fz, k, axc, ayc, o);
+    planar_rhs<R, REAR0, AUX, TY1>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o);
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] += (R)2 * k[i];
 #pragma unroll
@@ -204,8 +211,9 @@ B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> 
     say += (R)2 * ayc;
     if (AUX)
         for (int i = 0; i < 18; ++i) outs[i] += (R)2 * o[i];
+    if (!M::rotate_small(s0, c0, h2 * k[7], &sj, &cj)) M::sincos(ys[7], &sj, &cj);
 
-    planar_rhs<R, REAR0, AUX>(P, D, ys, c, Fz, k, axc, ayc, o);
+    planar_rhs<R, REAR0, AUX, TY1>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o);
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] += (R)2 * k[i];
 #pragma unroll
@@ -214,8 +222,9 @@ B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> 
     say += (R)2 * ayc;
     if (AUX)
         for (int i = 0; i < 18; ++i) outs[i] += (R)2 * o[i];
+    if (!M::rotate_small(s0, c0, h * k[7], &sj, &cj)) M::sincos(ys[7], &sj, &cj);
 
-    planar_rhs<R, REAR0, AUX>(P, D, ys, c, Fz, k, axc, ayc, o);
+    planar_rhs<R, REAR0, AUX, TY1>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o);
     const R h6 = (R)(1.0 / 6) * h;       // :438  state + 1/6*h*(K1+2K2+2K3+K4)
     const R sixth = (R)(1.0 / 6);
 #pragma unroll
