@@ -55,6 +55,23 @@ int ensure_scratch(int device, size_t bytes, void **out)
     return 0;
 }
 
+int acquire_sched_slot(int device, void **area, cudaEvent_t *done)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceState &ds = dev_state(device);
+    if (!ds.sched_ring) {
+        B200MP_CUDA(cudaMalloc(&ds.sched_ring, kSchedSlots * kSchedSlotBytes));
+        for (int i = 0; i < kSchedSlots; ++i) B200MP_CUDA(cudaEventCreateWithFlags(&ds.sched_event[i], cudaEventDisableTiming));
+    }
+    const int slot = ds.sched_next;
+    ds.sched_next = (slot + 1) % kSchedSlots;
+    if (ds.sched_used[slot]) B200MP_CUDA(cudaEventSynchronize(ds.sched_event[slot]));   // 32 launches ago: long done
+    ds.sched_used[slot] = true;
+    *area = (char *)ds.sched_ring + (size_t)slot * kSchedSlotBytes;
+    *done = ds.sched_event[slot];
+    return 0;
+}
+
 DeviceGuard::DeviceGuard(int device)
 {
     int n = 0;
@@ -238,12 +255,16 @@ int b200mp_shutdown(void)
     (void)cudaGetDevice(&prev);
     for (int d = 0; d < n && d < kMaxDevices; ++d) {
         DeviceState &ds = g_states[d];
-        if (!ds.table64 && !ds.table32 && !ds.scratch) continue;
+        if (!ds.table64 && !ds.table32 && !ds.scratch && !ds.sched_ring) continue;
         if (cudaSetDevice(d) != cudaSuccess) continue;
         (void)cudaDeviceSynchronize();
         if (ds.table64) (void)cudaFree(ds.table64);
         if (ds.table32) (void)cudaFree(ds.table32);
         if (ds.scratch) (void)cudaFree(ds.scratch);
+        if (ds.sched_ring) {
+            (void)cudaFree(ds.sched_ring);
+            for (int i = 0; i < kSchedSlots; ++i) (void)cudaEventDestroy(ds.sched_event[i]);
+        }
         ds = DeviceState{};
     }
     if (prev >= 0) (void)cudaSetDevice(prev);

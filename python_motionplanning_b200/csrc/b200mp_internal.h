@@ -9,6 +9,8 @@
 namespace b200mp {
 
 constexpr int kMaxDevices = 64;
+constexpr int kSchedSlots = 32;
+constexpr size_t kSchedSlotBytes = 64 * 1024;   // counter + one int per rollout block of a sliced launch
 
 // printf-style message for b200mp_last_error() (thread-local)
 void set_error(const char *fmt, ...);
@@ -29,9 +31,17 @@ struct DeviceState {
     DevParams<float> *table32 = nullptr;
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    // ring of small work-queue areas for time-sliced rollout launches (one per launch in flight)
+    void *sched_ring = nullptr;
+    cudaEvent_t sched_event[kSchedSlots] = {};
+    bool sched_used[kSchedSlots] = {};
+    int sched_next = 0;
 };
 DeviceState &dev_state(int device);
 int ensure_scratch(int device, size_t bytes, void **out);
+// A zero-initialisable kSchedSlotBytes device area that no launch still in flight is using; the caller
+// records `*done` on its stream after the launch that uses the area.
+int acquire_sched_slot(int device, void **area, cudaEvent_t *done);
 
 // Sets `device` current for the scope of an ABI call and restores the caller's device afterwards.
 class DeviceGuard {

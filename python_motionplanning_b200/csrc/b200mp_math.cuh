@@ -9,8 +9,8 @@
 //   * keep every polynomial coefficient in __constant__ memory, so it is a constant-bank operand of the
 //     DFMA itself (no UMOV, no load, no register),
 //   * are branch-free on their whole working range,
-//   * take the hardware seeds MUFU.RCP64H / MUFU.RSQ64H plus two Newton steps for 1/x and 1/sqrt(x)
-//     (1-2 ulp; no IEEE-rounding fix-up code),
+//   * take the hardware seeds MUFU.RCP64H / MUFU.RSQ64H plus one third-order correction step for 1/x
+//     and 1/sqrt(x) (1-2 ulp; no IEEE-rounding fix-up code),
 //   * use argument ranges the model guarantees (atan of a real, sin of C*atan(.), sincos of a heading).
 // Accuracy of each scheme is ~1-2 ulp (tools/gen_poly.py prints the measured bounds), three orders of
 // magnitude inside the 1e-9 parity contract.
@@ -72,10 +72,10 @@ template <> struct Math<double> {
 #if defined(__CUDA_ARCH__)
         double y;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-        double e = fma(-x, y, 1.0);
-        y = fma(y, e, y);
-        e = fma(-x, y, 1.0);
-        return fma(y, e, y);
+        // one third-order step: 1/x = y (1 + e + e^2 + ...), e = 1 - x y ~ 2^-23  ->  error ~ e^3
+        const double e = fma(-x, y, 1.0);
+        const double t = fma(e, e, e);
+        return fma(y, t, y);
 #else
         return 1.0 / x;
 #endif
@@ -86,11 +86,10 @@ template <> struct Math<double> {
 #if defined(__CUDA_ARCH__)
         double y;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
-        const double h = 0.5 * q;
-        double e = fma(-h * y, y, 0.5);
-        y = fma(y, e, y);
-        e = fma(-h * y, y, 0.5);
-        return fma(y, e, y);
+        // one third-order step: q^-1/2 = y (1 - e)^-1/2 = y (1 + e/2 + 3 e^2/8 + ...), e = 1 - q y^2
+        const double e = fma(-(q * y), y, 1.0);
+        const double t = fma(e, 0.375, 0.5);
+        return fma(y, t * e, y);
 #else
         return 1.0 / ::sqrt(q);
 #endif

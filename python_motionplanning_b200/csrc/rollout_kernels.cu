@@ -16,6 +16,30 @@
 
 namespace b200mp {
 
+// Time-sliced scheduling.  Every thread's work is identical, so a batch whose warp count is not a
+// multiple of what the GPU holds at once ends in a tail wave at low occupancy (65,536 rollouts at 12
+// warps per SM = 1.15 waves: the last 15 % of the blocks run alone for a full rollout).  Rollouts are
+// resumable, so instead the launch is cut into (block, time-chunk) items, one CTA each, claimed through
+// an atomic ticket in chunk-major order; item (b, c) starts once done[b] == c, carrying the state
+// through state_end (and the running cost through cost).  An item's predecessor was always claimed
+// earlier by a CTA that is already running, so waiting cannot deadlock.
+struct SliceSched {
+    int *counter;   // next item to claim
+    int *done;      // [n_blocks] chunks completed per rollout block
+    int n_blocks, n_chunks, chunk;
+};
+
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <typename R> struct RolloutDev {
     int B, n_steps, step0, hold, store_stride, torque_ch;
     R dt;
@@ -44,93 +68,195 @@ constexpr int kRolloutBlock = B200MP_ROLLOUT_BLOCK;
 #define B200MP_ROLLOUT_BOUNDS __launch_bounds__(B200MP_ROLLOUT_BLOCK)
 #endif
 
-template <typename R, bool REAR0, bool GENERIC, bool AUX>
+// SLICED = false: one CTA = one rollout block for the whole launch (no queue code in the kernel at all).
+template <typename R, bool REAR0, bool GENERIC, bool AUX, bool SLICED>
 __global__ void B200MP_ROLLOUT_BOUNDS
-rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constant__ DevParams<R> P0)
+rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constant__ DevParams<R> P0,
+                   const __grid_constant__ SliceSched sc)
 {
-    const int r = blockIdx.x * kRolloutBlock + threadIdx.x;
-    if (r >= a.B) return;
+    __shared__ int s_item;
     const size_t B = (size_t)a.B;
-
-    R y[10], ax, ay;
-#pragma unroll
-    for (int c = 0; c < 10; ++c) y[c] = a.state0[c * B + r];
-    ax = a.state0[10 * B + r];
-    ay = a.state0[11 * B + r];
-
-    // parameters: constant bank (P0) or a per-rollout gather
-    DevParams<R> Pl;
-    R Dl[4];
-    if (GENERIC) {
-        Pl = a.param_set ? a.table[a.param_set[r]] : P0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) Dl[i] = a.mu ? a.mu[i * B + r] : Pl.Dc[i];   // vehicle_model.py:232-235
-    }
-    const DevParams<R> &P = GENERIC ? Pl : P0;
-    const R *D = GENERIC ? Dl : P0.Dc;
-
-    const size_t cb = a.ctrl_bstride;
-    const size_t rc = cb ? (size_t)r : 0;
-    const size_t cB = cb ? B : 1;
-    R J = (a.cost && a.cost_in) ? a.cost_in[r] : (R)0;
-
-    R *tp = a.traj ? a.traj + r : nullptr;
-    R *xp = (AUX && a.aux) ? a.aux + r : nullptr;
-    int until_store = a.store_stride;
-
-    WheelCtrl<R> c;
-    int n = 0;
-    while (n < a.n_steps) {
-        const int seg = (a.step0 + n) / a.hold;
-        int seg_end = (seg + 1) * a.hold - a.step0;
-        if (seg_end > a.n_steps) seg_end = a.n_steps;
-        {   // controls of this segment
-            R dl[4];
-            if (REAR0) {
-                dl[0] = a.delta[(size_t)seg * cB + rc];
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dl[i] = a.delta[((size_t)seg * 4 + i) * cB + rc];
-            }
-            set_steer<R, REAR0>(c, dl);
-            if (a.torque_ch == 1) {
-                c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = a.torque[(size_t)seg * cB + rc];
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) c.tq[i] = a.torque[((size_t)seg * 4 + i) * cB + rc];
-            }
+    int item = blockIdx.x;
+    {
+        if (SLICED) {
+            // one CTA per (block, chunk) item; items are claimed through a ticket so that an item's
+            // predecessor is always held by a CTA that is already running (dispatch order is not relied on)
+            if (threadIdx.x == 0) s_item = atomicAdd(sc.counter, 1);
+            __syncthreads();
+            item = s_item;
         }
-#pragma unroll 1
-        for (; n < seg_end; ++n) {
-            R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
-            rk4_step<R, REAR0, AUX, !GENERIC>(P, D, c, a.dt, y, ax, ay, sdot, outs);
+        const int chunk_idx = SLICED ? item / sc.n_blocks : 0;
+        const int blk = SLICED ? item - chunk_idx * sc.n_blocks : item;
+        const int n_begin = SLICED ? chunk_idx * sc.chunk : 0;
+        const int n_end = SLICED ? min(a.n_steps, n_begin + sc.chunk) : a.n_steps;
+        if (SLICED && chunk_idx > 0) {   // wait for this block's previous time-chunk
+            if (threadIdx.x == 0)
+                while (ld_acquire(sc.done + blk) < chunk_idx) __nanosleep(100);
+            __syncthreads();
+        }
+        const int r = blk * kRolloutBlock + threadIdx.x;
+        if (r < a.B) {
+            R y[10], ax, ay;
+            if (!SLICED || chunk_idx == 0) {
+#pragma unroll
+                for (int c = 0; c < 10; ++c) y[c] = a.state0[c * B + r];
+                ax = a.state0[10 * B + r];
+                ay = a.state0[11 * B + r];
+            } else {   // carried state, written by another SM: read through L2
+#pragma unroll
+                for (int c = 0; c < 10; ++c) y[c] = __ldcg(a.state_end + c * B + r);
+                ax = __ldcg(a.state_end + 10 * B + r);
+                ay = __ldcg(a.state_end + 11 * B + r);
+            }
+
+            // parameters: constant bank (P0) or a per-rollout gather
+            DevParams<R> Pl;
+            R Dl[4];
+            if (GENERIC) {
+                Pl = a.param_set ? a.table[a.param_set[r]] : P0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) Dl[i] = a.mu ? a.mu[i * B + r] : Pl.Dc[i];   // vehicle_model.py:232-235
+            }
+            const DevParams<R> &P = GENERIC ? Pl : P0;
+            const R *D = GENERIC ? Dl : P0.Dc;
+
+            const size_t cb = a.ctrl_bstride;
+            const size_t rc = cb ? (size_t)r : 0;
+            const size_t cB = cb ? B : 1;
+            R J = (R)0;
             if (a.cost) {
-                const size_t g = (size_t)(a.step0 + n);
-                const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;
-                J = J + (ex * ex + ey * ey + a.w_u * (eu * eu));
+                if (SLICED && chunk_idx > 0)
+                    J = __ldcg(a.cost + r);
+                else if (a.cost_in)
+                    J = a.cost_in[r];
             }
-            if (a.store_stride > 0 && --until_store == 0) {
-                until_store = a.store_stride;
-                if (tp) {
+
+            const size_t out0 = a.store_stride > 0 ? (size_t)(n_begin / a.store_stride) : 0;
+            R *tp = a.traj ? a.traj + out0 * 10 * B + r : nullptr;
+            R *xp = (AUX && a.aux) ? a.aux + out0 * 28 * B + r : nullptr;
+            int until_store = a.store_stride;
+
+            WheelCtrl<R> c;
+            int n = n_begin;
+            while (n < n_end) {
+                const int seg = (a.step0 + n) / a.hold;
+                int seg_end = (seg + 1) * a.hold - a.step0;
+                if (seg_end > n_end) seg_end = n_end;
+                {   // controls of this segment
+                    R dl[4];
+                    if (REAR0) {
+                        dl[0] = a.delta[(size_t)seg * cB + rc];
+                    } else {
 #pragma unroll
-                    for (int cidx = 0; cidx < 10; ++cidx) tp[cidx * B] = y[cidx];
-                    tp += 10 * B;
+                        for (int i = 0; i < 4; ++i) dl[i] = a.delta[((size_t)seg * 4 + i) * cB + rc];
+                    }
+                    set_steer<R, REAR0>(c, dl);
+                    if (a.torque_ch == 1) {
+                        c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = a.torque[(size_t)seg * cB + rc];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) c.tq[i] = a.torque[((size_t)seg * 4 + i) * cB + rc];
+                    }
                 }
-                if (AUX && xp) {
+#pragma unroll 1
+                for (; n < seg_end; ++n) {
+                    R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
+                    rk4_step<R, REAR0, AUX, !GENERIC>(P, D, c, a.dt, y, ax, ay, sdot, outs);
+                    if (a.cost) {
+                        const size_t g = (size_t)(a.step0 + n);
+                        const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;
+                        J = J + (ex * ex + ey * ey + a.w_u * (eu * eu));
+                    }
+                    if (a.store_stride > 0 && --until_store == 0) {
+                        until_store = a.store_stride;
+                        if (tp) {
 #pragma unroll
-                    for (int cidx = 0; cidx < 10; ++cidx) xp[cidx * B] = sdot[cidx];
+                            for (int cidx = 0; cidx < 10; ++cidx) tp[cidx * B] = y[cidx];
+                            tp += 10 * B;
+                        }
+                        if (AUX && xp) {
 #pragma unroll
-                    for (int cidx = 0; cidx < 18; ++cidx) xp[(10 + cidx) * B] = outs[cidx];
-                    xp += 28 * B;
+                            for (int cidx = 0; cidx < 10; ++cidx) xp[cidx * B] = sdot[cidx];
+#pragma unroll
+                            for (int cidx = 0; cidx < 18; ++cidx) xp[(10 + cidx) * B] = outs[cidx];
+                            xp += 28 * B;
+                        }
+                    }
                 }
             }
+#pragma unroll
+            for (int cidx = 0; cidx < 10; ++cidx) a.state_end[cidx * B + r] = y[cidx];
+            a.state_end[10 * B + r] = ax;
+            a.state_end[11 * B + r] = ay;
+            if (a.cost) a.cost[r] = J;
+        }
+        if (SLICED && chunk_idx + 1 < sc.n_chunks) {   // publish the carried state of this block
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release(sc.done + blk, chunk_idx + 1);
         }
     }
-#pragma unroll
-    for (int cidx = 0; cidx < 10; ++cidx) a.state_end[cidx * B + r] = y[cidx];
-    a.state_end[10 * B + r] = ax;
-    a.state_end[11 * B + r] = ay;
-    if (a.cost) a.cost[r] = J;
+}
+
+// Resident CTAs per device for one kernel instantiation (cached per function pointer).
+template <typename K> static int resident_ctas(K kernel, int *out)
+{
+    int dev = 0, sms = 0, occ = 0;
+    B200MP_CUDA(cudaGetDevice(&dev));
+    B200MP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    B200MP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kRolloutBlock, 0));
+    *out = sms * (occ > 0 ? occ : 1);
+    return 0;
+}
+
+// Chooses the time slicing of a launch (see SliceSched) and starts the kernel.
+template <typename R, typename K>
+static int start_rollout(K kernel, K kernel_sliced, int device, cudaStream_t st, const RolloutDev<R> &a,
+                         const DevParams<R> &P0)
+{
+    const int n_blocks = (a.B + kRolloutBlock - 1) / kRolloutBlock;
+    int resident = 0;
+    int rc = resident_ctas(kernel_sliced, &resident);
+    if (rc) return rc;
+    SliceSched sc{nullptr, nullptr, n_blocks, 1, a.n_steps};
+    // slice only when the batch is more than one wave but too few waves for the tail to vanish
+    const int min_chunk = 20;
+    const size_t sched_bytes = sizeof(int) * ((size_t)n_blocks + 1);
+    if (n_blocks > resident && n_blocks < 8 * resident && a.n_steps >= 2 * min_chunk && sched_bytes <= kSchedSlotBytes) {
+        long long want = (12LL * resident + n_blocks - 1) / n_blocks;      // ~12 rounds of items
+        long long max_chunks = a.n_steps / min_chunk;
+        if (want > max_chunks) want = max_chunks;
+        int chunk = (int)((a.n_steps + want - 1) / want);
+        if (a.hold > 1 && a.hold < chunk) chunk = (chunk + a.hold - 1) / a.hold * a.hold;   // whole ZOH segments
+        if (a.store_stride > 1) chunk = (chunk + a.store_stride - 1) / a.store_stride * a.store_stride;
+        const int n_chunks = (a.n_steps + chunk - 1) / chunk;
+        if (n_chunks > 1) {
+            sc.n_chunks = n_chunks;
+            sc.chunk = chunk;
+        }
+    }
+    int grid = n_blocks;
+    void *sched_mem = nullptr;
+    cudaEvent_t sched_done = nullptr;
+    if (sc.n_chunks > 1) {
+        rc = acquire_sched_slot(device, &sched_mem, &sched_done);
+        if (rc) return rc;
+        B200MP_CUDA(cudaMemsetAsync(sched_mem, 0, sched_bytes, st));
+        sc.counter = (int *)sched_mem;
+        sc.done = (int *)sched_mem + 1;
+        grid = n_blocks * sc.n_chunks;
+    }
+    if (sc.n_chunks > 1)
+        kernel_sliced<<<grid, kRolloutBlock, 0, st>>>(a, P0, sc);
+    else
+        kernel<<<grid, kRolloutBlock, 0, st>>>(a, P0, sc);
+    cudaError_t e = cudaGetLastError();
+    if (sched_mem) {
+        cudaError_t e2 = cudaEventRecord(sched_done, st);
+        if (e == cudaSuccess) e = e2;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "rk4_rollout_kernel launch");
+    return 0;
 }
 
 template <typename R>
@@ -201,26 +327,16 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
                         ds.set0.D[i] == ds.set0.D[0];
     const bool generic = g.mu != nullptr || g.param_set != nullptr || !uniform_tyres;
     const bool aux = g.aux != nullptr;
-    const dim3 grid((unsigned)((g.B + kRolloutBlock - 1) / kRolloutBlock)), block(kRolloutBlock);
     if (aux) {
         // logging mode (state_dot + outputs): one generic instantiation per steer layout
-        if (rear0)
-            rk4_rollout_kernel<R, true, true, true><<<grid, block, 0, st>>>(a, P0);
-        else
-            rk4_rollout_kernel<R, false, true, true><<<grid, block, 0, st>>>(a, P0);
-    } else if (rear0) {
-        if (generic)
-            rk4_rollout_kernel<R, true, true, false><<<grid, block, 0, st>>>(a, P0);
-        else
-            rk4_rollout_kernel<R, true, false, false><<<grid, block, 0, st>>>(a, P0);
-    } else {
-        if (generic)
-            rk4_rollout_kernel<R, false, true, false><<<grid, block, 0, st>>>(a, P0);
-        else
-            rk4_rollout_kernel<R, false, false, false><<<grid, block, 0, st>>>(a, P0);
+        return rear0 ? start_rollout<R>(rk4_rollout_kernel<R, true, true, true, false>, rk4_rollout_kernel<R, true, true, true, true>, device, st, a, P0)
+                     : start_rollout<R>(rk4_rollout_kernel<R, false, true, true, false>, rk4_rollout_kernel<R, false, true, true, true>, device, st, a, P0);
     }
-    B200MP_CUDA(cudaGetLastError());
-    return 0;
+    if (rear0)
+        return generic ? start_rollout<R>(rk4_rollout_kernel<R, true, true, false, false>, rk4_rollout_kernel<R, true, true, false, true>, device, st, a, P0)
+                       : start_rollout<R>(rk4_rollout_kernel<R, true, false, false, false>, rk4_rollout_kernel<R, true, false, false, true>, device, st, a, P0);
+    return generic ? start_rollout<R>(rk4_rollout_kernel<R, false, true, false, false>, rk4_rollout_kernel<R, false, true, false, true>, device, st, a, P0)
+                   : start_rollout<R>(rk4_rollout_kernel<R, false, false, false, false>, rk4_rollout_kernel<R, false, false, false, true>, device, st, a, P0);
 }
 
 int launch_rollout_f64(int device, cudaStream_t st, const B200mpRolloutArgs &a) { return launch_rollout<double>(device, st, a); }

@@ -118,8 +118,9 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
     s = slipping ? q * rs : (R)0;        // sqrt(q); rsqrt(0) = inf must not leak into s
     const R mu = D * M::sin(P.Cc[J] * M::atan(P.Bc[J] * s));   // :303-306
     const R g = slipping ? mu * rs : (R)0;                     // :309-348 (zero slip -> zero friction)
-    fxt = (sx * g) * Fz;                 // :351-360
-    fyt = (sy * g) * Fz;
+    const R gF = g * Fz;                 // :351-360  mu_x*Fz = sx*(mu/s)*Fz
+    fxt = sx * gF;
+    fyt = sy * gF;
     if (REAR0 && I >= 2) {
         fx = fxt;
         fy = fyt;
