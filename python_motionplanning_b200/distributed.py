@@ -36,6 +36,17 @@ def shard_sets(n_sets: int, rank: int, world_size: int) -> Tuple[int, int]:
     return shard_range(n_sets, rank, world_size)
 
 
+def pick_winner(pairs) -> Tuple[float, int, int]:
+    """Lowest-index argmin over per-rank ``(min cost, global index)`` pairs -> ``(cost, index, owner_rank)``."""
+    best_cost, best_idx, owner = float("inf"), -1, -1
+    for r, (c, i) in enumerate(pairs):
+        if i < 0 or c != c:
+            continue
+        if c < best_cost or (c == best_cost and i < best_idx):
+            best_cost, best_idx, owner = c, i, r
+    return best_cost, best_idx, owner
+
+
 def global_argmin(local_min: torch.Tensor, local_idx: torch.Tensor, group=None) -> Tuple[float, int, int]:
     """Combine per-rank ``(min cost, GLOBAL index)`` pairs into the global winner.
 
@@ -53,14 +64,7 @@ def global_argmin(local_min: torch.Tensor, local_idx: torch.Tensor, group=None) 
         dist.all_gather(buf, pair, group=group)
         allp = torch.stack(buf)
     allp = allp.cpu()
-    best_cost, best_idx, owner = float("inf"), -1, -1
-    for r in range(allp.shape[0]):
-        c, i = float(allp[r, 0]), int(allp[r, 1])
-        if i < 0 or c != c:
-            continue
-        if c < best_cost or (c == best_cost and i < best_idx):
-            best_cost, best_idx, owner = c, i, r
-    return best_cost, best_idx, owner
+    return pick_winner([(float(allp[r, 0]), int(allp[r, 1])) for r in range(allp.shape[0])])
 
 
 def broadcast_from(t: torch.Tensor, owner: int, group=None) -> torch.Tensor:
