@@ -147,6 +147,15 @@ int b200mp_collision_check_f64(int device, void *stream, int P, int n_pts, int n
                                const double *psin, const double *pyaw, int yaw_stride, int M, const double *obs,
                                unsigned char *free_out, double *min_clear);
 
+/* Arithmetic of the boolean-only collision test (min_clear == NULL).  AUTO (default): every circle/point
+ * pair is screened in FP32 with a proven error bound and only undecided pairs repeat the exact FP64
+ * sequence above -- the flags are bit-identical to FP64_ONLY for every input, the FP64 pipe is simply not
+ * spent on pairs single precision already decides.  FP64_ONLY forces the all-FP64 kernel (A/B checks).
+ * Process-wide; returns the previous mode, or B200MP_E_ARG. */
+#define B200MP_COLLISION_AUTO 0
+#define B200MP_COLLISION_FP64_ONLY 1
+int b200mp_set_collision_mode(int mode);
+
 /* select_best_path_index on the path end points (collision_checker.py:134-203):
  *   score_i = norm([ex_i-gx, ey_i-gy]) + sum over colliding j (ascending) of weight*norm([ex_i-ex_j, ey_i-ey_j])
  * colliding i -> +inf; first strict minimum wins; best_out[0] = -1 for the reference's None.

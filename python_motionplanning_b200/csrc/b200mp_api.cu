@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "b200mp_internal.h"
@@ -31,6 +32,9 @@ int cuda_fail(cudaError_t e, const char *what)
 
 static DeviceState g_states[kMaxDevices];
 static std::mutex g_mutex;
+
+static std::atomic<int> g_collision_mode{B200MP_COLLISION_AUTO};
+int collision_mode() { return g_collision_mode.load(std::memory_order_relaxed); }
 
 DeviceState &dev_state(int device) { return g_states[(device >= 0 && device < kMaxDevices) ? device : 0]; }
 
@@ -226,6 +230,16 @@ int b200mp_collision_check_f64(int device, void *stream, int P, int n_pts, int n
     B200MP_ENTER(device);
     return launch_collision_f64(device, (cudaStream_t)stream, P, n_pts, n_circ, off, rad, px, py, pcos, psin, pyaw,
                                 yaw_stride, M, obs, free_out, min_clear);
+}
+
+int b200mp_set_collision_mode(int mode)
+{
+    g_err[0] = 0;
+    if (mode != B200MP_COLLISION_AUTO && mode != B200MP_COLLISION_FP64_ONLY) {
+        set_error("set_collision_mode: unknown mode %d", mode);
+        return B200MP_E_ARG;
+    }
+    return g_collision_mode.exchange(mode);
 }
 
 int b200mp_select_best_f64(int device, void *stream, int P, const double *ex, const double *ey,

@@ -43,6 +43,9 @@ int ensure_scratch(int device, size_t bytes, void **out);
 // records `*done` on its stream after the launch that uses the area.
 int acquire_sched_slot(int device, void **area, cudaEvent_t *done);
 
+// B200MP_COLLISION_* (process-wide, b200mp_set_collision_mode)
+int collision_mode();
+
 // Sets `device` current for the scope of an ABI call and restores the caller's device afterwards.
 class DeviceGuard {
   public:

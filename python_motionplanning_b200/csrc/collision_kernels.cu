@@ -102,6 +102,211 @@ collision_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, 
     if (CLEAR && t < n_items) clear_pts[t] = clr;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K2 fast path: FP32 filter + exact FP64 recheck.  The verdict of a path is a boolean, so the FP64
+// arithmetic above is needed only for tests whose outcome single precision cannot decide.  Every
+// (circle, obstacle point) pair is first evaluated in FP32 on coordinates shifted to a common origin
+// (obs[0]); with
+//   A   = max |o - origin| over the obstacle tile (as stored in FP32), Ac = max |c - origin| of the thread,
+//   E0  = 2 u (A + Ac) (1 + 1e-6) + 1e-18,  u = 2^-24     (conversion errors of both points, both axes)
+//   d^  = sqrt(q32) (1 +- 4u)                              (FP32 subtract / multiply / FMA roundings)
+// the FP64 distance the exact test uses satisfies |d - d^| <= E0, hence
+//   q32 <  LO = ((r (1 - 2^-40) - E0) / (1 + 4u))^2  (rounded down)  =>  q64 <  T(r): certain collision
+//   q32 >= HI = ((r (1 + 2^-40) + E0) / (1 - 4u))^2  (rounded up)    =>  q64 >= T(r): certainly free
+// and only a thread whose per-circle minimum lands in [LO, HI) repeats its obstacle tile with the exact
+// FP64 sequence (a band a few 1e-5 m wide around each circle: ~1e-3 of the threads per tile on
+// BASELINE config 3).  Non-finite or huge coordinates make E0 non-finite/large, which sends the thread
+// to the exact path, so the result is bit-identical to collision_kernel for every input.
+// One CTA = 128 path points x one obstacle tile (grid.y = tiles): 5x more CTAs than tiles-in-a-loop,
+// which evens out the per-SM load once early-exiting paths drop out.
+constexpr int kFTile = 2048;
+
+#ifndef B200MP_COLLISION_PACKED
+#define B200MP_COLLISION_PACKED 1
+#endif
+__device__ __forceinline__ unsigned long long pack2(float a, float b)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float lo2(unsigned long long v)
+{
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float hi2(unsigned long long v)
+{
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+template <int NC>
+__device__ __noinline__ bool exact_tile_hit(const CircleSpec &cs, const double *cx, const double *cy,
+                                            const double2 *__restrict__ obs, int m_begin, int m_end)
+{
+    bool hit = false;
+    for (int o = m_begin; o < m_end; ++o) {
+        const double2 ob = obs[o];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const double dx = __dsub_rn(ob.x, cx[k]);
+            const double dy = __dsub_rn(ob.y, cy[k]);
+            hit |= __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < cs.thr[k];
+        }
+    }
+    return hit;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kColBlock)
+collision_filter_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, const double *__restrict__ px,
+                        const double *__restrict__ py, const double *__restrict__ pcos, const double *__restrict__ psin,
+                        const double *__restrict__ pyaw, int yaw_stride, int M, const double2 *__restrict__ obs,
+                        unsigned char *free_out)
+{
+    __shared__ __align__(16) float2 tile[kFTile];
+    __shared__ int s_amax;
+    const int t = blockIdx.x * kColBlock + threadIdx.x;
+    bool active = t < n_items;
+    const int p = active ? t / n_pts : 0;
+    const int m0 = blockIdx.y * kFTile;
+    const int m1 = min(kFTile, M - m0);
+    const int m1pad = (m1 + 7) & ~7;
+    const double2 org = obs[0];
+    if (threadIdx.x == 0) s_amax = 0;
+    if (active && ((volatile unsigned char *)free_out)[p] == 0) active = false;   // path already known to collide
+    if (!__syncthreads_or(active)) return;
+
+    // obstacle tile -> FP32 relative to the origin; padding points are far away from everything
+    float amax = 0.0f;
+    for (int i = threadIdx.x; i < m1pad; i += kColBlock) {
+        float2 v = make_float2(INFINITY, INFINITY);   // padding: q32 = +inf, never below a threshold
+        if (i < m1) {
+            const double2 o = obs[m0 + i];
+            v.x = (float)(o.x - org.x);
+            v.y = (float)(o.y - org.y);
+            amax = fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y)));   // a NaN point never hits in either precision
+        }
+#if B200MP_COLLISION_PACKED
+        float *tf = reinterpret_cast<float *>(tile);
+        tf[(i >> 1) * 4 + (i & 1)] = v.x;       // pair layout (xa, xb, ya, yb)
+        tf[(i >> 1) * 4 + 2 + (i & 1)] = v.y;
+#else
+        tile[i] = v;
+#endif
+    }
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, w));
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_amax, __float_as_int(amax));   // non-negative floats order as ints
+    __syncthreads();
+    if (!active) return;
+
+    double cx[NC], cy[NC];
+    float fx[NC], fy[NC], lo[NC], hi[NC];
+    {
+        const double x = px[t], y = py[t];
+        double c, s;
+        if (pcos) {
+            c = pcos[t];
+            s = psin[t];
+        } else {
+            sincos(pyaw[(size_t)p * yaw_stride + (t - p * n_pts)], &s, &c);
+        }
+        double ac = 0.0;
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            cx[k] = __dadd_rn(x, __dmul_rn(cs.off[k], c));
+            cy[k] = __dadd_rn(y, __dmul_rn(cs.off[k], s));
+            const double rx = cx[k] - org.x, ry = cy[k] - org.y;
+            fx[k] = (float)rx;
+            fy[k] = (float)ry;
+            const double m = fmax(fabs(rx), fabs(ry));
+            bad |= !(fabs(rx) <= 1.0e30) | !(fabs(ry) <= 1.0e30);   // NaN / Inf / beyond FP32 range (fmax drops NaNs)
+            ac = fmax(ac, m);
+        }
+        const double u = 5.9604644775390625e-08;   // 2^-24
+        const double e0 = 2.0 * u * ((double)__int_as_float(s_amax) + ac) * 1.000001 + 1.0e-18;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const double r = cs.rad[k];
+            // the screen is used only where it is sharp (error far below the radius) and nothing can overflow;
+            // otherwise hi = NaN makes every outcome "undecided" and the tile is evaluated exactly
+            const bool sharp = !bad && e0 < 0.25 * r && r < 1.0e15;
+            const double a = (r * (1.0 - 9.094947017729282e-13) - e0) / (1.0 + 4.0 * u);
+            const double b = (r * (1.0 + 9.094947017729282e-13) + e0) / (1.0 - 4.0 * u);
+            lo[k] = sharp ? __double2float_rd(a * a * (1.0 - 1.0e-15)) : 0.0f;
+            hi[k] = sharp ? __double2float_ru(b * b * (1.0 + 1.0e-15)) : __int_as_float(0x7fc00000);
+            if (!(r > 0.0)) hi[k] = 0.0f;   // r <= 0 or NaN: d >= 0 is never < r, nothing to decide
+        }
+    }
+    float mn[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) mn[k] = INFINITY;
+#if B200MP_COLLISION_PACKED
+    // two obstacle points per instruction (Blackwell packed FP32: add/mul/fma.f32x2); the tile stores
+    // obstacle pairs as (xa, xb, ya, yb)
+    unsigned long long ncx[NC], ncy[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        ncx[k] = pack2(-fx[k], -fx[k]);
+        ncy[k] = pack2(-fy[k], -fy[k]);
+    }
+    const float4 *tile4 = reinterpret_cast<const float4 *>(tile);
+#pragma unroll 2
+    for (int o = 0; o < m1pad / 2; ++o) {
+        const float4 ob = tile4[o];
+        const unsigned long long X = pack2(ob.x, ob.y), Y = pack2(ob.z, ob.w);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const unsigned long long dx = add2(X, ncx[k]), dy = add2(Y, ncy[k]);
+            const unsigned long long q = fma2(dy, dy, mul2(dx, dx));
+            mn[k] = fminf(mn[k], fminf(lo2(q), hi2(q)));
+        }
+    }
+#else
+#pragma unroll 4
+    for (int o = 0; o < m1pad; ++o) {
+        const float2 ob = tile[o];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const float dx = ob.x - fx[k];
+            const float dy = ob.y - fy[k];
+            mn[k] = fminf(mn[k], fmaf(dy, dy, dx * dx));
+        }
+    }
+#endif
+    bool hit = false, undecided = false;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        hit |= mn[k] < lo[k];
+        undecided |= !(mn[k] >= hi[k]);
+    }
+    if (!hit && undecided) hit = exact_tile_hit<NC>(cs, cx, cy, obs, m0, m0 + m1);
+    if (hit) free_out[p] = 0;
+}
+
 __global__ void clearance_reduce_kernel(int P, int n_pts, const double *__restrict__ clear_pts, double *__restrict__ out)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,9 +331,13 @@ static int launch_collision_nc(int device, cudaStream_t st, int P, int n_pts, co
                                                               M, (const double2 *)obs, free_out, (double *)scratch);
         B200MP_CUDA(cudaGetLastError());
         clearance_reduce_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, n_pts, (const double *)scratch, min_clear);
-    } else {
+    } else if (collision_mode() == B200MP_COLLISION_FP64_ONLY) {
         collision_kernel<NC, false><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
                                                                M, (const double2 *)obs, free_out, nullptr);
+    } else {
+        const dim3 g2(grid, (M + kFTile - 1) / kFTile);
+        collision_filter_kernel<NC><<<g2, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride, M,
+                                                             (const double2 *)obs, free_out);
     }
     B200MP_CUDA(cudaGetLastError());
     return 0;

@@ -303,6 +303,17 @@ class Engine:
                                                   self._ptr(clr)), "b200mp_collision_check_f64")
         return (free, clr) if want_clearance else free
 
+    def set_collision_mode(self, mode: str) -> str:
+        """``"auto"`` (FP32 screen + exact FP64 recheck of undecided pairs; default) or ``"fp64"`` (all-FP64
+        kernel).  Both give bit-identical flags; process-wide.  Returns the previous mode."""
+        names = {"auto": 0, "fp64": 1}
+        if mode not in names:
+            raise ValueError(f"collision mode must be one of {sorted(names)}")
+        prev = self.lib.b200mp_set_collision_mode(names[mode])
+        if prev < 0:
+            check(prev, "b200mp_set_collision_mode")
+        return "fp64" if prev == 1 else "auto"
+
     def select_best_path_index_batch(self, end_x, end_y, free, goal_xy, weight: float, norm_mode: Optional[int] = None,
                                      want_scores: bool = False):
         """``select_best_path_index`` on end points; returns ``int`` or ``None`` (synchronises)."""

@@ -22,6 +22,15 @@ def _np(t):
     return t.cpu().numpy()
 
 
+@pytest.fixture(autouse=True, params=["auto", "fp64"])
+def collision_mode(request, engine):
+    """Every test runs through both arithmetic modes of the boolean kernel: the FP32-screened default and the
+    all-FP64 kernel must give the same bits."""
+    prev = engine.set_collision_mode(request.param)
+    yield request.param
+    engine.set_collision_mode(prev)
+
+
 def test_collision_subsample_vs_literal(engine, golden):
     g = golden("collision_cfg3_sub.npz")
     free = engine.collision_check_batch(g["px"], g["py"], g["pyaw"], g["obstacles"], OFF, RAD)
@@ -151,3 +160,78 @@ def test_collision_edge_cases(engine):
     assert _np(f).tolist() == [1, 1, 1]
     with pytest.raises(ValueError):
         engine.collision_check_batch(np.zeros((3, 4)), np.zeros((3, 4)), np.zeros((3, 4)), np.zeros((2, 2)), [0.0] * 9, [1.0] * 9)
+
+
+def _ring(rng, cx, cy, r, n, rel):
+    """n points at distance r*(1+rel_i) from (cx, cy) in random directions."""
+    th = rng.uniform(-np.pi, np.pi, n)
+    d = r * (1.0 + rel)
+    return np.stack([cx + d * np.cos(th), cy + d * np.sin(th)], axis=1)
+
+
+@pytest.mark.parametrize("scale_shift", [(1.0, 0.0), (1.0, 1.0e3), (1.0, 1.0e6), (1.0, 1.0e9), (1.0e-3, 0.0), (1.0e4, -3.0e7)])
+def test_collision_filter_adversarial_bands(engine, scale_shift):
+    """Obstacle points packed around the circle boundaries at every scale the FP32 screen has to get right:
+    a few FP64 ulps, around the FP32 rounding band (1e-8 .. 1e-4 relative), and clearly inside / outside."""
+    scale, shift = scale_shift
+    rng = np.random.default_rng(7)
+    w = wl.config3_lattice(P=256, M=64)
+    px, py, pyaw = w["px"] * scale + shift, w["py"] * scale + shift, w["pyaw"]
+    off = [o * scale for o in OFF]
+    rad = [r * scale for r in RAD]
+    P, n = px.shape
+    obs = []
+    rels = np.concatenate([np.arange(-8, 9) * 2.0 ** -52, [-1e-4, -1e-5, -1e-6, -1e-7, -1e-8, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4]])
+    for p in range(0, P, 2):                       # every second path gets boundary points; the others stay far from them
+        j = int(rng.integers(0, n))
+        k = int(rng.integers(0, 3))
+        c, s_ = np.cos(pyaw[p, j]), np.sin(pyaw[p, j])
+        cx, cy = px[p, j] + off[k] * c, py[p, j] + off[k] * s_
+        obs.append(_ring(rng, cx, cy, rad[k], len(rels), rng.permutation(rels)))
+    obs = np.concatenate(obs)
+    ref, _, _ = c_oracle.collision_check(px, py, pyaw, obs, off, rad)
+    got = _np(engine.collision_check_batch(px, py, pyaw, obs, off, rad)).astype(bool)
+    assert np.array_equal(got, ref)
+    assert 0 < ref.sum() < P                       # the case exercises both verdicts
+    # one path at a time as well (different tile / origin per call)
+    for p in range(0, 32):
+        ref1, _, _ = c_oracle.collision_check(px[p:p + 1], py[p:p + 1], pyaw[p:p + 1], obs, off, rad)
+        got1 = _np(engine.collision_check_batch(px[p:p + 1], py[p:p + 1], pyaw[p:p + 1], obs, off, rad)).astype(bool)
+        assert np.array_equal(got1, ref1), p
+
+
+def test_collision_filter_exceptional_values(engine):
+    """NaN / Inf / huge coordinates and degenerate radii: the screened kernel must fall back to the exact
+    sequence wherever single precision cannot bound its own error."""
+    rng = np.random.default_rng(11)
+    w = wl.config3_lattice(P=128, M=512)
+    px, py, pyaw, obs = w["px"].copy(), w["py"].copy(), w["pyaw"], w["obstacles"].copy()
+
+    def both(px, py, obs, off=OFF, rad=RAD, what=""):
+        ref, _, _ = c_oracle.collision_check(px, py, pyaw, obs, off, rad)
+        got = _np(engine.collision_check_batch(px, py, pyaw, obs, off, rad)).astype(bool)
+        assert np.array_equal(got, ref), f"{what}: {int((got != ref).sum())} flags differ"
+        return ref
+
+    base = both(px, py, obs)
+    assert 0 < base.sum() < len(base)
+    for bad in (np.nan, np.inf, -np.inf, 1.0e300, -1.0e39, 3.5e38):
+        o = obs.copy()
+        o[0, 0] = bad                                         # the shift origin itself is unusable
+        both(px, py, o, what=f"origin {bad}")
+        o = obs.copy()
+        o[rng.integers(1, len(o), 20), rng.integers(0, 2, 20)] = bad
+        both(px, py, o, what=f"obstacles {bad}")
+        x = px.copy()
+        x[rng.integers(0, 128, 10), rng.integers(0, 49, 10)] = bad
+        both(x, py, obs, what=f"path {bad}")
+    # both far away and close together: differences are small, magnitudes beyond FP32 range
+    both(px + 1.0e39, py, obs + np.array([1.0e39, 0.0]), what="1e39")
+    both(px + 1.0e15, py - 1.0e15, obs + np.array([1.0e15, -1.0e15]), what="1e15")
+    # degenerate radii / offsets
+    for rad in ([0.0, 0.0, 0.0], [-1.0, 1.5, 0.0], [1.0e-9, 1.0e-12, 1.0e-300], [1.0e6, 1.5, 1.0e-3], [np.inf, 1.5, 1.5], [np.nan, 1.5, 1.5]):
+        both(px, py, obs, OFF, rad, what=f"radii {rad}")
+    # an obstacle exactly on a circle centre and on a path point
+    o = obs.copy()
+    o[5] = (px[3, 7], py[3, 7])
+    both(px, py, o)
