@@ -205,6 +205,39 @@ template <> struct Math<double> {
 #endif
     }
 
+    // Speculative forms for straight-line code: same arithmetic without the range branch; the return value
+    // says whether the argument was inside the range the fast scheme is valid for.  A caller that collects
+    // the flags of a whole RK4 step and repeats the (rare) step on the branching versions keeps the four
+    // stages in one basic block, which lets the scheduler overlap the serial tail of one stage with the
+    // head of the next.
+    static B200MP_HD bool sincos_core(double x, double *s, double *c)
+    {
+#if B200MP_POLY
+        const double t = fma(x, kTrig[0], kRoundMagic);
+        const double kf = t - kRoundMagic;
+        double r = fma(-kf, kTrig[1], x);
+        r = fma(-kf, kTrig[2], r);
+        const double a = (kTrig[3] - ::fabs(r)) + kTrig[4];
+        const int k = lo_word(t);
+        *s = xor_sign(sin_poly(r), k);
+        *c = xor_sign(sin_poly(a), k);
+        return ::fabs(x) <= 1.0e5;
+#else
+        *s = ::sin(x);
+        *c = ::cos(x);
+        return true;
+#endif
+    }
+    static B200MP_HD bool rotate_core(double sa, double ca, double e, double *s, double *c)
+    {
+        const double u = e * e;
+        const double se = fma(e * u, -1.0 / 6, e);
+        const double ce = fma(u, fma(u, 1.0 / 24, -0.5), 1.0);
+        *s = fma(sa, ce, ca * se);
+        *c = fma(ca, ce, -(sa * se));
+        return ::fabs(e) <= 0.0009765625;
+    }
+
     // (sin, cos) of (a + e) from (sin a, cos a) for a small increment e: used for the RK4 stage headings,
     // which differ from the step's heading by h/2*wz or h*wz.  sin e = e - e^3/6, cos e = 1 - e^2/2 + e^4/24
     // (|e| <= 2^-10: truncation < 8e-18); returns false when e is too large for the series (the caller
@@ -254,6 +287,20 @@ template <> struct Math<float> {
 #else
         return a * b;
 #endif
+    }
+    static B200MP_HD bool sincos_core(float x, float *s, float *c)
+    {
+        sincos(x, s, c);
+        return true;
+    }
+    static B200MP_HD bool rotate_core(float sa, float ca, float e, float *s, float *c)
+    {
+        const float u = e * e;
+        const float se = fmaf(e * u, -1.0f / 6, e);
+        const float ce = fmaf(u, fmaf(u, 1.0f / 24, -0.5f), 1.0f);
+        *s = fmaf(sa, ce, ca * se);
+        *c = fmaf(ca, ce, -(sa * se));
+        return ::fabsf(e) <= 0.015625f;
     }
     static B200MP_HD float sin(float x) { return ::sinf(x); }
     static B200MP_HD float atan(float x) { return ::atanf(x); }

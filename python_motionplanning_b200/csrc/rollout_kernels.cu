@@ -62,6 +62,10 @@ template <typename R> struct RolloutDev {
 #define B200MP_ROLLOUT_MAXNREG 0
 #endif
 constexpr int kRolloutBlock = B200MP_ROLLOUT_BLOCK;
+#ifndef B200MP_RK4_SPECULATIVE
+#define B200MP_RK4_SPECULATIVE 1
+#endif
+constexpr bool kRolloutSpeculative = B200MP_RK4_SPECULATIVE != 0;
 #if B200MP_ROLLOUT_MAXNREG > 0
 #define B200MP_ROLLOUT_BOUNDS __maxnreg__(B200MP_ROLLOUT_MAXNREG)
 #else
@@ -161,7 +165,7 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
 #pragma unroll 1
                 for (; n < seg_end; ++n) {
                     R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
-                    rk4_step<R, REAR0, AUX, !GENERIC>(P, D, c, a.dt, y, ax, ay, sdot, outs);
+                    rk4_step<R, REAR0, AUX, !GENERIC, kRolloutSpeculative && !GENERIC && !AUX>(P, D, c, a.dt, y, ax, ay, sdot, outs);
                     if (a.cost) {
                         const size_t g = (size_t)(a.step0 + n);
                         const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;

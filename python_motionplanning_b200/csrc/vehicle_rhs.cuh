@@ -178,9 +178,13 @@ B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R 
 // One classic RK4 step (:427-445).  y[10] is advanced in place; ax, ay hold ax_prev, ay_prev on entry
 // and the RK4-averaged axc, ayc on exit (the next step's ax_prev, ay_prev, drive.py:141).
 // With AUX, sdot[10] and outs[18] receive the RK4-weighted means the reference returns (:440-441).
-template <typename R, bool REAR0, bool AUX, bool TY1>
-B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> &c, R h, R y[10], R &ax, R &ay,
-                        R *sdot, R *outs)
+//
+// SPEC = true: the heading trigonometry uses the branch-free "core" forms and the step is one basic
+// block; nothing is committed and false is returned when an argument left their range (the caller then
+// repeats the step with SPEC = false, which branches to the library where needed).
+template <typename R, bool REAR0, bool AUX, bool TY1, bool SPEC>
+B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtrl<R> &c, R h, R y[10], R &ax, R &ay,
+                             R *sdot, R *outs)
 {
     typedef Math<R> M;
     R Fz[4];
@@ -190,7 +194,11 @@ B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> 
     // heading trigonometry: one sincos per step; the three later stage headings are yaw + e with
     // e = h/2*wz or h*wz (tiny), obtained by a small-angle rotation of (s0, c0)
     R s0, c0, sj, cj;
-    M::sincos(y[7], &s0, &c0);
+    bool ok = true;
+    if (SPEC)
+        ok = M::sincos_core(y[7], &s0, &c0);
+    else
+        M::sincos(y[7], &s0, &c0);
 
     planar_rhs<R, REAR0, AUX, TY1>(P, D, y, s0, c0, c, Fz, k, axc, ayc, o);
 #pragma unroll
@@ -201,7 +209,10 @@ B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> 
     say = ayc;
     if (AUX)
         for (int i = 0; i < 18; ++i) outs[i] = o[i];
-    if (!M::rotate_small(s0, c0, h2 * k[7], &sj, &cj)) M::sincos(ys[7], &sj, &cj);
+    if (SPEC)
+        ok &= M::rotate_core(s0, c0, h2 * k[7], &sj, &cj);
+    else if (!M::rotate_small(s0, c0, h2 * k[7], &sj, &cj))
+        M::sincos(ys[7], &sj, &cj);
 
     planar_rhs<R, REAR0, AUX, TY1>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o);
 #pragma unroll
@@ -212,7 +223,10 @@ B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> 
     say += (R)2 * ayc;
     if (AUX)
         for (int i = 0; i < 18; ++i) outs[i] += (R)2 * o[i];
-    if (!M::rotate_small(s0, c0, h2 * k[7], &sj, &cj)) M::sincos(ys[7], &sj, &cj);
+    if (SPEC)
+        ok &= M::rotate_core(s0, c0, h2 * k[7], &sj, &cj);
+    else if (!M::rotate_small(s0, c0, h2 * k[7], &sj, &cj))
+        M::sincos(ys[7], &sj, &cj);
 
     planar_rhs<R, REAR0, AUX, TY1>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o);
 #pragma unroll
@@ -223,9 +237,13 @@ B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> 
     say += (R)2 * ayc;
     if (AUX)
         for (int i = 0; i < 18; ++i) outs[i] += (R)2 * o[i];
-    if (!M::rotate_small(s0, c0, h * k[7], &sj, &cj)) M::sincos(ys[7], &sj, &cj);
+    if (SPEC)
+        ok &= M::rotate_core(s0, c0, h * k[7], &sj, &cj);
+    else if (!M::rotate_small(s0, c0, h * k[7], &sj, &cj))
+        M::sincos(ys[7], &sj, &cj);
 
     planar_rhs<R, REAR0, AUX, TY1>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o);
+    if (SPEC && !ok) return false;
     const R h6 = (R)(1.0 / 6) * h;       // :438  state + 1/6*h*(K1+2K2+2K3+K4)
     const R sixth = (R)(1.0 / 6);
 #pragma unroll
@@ -238,6 +256,41 @@ B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> 
     ay = (say + ayc) * sixth;
     if (AUX)
         for (int i = 0; i < 18; ++i) outs[i] = (outs[i] + o[i]) * sixth;
+    return true;
+}
+
+#if defined(__CUDACC__)
+#define B200MP_NOINLINE __noinline__
+#else
+#define B200MP_NOINLINE
+#endif
+
+// the branching version, out of line: reached only when a heading or a stage rotation is out of range
+template <typename R, bool REAR0, bool AUX, bool TY1>
+#if defined(__CUDACC__)
+__host__ __device__ B200MP_NOINLINE
+#endif
+void rk4_step_checked(const DevParams<R> &P, const R *D, const WheelCtrl<R> &c, R h, R *y, R *axay, R *sdot, R *outs)
+{
+    rk4_step_impl<R, REAR0, AUX, TY1, false>(P, D, c, h, y, axay[0], axay[1], sdot, outs);
+}
+
+// SPEC: run the straight-line speculative form first (used by the register-lean fast-path kernels; the
+// generic / logging instantiations are already at the register ceiling and keep the branching form).
+template <typename R, bool REAR0, bool AUX, bool TY1, bool SPEC>
+B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> &c, R h, R y[10], R &ax, R &ay,
+                        R *sdot, R *outs)
+{
+    if (SPEC) {
+        if (!rk4_step_impl<R, REAR0, AUX, TY1, true>(P, D, c, h, y, ax, ay, sdot, outs)) {
+            R axay[2] = {ax, ay};
+            rk4_step_checked<R, REAR0, AUX, TY1>(P, D, c, h, y, axay, sdot, outs);
+            ax = axay[0];
+            ay = axay[1];
+        }
+    } else {
+        rk4_step_impl<R, REAR0, AUX, TY1, false>(P, D, c, h, y, ax, ay, sdot, outs);
+    }
 }
 
 }  // namespace b200mp

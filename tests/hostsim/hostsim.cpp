@@ -32,7 +32,7 @@ static void run(int B, int n_steps, double dt, int hold, const double *state0, c
                 for (int i = 0; i < 4; ++i) c.tq[i] = (R)torque[(seg * tch + (tch == 1 ? 0 : i)) * B + r];
             }
             R sdot[10], outs[18];
-            rk4_step<R, REAR0, AUX, false>(P, D, c, (R)dt, y, ax, ay, sdot, outs);
+            rk4_step<R, REAR0, AUX, false, !AUX>(P, D, c, (R)dt, y, ax, ay, sdot, outs);   // !AUX: speculative form + checked fallback
             if (store_stride > 0 && (n + 1) % store_stride == 0) {
                 const size_t o = (size_t)((n + 1) / store_stride - 1);
                 if (traj) for (int k = 0; k < 10; ++k) traj[(o * 10 + k) * B + r] = (double)y[k];

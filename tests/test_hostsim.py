@@ -55,3 +55,20 @@ def test_device_headers_match_oracle(hostsim):
     # FP32 instantiation stays within the stated drift bound
     traj32, _, _ = _run(hostsim, 1, s0, d, t, par, N, 10, 50)
     assert rel_err(traj32, ref["traj"]).max() < 2e-3
+
+
+def test_speculative_step_falls_back_out_of_range(hostsim):
+    """Headings beyond the fast sincos range (|yaw| > 1e5) and yaw rates whose stage increments exceed the
+    small-angle rotation (|h*wz| > 2^-10) must take the checked step and still match the oracle."""
+    B, N = 64, 60
+    s0, d, t = wl.config2_rollouts(B=B, n_steps=N)
+    s0 = s0.copy()
+    s0[7, :16] = 3.0e5 + np.arange(16)          # huge heading
+    s0[2, 16:32] = 12.0                          # |h*wz| = 1.2e-3 > 2^-10
+    s0[7, 32:40] = -2.5e5
+    par = c_oracle.make_params(pn.VehicleParams())
+    par[0].D[:] = (1.0,) * 4
+    ref = c_oracle.rollout(s0, d, t, par, 1e-4, N, hold=10, store_stride=20)
+    traj, _, end = _run(hostsim, 0, s0, d, t, par, N, 10, 20)
+    assert rel_err(traj, ref["traj"]).max() < 1e-10      # sin/cos of 3e5: conditioning, not method
+    assert rel_err(end, ref["state_end"]).max() < 1e-10
