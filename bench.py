@@ -97,7 +97,8 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    """Samples SM clock, power and throttle reasons of one GPU while the timed region runs: NVML in a
+    thread (2 ms period, so even a 60 ms region gets ~30 samples), nvidia-smi polling as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -105,42 +106,90 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.tmp = None
+        self.rows = []
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.how = None
+
+    def _nvml_loop(self, nv, h, max_mhz):
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mw = nv.nvmlDeviceGetPowerUsage(h)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(mhz), float(max_mhz), mw / 1000.0, [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical order; map through the UUID of the CUDA device when visible-devices remaps
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = None
+            for i in range(nv.nvmlDeviceGetCount()):
+                cand = nv.nvmlDeviceGetHandleByIndex(i)
+                u = nv.nvmlDeviceGetUUID(cand)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u:
+                    h = cand
+                    break
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h, max_mhz), daemon=True)
+            self.thread.start()
+            self.how = "nvml thread, 2 ms period"
+            return
+        except Exception:
+            self.thread = None
+        try:
             self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.tmp,
                                          stderr=subprocess.DEVNULL)
+            self.how = "nvidia-smi -lms 20"
         except Exception:
             self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.tmp.flush()
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": self.how}
         rows = []
-        with open(self.tmp.name) as f:
-            for ln in f:
-                parts = [p.strip() for p in ln.split(",")]
-                if len(parts) >= 7:
-                    try:
-                        rows.append((float(parts[0]), float(parts[1]), float(parts[2]), parts[3:7]))
-                    except ValueError:
-                        pass
-        os.unlink(self.tmp.name)
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            rows = [(a, b, c, d) for a, b, c, d in self.rows]
+            names = None
+        elif self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.tmp.flush()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            with open(self.tmp.name) as f:
+                for ln in f:
+                    parts = [p.strip() for p in ln.split(",")]
+                    if len(parts) >= 7:
+                        try:
+                            rows.append((float(parts[0]), float(parts[1]), float(parts[2]),
+                                         [names[i] for i in range(4) if parts[3 + i].lower().startswith("active")]))
+                        except ValueError:
+                            pass
+            os.unlink(self.tmp.name)
         if not rows:
             return out
         loaded = [r for r in rows if r[2] > 0.5 * max(x[2] for x in rows)] or rows
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in rows for i in range(4) if r[3][i].lower().startswith("active")})
+        reasons = sorted({k for r in rows for k in r[3]})
         out.update(sm_mhz=statistics.median(r[0] for r in loaded), sm_max_mhz=max(r[1] for r in rows), reasons=reasons,
                    samples=len(rows), power_w_max=max(r[2] for r in rows))
         return out
@@ -285,7 +334,8 @@ def run_gpu(args):
                     "api": "Engine.rollout_to_host: pinned host inputs -> H2D, 10 time-chunks of 50 steps, D2H of the full trajectory overlapped on a copy stream"},
             "gpu_launches": args.steps * world,
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
-                       "samples": clocks["samples"], "power_w_max": clocks.get("power_w_max"), "remeasured": remeasured},
+                       "samples": clocks["samples"], "how": clocks.get("how"), "power_w_max": clocks.get("power_w_max"),
+                       "remeasured": remeasured},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_s_timed_region": wall,
         }
         if extras:
@@ -327,6 +377,33 @@ def secondary_metrics(eng, wl, np, torch):
                      "ms": sec * 1e3, "paths_per_s": P / sec, "free_fraction": float(free.float().mean().item()),
                      "includes": "host numpy cos/sin of 200k yaws + H2D of them + kernel(s) + sync",
                      "algorithmic_tflops": tests * ALG_FLOP_PER_TEST / sec * 1e-12}
+    # kernel-only (paths, host-evaluated cos/sin and obstacles resident; CUDA events), the shipped scene and the same
+    # scene with the obstacles moved out of reach (nothing collides -> no early exit, every nominal test is executed)
+    trig = eng.path_trig(w["pyaw"], n)
+    far = eng.dev(w["obstacles"] + np.array([400.0, 0.0]))
+    peak32 = eng.fma_peak(32, reps=3)
+    for name, ob in (("collision_kernel", obs), ("collision_kernel_no_early_exit", far)):
+        for mode in ("auto", "fp64"):
+            eng.set_collision_mode(mode)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(13)]
+            for e0, e1 in evs:
+                e0.record()
+                fr = eng.collision_check_batch(px, py, None, ob, w["offsets"], w["radii"], trig=trig)
+                e1.record()
+            torch.cuda.synchronize()
+            ms = statistics.median(e0.elapsed_time(e1) for e0, e1 in evs[3:])
+            key = name + ("" if mode == "auto" else "_fp64_only")
+            out[key] = {"ms": ms, "value": tests / (ms * 1e-3), "unit": "circle-point tests/s (nominal)",
+                        "free_fraction": float(fr.float().mean().item()),
+                        "arithmetic": "FP32 screen (packed f32x2) + exact FP64 recheck of undecided pairs" if mode == "auto"
+                        else "all FP64"}
+        eng.set_collision_mode("auto")
+    k = out["collision_kernel_no_early_exit"]
+    # 4 FP32 lane-operations per test (2 subtractions, 1 multiply, 1 FMA = 5 flop) against the measured FP32 FMA peak
+    k["roofline"] = {"bound": "fp32", "achieved": k["value"] * 5 * 1e-12, "peak": peak32, "unit": "TFLOP/s",
+                     "frac": k["value"] * 5 * 1e-12 / peak32, "frac_of_fp32_lane_issue": k["value"] * 4 / (peak32 * 1e12 / 2),
+                     "flop_per_test_executed": 5, "flop_per_test_algorithmic": ALG_FLOP_PER_TEST,
+                     "peak_source": "measured live: register-resident FFMA chains (b200mp_fma_peak 32)"}
     t0 = time.perf_counter()
     best = eng.select_best_path_index_batch(px[:, -1].contiguous(), py[:, -1].contiguous(), free, w["goal"], w["weight"])
     out["select_best"] = {"P": P, "ms": (time.perf_counter() - t0) * 1e3, "best_index": best}
@@ -342,7 +419,6 @@ def secondary_metrics(eng, wl, np, torch):
     ev1.record()
     torch.cuda.synchronize()
     ms32 = ev0.elapsed_time(ev1)
-    peak32 = eng.fma_peak(32, reps=3)
     out["rollout_f32"] = {"value": B * N_STEPS / (ms32 * 1e-3), "unit": UNIT, "ms": ms32, "fp32_peak_tflops": peak32,
                           "frac_of_fp32_peak": B * N_STEPS / (ms32 * 1e-3) * ALG_FLOP_PER_STEP * 1e-12 / peak32}
     del tr32

@@ -266,8 +266,16 @@ class Engine:
         return mn, ix
 
     # ---------------------------------------------------------------- collision
+    def path_trig(self, pyaw, n: int):
+        """cos / sin of the first ``n`` yaws of every path, evaluated on the HOST with numpy (what the reference
+        does, collision_checker.py:88-89) and uploaded: pass the pair as ``trig=`` to reuse it across calls."""
+        if isinstance(pyaw, torch.Tensor):
+            pyaw = pyaw.detach().cpu().numpy()
+        yaw = np.asarray(pyaw, dtype=np.float64)[:, :n]
+        return self.dev(np.cos(yaw)), self.dev(np.sin(yaw))
+
     def collision_check_batch(self, px, py, pyaw, obstacles, offsets: Sequence[float], radii: Sequence[float],
-                              want_clearance: bool = False, device_trig: bool = False):
+                              want_clearance: bool = False, device_trig: bool = False, trig=None):
         """``free[P]`` (uint8, 1 = collision-free) for P paths at once (``b200mp_collision_check_f64``).
 
         px, py ``[P,n]``; pyaw ``[P,>=n]`` (first n used).  By default cos/sin of the yaws are evaluated on the
@@ -290,11 +298,12 @@ class Engine:
         if device_trig:
             yaw_t = self.dev(pyaw)
             stride = yaw_t.shape[1]
+        elif trig is not None:
+            pc, ps = self.dev(trig[0]), self.dev(trig[1])
+            if pc.shape != (P, n) or ps.shape != (P, n):
+                raise ValueError("trig must be (cos[P,n], sin[P,n])")
         else:
-            if isinstance(pyaw, torch.Tensor):
-                pyaw = pyaw.detach().cpu().numpy()
-            yaw = np.asarray(pyaw, dtype=np.float64)[:, :n]
-            pc, ps = self.dev(np.cos(yaw)), self.dev(np.sin(yaw))
+            pc, ps = self.path_trig(pyaw, n)
         free = self.empty(P, dtype=torch.uint8)
         clr = self.empty(P) if want_clearance else None
         check(self.lib.b200mp_collision_check_f64(self.device, self._stream(), P, n, len(offsets), off, rad,
