@@ -165,6 +165,53 @@ int b200mp_select_best_f64(int device, void *stream, int P, const double *ex, co
                            const unsigned char *free_in, double gx, double gy, double weight, int norm_mode,
                            double *scores_out, int *best_out);
 
+/* Batched closed-loop path tracking: for every vehicle, every ctrl_every-th sub-step,
+ * StanleyController.stanley_control (reference libs/controllers/stanley_controller.py:56-129) and
+ * LongitudinalController.long_control (:138-159) on the current state, the first-order steering filter of
+ * drive.py:137-138, then VehicleModel.planar_model_RK4 with delta = [d, d, 0, 0], torque = [tau]*4
+ * (drive.py:141-143; the parameter set's D plays mu_max = [1,1,1,1] of drive.py:142).
+ *   state0     dev [12][V]
+ *   ctrl0      dev [3][V]   steering-filter state x_del, integral of the speed error, previous speed
+ *                           (drive.py: x_del[-1], total_vel_error, prev_vel)
+ *   waypoints  dev [n_sets][w_max][2] (16-byte aligned), wp_count dev [n_sets]; vehicle r tracks set
+ *              r / vehicles_per_set (the planner hands one waypoint list to each tracker, local_planner.py:419)
+ *   traj       dev [n_steps/store_stride][10][V] or NULL
+ *   log        dev [n_steps/store_stride][45][V] or NULL: the DataLog row of drive.py:145-151
+ *              [time, state(10), state_dot(10), delta, torque(4), outputs(18), crosstrack]; time = (step0+n)*dt
+ *   target_idx dev [ceil(n_steps/ctrl_every)][V] or NULL: the look-ahead waypoint index of every control update
+ *   state_end  dev [12][V], ctrl_end dev [3][V] (may alias the inputs): the loop is resumable
+ * step0 must be a multiple of ctrl_every (a launch starts on a control update).  norm_mode as in
+ * b200mp_select_best_f64.  Target indices and crosstrack errors follow the reference bit for bit given the
+ * same states; headings use CUDA atan2/sincos (<= 1-2 ulp from numpy's). */
+typedef struct B200mpTrackArgs {
+    int V;
+    int n_steps;
+    int step0;
+    int ctrl_every;
+    int store_stride;
+    int n_sets;
+    int w_max;
+    int vehicles_per_set;
+    int norm_mode;
+    double dt;
+    double target_vel;
+    double k, k_soft, max_steer;       /* StanleyController gains (drive.py:71-74) */
+    double kp, ki, kd;                 /* LongitudinalController gains (drive.py:82-84) */
+    double lookahead, deadband;        /* stanley_controller.py:44-45 */
+    double steer_filter;               /* 1e-5 / (2 * 0.001), drive.py:137 */
+    const double *state0;
+    const double *ctrl0;
+    const double *waypoints;
+    const int *wp_count;
+    double *traj;
+    double *log;
+    int *target_idx;
+    double *state_end;
+    double *ctrl_end;
+} B200mpTrackArgs;
+#define B200MP_N_LOG 45 /* columns of the reference's DataLog (drive.py:44, plots.py:19-27) */
+int b200mp_track_closed_loop_f64(int device, void *stream, const B200mpTrackArgs *args);
+
 /* Measured pipe peak for the roofline denominator: runs a register-resident FMA chain kernel
  * (dtype_bits 64 or 32) `reps` times, synchronises, and returns the best TFLOP/s (FMA = 2 flop). */
 int b200mp_fma_peak(int device, int dtype_bits, int reps, double *tflops_out);

@@ -40,6 +40,13 @@ def lib():
         L.oracle_norm2.argtypes = [C.c_int, dp, dp, C.c_int, dp]
         L.oracle_norm2.restype = None
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_track_loop.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, dp, dp, dp, ip, C.c_int, C.c_int,
+                                        C.POINTER(OracleParams), C.c_double, dp, C.c_int, C.c_int, dp, dp, ip, dp, dp,
+                                        C.c_int]
+        L.oracle_track_loop.restype = C.c_long
+        L.oracle_stanley_control.argtypes = [dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, C.c_int,
+                                             ip, dp]
+        L.oracle_stanley_control.restype = C.c_double
         _lib = L
     return _lib
 
@@ -150,3 +157,45 @@ def norm2(v0, v1, mode):
     out = np.empty_like(v0)
     L.oracle_norm2(len(v0), _dp(v0), _dp(v1), int(mode), _dp(out))
     return out
+
+
+def track_gains(k=100.0, k_soft=1.0, max_steer=np.deg2rad(30), kp=1000.0, ki=100.0, kd=0.0, lookahead=5.0,
+                deadband=0.01, alpha=1e-5 / (2 * 0.001)):
+    """[k, k_soft, max_steer, kp, ki, kd, lookahead, deadband, alpha] with the reference's values
+    (drive.py:71-85, stanley_controller.py:44-45, drive.py:137)."""
+    return np.array([k, k_soft, max_steer, kp, ki, kd, lookahead, deadband, alpha], dtype=np.float64)
+
+
+def stanley_control(waypoints, x, y, yaw, v, gains, norm_mode):
+    """One ``StanleyController.stanley_control`` call: (steer, target index, crosstrack error)."""
+    L = lib()
+    wp = _f64(waypoints).reshape(-1, 2)
+    idx, cte = C.c_int(0), C.c_double(0.0)
+    st = L.oracle_stanley_control(_dp(wp), len(wp), float(x), float(y), float(yaw), float(v), _dp(_f64(gains)),
+                                  int(norm_mode), C.byref(idx), C.byref(cte))
+    return st, idx.value, cte.value
+
+
+def track_loop(state0, ctrl0, waypoints, wp_count, params, dt, n_steps, target_vel, gains, norm_mode, ctrl_every=10,
+               vehicles_per_set=None, store_stride=0, want_log=False, step0=0, nthreads=None):
+    """Closed-loop Stanley/PID tracking.  state0 [12,V]; ctrl0 [3,V]; waypoints [n_sets,Wmax,2]; wp_count [n_sets]."""
+    L = lib()
+    state0, ctrl0 = _f64(state0), _f64(ctrl0)
+    V = state0.shape[1]
+    wp = _f64(waypoints)
+    if wp.ndim == 2:
+        wp = wp[None]
+    n_sets, Wmax = wp.shape[0], wp.shape[1]
+    cnt = np.ascontiguousarray(wp_count if wp_count is not None else [Wmax] * n_sets, dtype=np.int32)
+    vps = int(vehicles_per_set or -(-V // n_sets))
+    n_out = n_steps // store_stride if store_stride else 0
+    traj = np.empty((n_out, 10, V)) if n_out else None
+    log = np.empty((n_out, 45, V)) if (n_out and want_log) else None
+    n_ctrl = -(-n_steps // ctrl_every)
+    tid = np.zeros((n_ctrl, V), dtype=np.int32)
+    end, cend = np.empty((12, V)), np.empty((3, V))
+    L.oracle_track_loop(V, int(n_steps), int(step0), float(dt), int(ctrl_every), _dp(state0), _dp(ctrl0), _dp(wp),
+                        cnt.ctypes.data_as(C.POINTER(C.c_int)), Wmax, vps, params, float(target_vel), _dp(_f64(gains)),
+                        int(norm_mode), int(store_stride), _dp(traj), _dp(log),
+                        tid.ctypes.data_as(C.POINTER(C.c_int)), _dp(end), _dp(cend), int(nthreads or host_threads()))
+    return dict(traj=traj, log=log, target_idx=tid, state_end=end, ctrl_end=cend)

@@ -17,6 +17,7 @@
  *
  * Pinned against tests/golden (literal reference outputs) by tests/test_oracle_pinned.py.
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -291,6 +292,144 @@ int oracle_select_best(int P, const double *ex, const double *ey, const unsigned
         }
     if (!scores_out) free(scores);
     return best;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Closed-loop tracking: the controllers around the RK4 step as Car.drive runs
+ * them (drive.py:126-151) -- StanleyController.get_lookahead_index / stanley_control
+ * (stanley_controller.py:56-129), LongitudinalController.long_control (:138-159), the first-order
+ * steering filter (drive.py:137-138) -- restated in the reference's operator order.
+ * gains = [k, k_soft, max_steer, kp, ki, kd, lookahead, deadband, alpha]; norm_mode as oracle_norm2. */
+static double py_mod(double a, double b) /* numpy float remainder for b > 0 */
+{
+    double m = fmod(a, b);
+    if (m != 0.0) {
+        if (m < 0.0) m += b;
+    } else
+        m = copysign(0.0, b);
+    return m;
+}
+
+static double np_sign(double v) { return v > 0 ? 1.0 : (v < 0 ? -1.0 : (v == 0 ? 0.0 : v)); }
+
+/* stanley_controller.py:56-76 */
+int oracle_lookahead_index(const double *wp, int W, double x, double y, double lookahead, int mode, double *min_dist_out)
+{
+    int min_idx = 0;
+    double min_dist = INFINITY;
+    for (int i = 0; i < W; ++i) {
+        const double d = norm2(wp[2 * i] - x, wp[2 * i + 1] - y, mode);
+        if (d < min_dist) {
+            min_dist = d;
+            min_idx = i;
+        }
+    }
+    double total = min_dist;
+    int la = min_idx;
+    for (int i = min_idx + 1; i < W; ++i) {
+        if (total >= lookahead) break;
+        total += norm2(wp[2 * i] - wp[2 * (i - 1)], wp[2 * i + 1] - wp[2 * (i - 1) + 1], mode);
+        la = i;
+    }
+    if (min_dist_out) *min_dist_out = min_dist;
+    return la;
+}
+
+/* stanley_controller.py:78-129; returns the limited steering angle */
+double oracle_stanley_control(const double *wp, int W, double x, double y, double yaw, double v, const double *gains,
+                              int mode, int *target_idx, double *crosstrack)
+{
+    const double k = gains[0], ksoft = gains[1], max_steer = gains[2], L = gains[6], deadband = gains[7];
+    const int ce = oracle_lookahead_index(wp, W, x, y, L, mode, NULL);
+    const double cv0 = wp[2 * ce] - x - L * cos(yaw);
+    const double cv1 = wp[2 * ce + 1] - y - L * sin(yaw);
+    double cte = norm2(cv0, cv1, mode);
+    if (cte < deadband) cte = 0;
+    const double ch = atan2(cv1, cv0);
+    double che = ch - yaw;
+    che = py_mod(che + M_PI, 2 * M_PI) - M_PI;
+    const double sgn = np_sign(che);
+    double th;
+    if (ce < W - 1)
+        th = atan2(wp[2 * (ce + 1) + 1] - wp[2 * ce + 1], wp[2 * (ce + 1)] - wp[2 * ce]);
+    else
+        th = atan2(wp[1] - wp[2 * (W - 1) + 1], wp[0] - wp[2 * (W - 1)]);
+    double he = th - yaw;
+    he = py_mod(he + M_PI, 2 * M_PI) - M_PI;
+    const double steer = he + atan(k * sgn * cte / (v + ksoft));
+    double lim = steer < -max_steer ? -max_steer : steer;   /* np.clip = minimum(maximum(x, lo), hi) */
+    lim = lim > max_steer ? max_steer : lim;
+    if (target_idx) *target_idx = ce;
+    if (crosstrack) *crosstrack = cte;
+    return lim;
+}
+
+/* Closed loop for V vehicles.  Layouts (vehicle index fastest):
+ *   state0 [12][V]; ctrl0 [3][V] = steering-filter state x_del, integral of the speed error, previous speed
+ *   wp [n_sets][Wmax][2], wp_count [n_sets]; vehicle r tracks set r / vehicles_per_set
+ *   traj [n_out][10][V], log [n_out][45][V] (the DataLog row of drive.py:145-151), target_idx [n_ctrl][V] (each may be NULL)
+ *   state_end [12][V], ctrl_end [3][V]
+ * step0 (a multiple of ctrl_every) only offsets the logged time column. */
+long oracle_track_loop(int V, int n_steps, int step0, double dt, int ctrl_every, const double *state0, const double *ctrl0,
+                       const double *wp, const int *wp_count, int Wmax, int vehicles_per_set, const oracle_params *p,
+                       double target_vel, const double *gains, int norm_mode, int store_stride, double *traj,
+                       double *log, int *target_idx, double *state_end, double *ctrl_end, int nthreads)
+{
+    if (nthreads <= 0) nthreads = 1;
+    const double kp = gains[3], ki = gains[4], kd = gains[5], alpha = gains[8];
+    const double mu1[4] = {1.0, 1.0, 1.0, 1.0};   /* drive.py:142 */
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int r = 0; r < V; ++r) {
+        double y[10], axay[2], sd[10], out[18];
+        for (int c = 0; c < 10; ++c) y[c] = state0[(size_t)c * V + r];
+        axay[0] = state0[(size_t)10 * V + r];
+        axay[1] = state0[(size_t)11 * V + r];
+        double x_del = ctrl0[r], e_int = ctrl0[(size_t)V + r], prev_v = ctrl0[(size_t)2 * V + r];
+        const int set = r / vehicles_per_set;
+        const double *w = wp + (size_t)set * Wmax * 2;
+        const int W = wp_count[set];
+        double delta = 0, tau = 0, cte = 0;
+        for (int n = 0; n < n_steps; ++n) {
+            if (n % ctrl_every == 0) {
+                const double v = y[0];
+                int ce = 0;
+                const double raw = oracle_stanley_control(w, W, y[8], y[9], y[7], v, gains, norm_mode, &ce, &cte);
+                /* long_control, :138-159 */
+                const double vel_error = target_vel - v;
+                e_int = e_int + vel_error * dt;
+                const double pp = kp * vel_error, ii = ki * e_int, dd = kd * (v - prev_v) / dt;
+                tau = pp + ii + dd;
+                if (v <= 0.01) tau = fabs(tau);
+                prev_v = v;
+                x_del = (1 - alpha) * x_del + alpha * raw;   /* drive.py:137-138 */
+                delta = x_del;
+                if (target_idx) target_idx[(size_t)(n / ctrl_every) * V + r] = ce;
+            }
+            const double dl[4] = {delta, delta, 0, 0}, tq[4] = {tau, tau, tau, tau};
+            oracle_rk4_step(y, tq, mu1, dl, p, dt, axay, sd, out);
+            if (store_stride > 0 && (n + 1) % store_stride == 0) {
+                const size_t o = (size_t)((n + 1) / store_stride - 1);
+                if (traj) for (int c = 0; c < 10; ++c) traj[(o * 10 + c) * V + r] = y[c];
+                if (log) {
+                    double *row = log + o * 45 * V + r;
+                    row[0] = (double)(step0 + n) * dt;
+                    for (int c = 0; c < 10; ++c) row[(size_t)(1 + c) * V] = y[c];
+                    for (int c = 0; c < 10; ++c) row[(size_t)(11 + c) * V] = sd[c];
+                    row[(size_t)21 * V] = delta;
+                    for (int c = 0; c < 4; ++c) row[(size_t)(22 + c) * V] = tau;
+                    for (int c = 0; c < 18; ++c) row[(size_t)(26 + c) * V] = out[c];
+                    row[(size_t)44 * V] = cte;
+                }
+            }
+        }
+        for (int c = 0; c < 10; ++c) state_end[(size_t)c * V + r] = y[c];
+        state_end[(size_t)10 * V + r] = axay[0];
+        state_end[(size_t)11 * V + r] = axay[1];
+        ctrl_end[r] = x_del;
+        ctrl_end[(size_t)V + r] = e_int;
+        ctrl_end[(size_t)2 * V + r] = prev_v;
+    }
+    return (long)V * n_steps;
 }
 
 int oracle_max_threads(void)

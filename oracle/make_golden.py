@@ -286,6 +286,59 @@ def gen_closedloop(frames=400, path_every=4):
     print(f"closedloop_cfg1.npz: {frames} frames, {n} RK4 steps, {time.time()-t0:.0f}s")
 
 
+
+# ------------------------------------------------------------------------- closed-loop tracking (N3 / N4)
+def gen_tracking(frames=200, every=8):
+    """Per-frame pins for the batched Stanley/PID closed loop and the 45-column log:
+    the unmodified reference Car (drive.py:112-154) runs `frames` frames; for every frame the waypoints the
+    planner handed to the tracker (local_planner.py:419), the vehicle + controller state at the frame start and
+    the 100 DataLog rows (drive.py:145-151) are recorded."""
+    ref = ref_loader.load()
+    drive, lp = ref.drive, ref.local_planner
+    lp.ThreadPool = _SerialPool
+    world = ref.env.world
+    path = world.path
+    car = drive.Car(path.px[10], path.py[10], path.pyaw[10], path.px, path.py, path.pyaw, DT)
+    wps, starts, ctrl0, target_ids = [], [], [], []
+    tracker = car.lateral_tracker
+    orig_stanley = tracker.stanley_control
+    ids = []
+
+    def stanley(x, y, yaw, v):
+        r = orig_stanley(x, y, yaw, v)
+        ids.append(r[1])
+        return r
+
+    tracker.stanley_control = stanley
+    t0 = time.time()
+    kept = []
+    for f in range(frames):
+        keep = f % every == 0
+        if keep:
+            kept.append(f)
+            starts.append(np.array(list(car.state) + [car.ax_prev, car.ay_prev], float))
+            ctrl0.append([car.x_del[-1], car.total_vel_error, car.prev_vel, car.delta, car.torque_vec[0]])
+        n_ids = len(ids)
+        car.drive(f)
+        if keep:
+            wp = np.asarray(tracker._waypoints, float)  # set at sub-step 0 of this frame, used for all 10 updates
+            wps.append(wp[:, :2].copy())
+            target_ids.append(ids[n_ids:])
+            print(f"tracking frame {f}/{frames} {time.time()-t0:.0f}s  waypoints {len(wp)}", flush=True)
+    W = max(len(w) for w in wps)
+    wp_pad = np.full((len(kept), W, 2), np.nan)
+    for f, w in enumerate(wps):
+        wp_pad[f, :len(w)] = w
+    log = car.DataLog[:frames * 100].reshape(frames, 100, 45)[kept].copy()
+    np.savez_compressed(os.path.join(GOLDEN, "tracking_frames.npz"), waypoints=wp_pad,
+                        n_waypoints=np.array([len(w) for w in wps]), start=np.array(starts), ctrl0=np.array(ctrl0, float),
+                        log=log, target_ids=np.array(target_ids), frame_index=np.array(kept), target_vel=car.target_vel,
+                        gains=np.array([car.k, car.ksoft, car.max_steer, car.k_v, car.k_i, car.k_d], float),
+                        lookahead=tracker._lookahead_distance, deadband=tracker.cross_track_deadband,
+                        steer_filter=1e-5 / (2 * 0.001), dt=DT, frames=len(kept), **_host_facts())
+    print(f"tracking_frames.npz: {len(kept)} of {frames} frames, W<= {W}, {time.time()-t0:.0f}s")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -302,6 +355,8 @@ def main():
         gen_collision()
     if a.only in (None, "closedloop"):
         gen_closedloop(a.frames)
+    if a.only in (None, "tracking"):
+        gen_tracking(min(a.frames, 200))
 
 
 if __name__ == "__main__":

@@ -37,6 +37,16 @@ class RolloutArgsC(C.Structure):
     ]
 
 
+class TrackArgsC(C.Structure):
+    """``B200mpTrackArgs``"""
+    _fields_ = [(n, C.c_int) for n in ("V", "n_steps", "step0", "ctrl_every", "store_stride", "n_sets", "w_max",
+                                       "vehicles_per_set", "norm_mode")] + [
+        (n, C.c_double) for n in ("dt", "target_vel", "k", "k_soft", "max_steer", "kp", "ki", "kd", "lookahead", "deadband",
+                                  "steer_filter")] + [
+        (n, C.c_void_p) for n in ("state0", "ctrl0", "waypoints", "wp_count", "traj", "log", "target_idx", "state_end",
+                                  "ctrl_end")]
+
+
 # every symbol include/b200mp.h declares: name -> (restype, argtypes)
 _vp, _i, _d, _ll, _ull = C.c_void_p, C.c_int, C.c_double, C.c_longlong, C.c_ulonglong
 _dp = C.POINTER(C.c_double)
@@ -53,6 +63,7 @@ PROTOTYPES = {
     "b200mp_collision_check_f64": (_i, [_i, _vp, _i, _i, _i, _dp, _dp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "b200mp_set_collision_mode": (_i, [_i]),
     "b200mp_select_best_f64": (_i, [_i, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp]),
+    "b200mp_track_closed_loop_f64": (_i, [_i, _vp, C.POINTER(TrackArgsC)]),
     "b200mp_fma_peak": (_i, [_i, _i, _i, _dp]),
     "b200mp_shutdown": (_i, []),
 }

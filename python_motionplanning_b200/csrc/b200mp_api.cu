@@ -251,6 +251,16 @@ int b200mp_select_best_f64(int device, void *stream, int P, const double *ex, co
                                   best_out);
 }
 
+int b200mp_track_closed_loop_f64(int device, void *stream, const B200mpTrackArgs *args)
+{
+    B200MP_ENTER(device);
+    if (!args) {
+        set_error("track: args is NULL");
+        return B200MP_E_ARG;
+    }
+    return launch_track_f64(device, (cudaStream_t)stream, *args);
+}
+
 int b200mp_fma_peak(int device, int dtype_bits, int reps, double *tflops_out)
 {
     B200MP_ENTER(device);

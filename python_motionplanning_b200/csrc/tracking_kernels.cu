@@ -1,0 +1,376 @@
+// K5: batched closed-loop path tracking -- Stanley lateral + PID longitudinal control around the RK4 step,
+// one thread per vehicle (sm_100a, FP64).
+//
+// Replaces, for many vehicles at once, the control half of Car.drive (reference drive.py:126-151):
+//   StanleyController.get_lookahead_index / stanley_control   libs/controllers/stanley_controller.py:56-129
+//   LongitudinalController.long_control                       libs/controllers/stanley_controller.py:138-159
+//   the first-order steering filter                            drive.py:137-138
+// feeding VehicleModel.planar_model_RK4 (vehicle_rhs.cuh) without leaving the GPU, and writing the
+// reference's 45-column DataLog row (drive.py:145-151) when asked to.
+//
+// The reference scans every waypoint (~3,000 at 1 cm spacing) with np.linalg.norm on each control update
+// and then walks forward summing segment lengths until the look-ahead distance is reached.  Here:
+//   * a prepare kernel evaluates, once per waypoint set, everything that does not depend on the vehicle:
+//     segment lengths (same closed form as the host's norm, so the walk adds the same doubles), segment
+//     headings, and the radius of every 32-waypoint chunk around its first waypoint;
+//   * the nearest-waypoint search is exact but sub-linear: the squared distance to every chunk's first
+//     waypoint gives an upper bound UB on the minimum; a chunk whose first waypoint is farther than
+//     UB + Rmax cannot contain the minimum (triangle inequality, with 1e-12 relative slack for rounding);
+//     the surviving chunks are searched on the squared distance in the host's rounding sequence
+//     (sqrt_rn is monotone, so the smallest square has the smallest rounded norm) and the reference's
+//     first-strict-minimum index is recovered by looking, among squares within 4 ulp of the minimum, for
+//     the first one whose rounded square root equals the minimum's;
+//   * the look-ahead walk adds the precomputed segment lengths in the reference's order, starting from
+//     the rounded minimum distance, so target indices are bit-identical to the reference's.
+// Waypoints, segment data and chunk data are read through L1 (a set is ~100 KB; vehicles of a CTA share it).
+#include <math.h>
+
+#include "b200mp_internal.h"
+
+namespace b200mp {
+
+constexpr int kTrackBlock = 64;
+constexpr int kChunk = 32;
+constexpr double kPi = 3.141592653589793;
+
+struct TrackDev {
+    int V, n_steps, step0, ctrl_every, store_stride, n_sets, w_max, vps, blocks_per_set, norm_mode;
+    double dt, target_vel, k, k_soft, max_steer, kp, ki, kd, lookahead, deadband, alpha;
+    const double *state0, *ctrl0;
+    const double2 *wp;
+    const int *wp_count;
+    const double *seg, *head, *rmax;
+    double *traj, *log, *state_end, *ctrl_end;
+    int *target_idx;
+};
+
+__device__ __forceinline__ double host_sq(double v0, double v1, int mode)
+{
+    // the argument of the square root in the host's np.linalg.norm([v0, v1]) closed form (B200MP_NORM2_*)
+    if (mode == B200MP_NORM2_FMA_V1) return __fma_rn(v1, v1, __dmul_rn(v0, v0));
+    if (mode == B200MP_NORM2_FMA_V0) return __fma_rn(v0, v0, __dmul_rn(v1, v1));
+    return __dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v1, v1));
+}
+
+// numpy's float remainder for a positive divisor (np.float64.__mod__)
+__device__ __forceinline__ double py_mod(double a, double b)
+{
+    double m = fmod(a, b);
+    if (m != 0.0) {
+        if (m < 0.0) m = __dadd_rn(m, b);
+    } else {
+        m = copysign(0.0, b);
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(256)
+track_prepare_kernel(int w_max, const double2 *__restrict__ wp, const int *__restrict__ wp_count, int norm_mode,
+                     double *__restrict__ seg, double *__restrict__ head, double *__restrict__ rmax)
+{
+    const int set = blockIdx.x;
+    const int W = wp_count[set];
+    const double2 *w = wp + (size_t)set * w_max;
+    double *sg = seg + (size_t)set * w_max, *hd = head + (size_t)set * w_max;
+    double r = 0.0;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) {
+        const double2 p = w[i];
+        if (i > 0) {
+            const double2 q = w[i - 1];
+            sg[i] = __dsqrt_rn(host_sq(__dsub_rn(p.x, q.x), __dsub_rn(p.y, q.y), norm_mode));   // stanley_controller.py:72-74
+        } else {
+            sg[i] = 0.0;
+        }
+        const double2 a = (i < W - 1) ? w[i + 1] : w[0];     // :105-116, the last waypoint wraps to the first
+        const double2 b = (i < W - 1) ? p : w[W - 1];
+        hd[i] = atan2(a.y - b.y, a.x - b.x);
+        const double2 c = w[i - (i % kChunk)];
+        const double dx = p.x - c.x, dy = p.y - c.y;
+        r = fmax(r, sqrt(dx * dx + dy * dy));                // NaN waypoints drop out (they never win a minimum)
+    }
+    __shared__ double sr[256];
+    sr[threadIdx.x] = r;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sr[threadIdx.x] = fmax(sr[threadIdx.x], sr[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) rmax[set] = sr[0] * (1.0 + 1.0e-12) + 1.0e-300;
+}
+
+// get_lookahead_index (stanley_controller.py:56-76): exact nearest waypoint, then the look-ahead walk.
+__device__ __noinline__ int lookahead_index(const double2 *__restrict__ w, const double *__restrict__ sg, int W, double rmax,
+                                            double x, double y, double lookahead, int mode)
+{
+    const int n_chunks = (W + kChunk - 1) / kChunk;
+    // A: upper bound on the minimum from the chunk heads
+    double qmin = INFINITY;
+    for (int c = 0; c < n_chunks; ++c) {
+        const double2 p = w[c * kChunk];
+        const double dx = p.x - x, dy = p.y - y;
+        qmin = fmin(qmin, dx * dx + dy * dy);
+    }
+    const double ub = sqrt(qmin) * (1.0 + 1.0e-12);
+    const double reach = (ub + rmax) * (ub + rmax) * (1.0 + 1.0e-12);
+    // B: smallest square (host rounding sequence) over the chunks that can hold the minimum
+    double qbest = INFINITY;
+    int ibest = 0, c_first = n_chunks;
+    for (int c = 0; c < n_chunks; ++c) {
+        const double2 p = w[c * kChunk];
+        const double dx = p.x - x, dy = p.y - y;
+        if (dx * dx + dy * dy > reach) continue;             // NaN compares false: such a chunk is searched
+        if (c < c_first) c_first = c;
+        const int i1 = min(W, (c + 1) * kChunk);
+        for (int i = c * kChunk; i < i1; ++i) {
+            const double2 v = w[i];
+            const double q = host_sq(__dsub_rn(v.x, x), __dsub_rn(v.y, y), mode);
+            if (q < qbest) {
+                qbest = q;
+                ibest = i;
+            }
+        }
+    }
+    int min_idx = 0;
+    double min_dist = INFINITY;
+    if (qbest < INFINITY) {
+        // C: the reference keeps the FIRST index whose rounded norm equals the minimum (strict '<' update)
+        min_dist = __dsqrt_rn(qbest);
+        min_idx = ibest;
+        const double qtie = qbest * (1.0 + 1.0e-15);
+        for (int c = c_first; c * kChunk < ibest; ++c) {
+            const double2 p = w[c * kChunk];
+            const double dx = p.x - x, dy = p.y - y;
+            if (dx * dx + dy * dy > reach) continue;
+            const int i1 = min(ibest, (c + 1) * kChunk);
+            bool found = false;
+            for (int i = c * kChunk; i < i1; ++i) {
+                const double2 v = w[i];
+                const double q = host_sq(__dsub_rn(v.x, x), __dsub_rn(v.y, y), mode);
+                if (q <= qtie && __dsqrt_rn(q) == min_dist) {
+                    min_idx = i;
+                    found = true;
+                    break;
+                }
+            }
+            if (found) break;
+        }
+    }
+    double total = min_dist;
+    int la = min_idx;
+    for (int i = min_idx + 1; i < W; ++i) {                  // :68-75
+        if (total >= lookahead) break;
+        total = __dadd_rn(total, sg[i]);
+        la = i;
+    }
+    return la;
+}
+
+template <bool LOG>
+__global__ void __launch_bounds__(kTrackBlock)
+track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevParams<double> P0)
+{
+    const int set = blockIdx.x / a.blocks_per_set;
+    const int local = (blockIdx.x - set * a.blocks_per_set) * kTrackBlock + threadIdx.x;
+    const int r = set * a.vps + local;
+    if (local >= a.vps || r >= a.V) return;
+    const size_t V = (size_t)a.V;
+    const double2 *w = a.wp + (size_t)set * a.w_max;
+    const double *sg = a.seg + (size_t)set * a.w_max, *hd = a.head + (size_t)set * a.w_max;
+    const int W = a.wp_count[set];
+    const double rmax = a.rmax[set];
+
+    double y[10], ax, ay;
+#pragma unroll
+    for (int c = 0; c < 10; ++c) y[c] = a.state0[c * V + r];
+    ax = a.state0[10 * V + r];
+    ay = a.state0[11 * V + r];
+    double x_del = a.ctrl0[r], e_int = a.ctrl0[V + r], prev_v = a.ctrl0[2 * V + r];
+    double delta = 0.0, tau = 0.0, cte = 0.0;
+    WheelCtrl<double> c;
+    set_steer<double, true>(c, &delta);
+    c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = 0.0;
+
+    double *tp = a.traj ? a.traj + r : nullptr;
+    double *lp = (LOG && a.log) ? a.log + r : nullptr;
+    int until_store = a.store_stride;
+
+    int n = 0;
+    while (n < a.n_steps) {
+        {   // ---- controllers (drive.py:128-138) on the current state
+            const double v = y[0], yaw = y[7], px = y[8], py = y[9];
+            int ce = 0;
+            double raw;
+            if (W > 0) {
+                ce = lookahead_index(w, sg, W, rmax, px, py, a.lookahead, a.norm_mode);
+                double sn, cs;
+                sincos(yaw, &sn, &cs);
+                const double2 t = w[ce];
+                const double cv0 = __dsub_rn(__dsub_rn(t.x, px), __dmul_rn(a.lookahead, cs));   // :88-92
+                const double cv1 = __dsub_rn(__dsub_rn(t.y, py), __dmul_rn(a.lookahead, sn));
+                cte = __dsqrt_rn(host_sq(cv0, cv1, a.norm_mode));
+                if (cte < a.deadband) cte = 0.0;                                               // :95-96
+                double che = atan2(cv1, cv0) - yaw;                                            // :99-102
+                che = py_mod(che + kPi, 2.0 * kPi) - kPi;
+                const double sgn = che > 0.0 ? 1.0 : (che < 0.0 ? -1.0 : che);
+                double he = hd[ce] - yaw;                                                      // :107-121
+                he = py_mod(he + kPi, 2.0 * kPi) - kPi;
+                const double steer = he + atan(__ddiv_rn(__dmul_rn(__dmul_rn(a.k, sgn), cte), v + a.k_soft));   // :122-124
+                raw = fmin(fmax(steer, -a.max_steer), a.max_steer);                            // :126
+                if (steer != steer) raw = steer;                                               // np.clip keeps NaN
+            } else {
+                raw = 0.0;
+                cte = 0.0;
+            }
+            const double vel_error = a.target_vel - v;                                         // :149-155
+            e_int = __dadd_rn(e_int, __dmul_rn(vel_error, a.dt));
+            const double pp = __dmul_rn(a.kp, vel_error), ii = __dmul_rn(a.ki, e_int);
+            const double dd = __ddiv_rn(__dmul_rn(a.kd, v - prev_v), a.dt);
+            tau = __dadd_rn(__dadd_rn(pp, ii), dd);
+            if (v <= 0.01) tau = fabs(tau);                                                    // :157-158
+            prev_v = v;
+            x_del = __dadd_rn(__dmul_rn(1.0 - a.alpha, x_del), __dmul_rn(a.alpha, raw));       // drive.py:137
+            delta = x_del;
+            set_steer<double, true>(c, &delta);
+            c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = tau;
+            if (a.target_idx) a.target_idx[(size_t)(n / a.ctrl_every) * V + r] = ce;
+        }
+        const int n_end = min(a.n_steps, n + a.ctrl_every);
+#pragma unroll 1
+        for (; n < n_end; ++n) {
+            double sdot[LOG ? 10 : 1], outs[LOG ? 18 : 1];
+            rk4_step<double, true, LOG, true, !LOG>(P0, P0.Dc, c, a.dt, y, ax, ay, sdot, outs);
+            if (a.store_stride > 0 && --until_store == 0) {
+                until_store = a.store_stride;
+                if (tp) {
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) tp[k * V] = y[k];
+                    tp += 10 * V;
+                }
+                if (LOG && lp) {   // the DataLog row of drive.py:145-151
+                    lp[0] = __dmul_rn((double)(a.step0 + n), a.dt);
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) lp[(1 + k) * V] = y[k];
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) lp[(11 + k) * V] = sdot[k];
+                    lp[21 * V] = delta;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) lp[(22 + k) * V] = tau;
+#pragma unroll
+                    for (int k = 0; k < 18; ++k) lp[(26 + k) * V] = outs[k];
+                    lp[44 * V] = cte;
+                    lp += 45 * V;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) a.state_end[k * V + r] = y[k];
+    a.state_end[10 * V + r] = ax;
+    a.state_end[11 * V + r] = ay;
+    a.ctrl_end[r] = x_del;
+    a.ctrl_end[V + r] = e_int;
+    a.ctrl_end[2 * V + r] = prev_v;
+}
+
+int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
+{
+    if (g.V < 0 || g.n_steps < 0 || g.ctrl_every < 1 || g.step0 < 0 || g.store_stride < 0 || g.n_sets < 1 || g.w_max < 0 ||
+        g.vehicles_per_set < 1) {
+        set_error("track: bad sizes V=%d n_steps=%d step0=%d ctrl_every=%d store_stride=%d n_sets=%d w_max=%d vehicles_per_set=%d",
+                  g.V, g.n_steps, g.step0, g.ctrl_every, g.store_stride, g.n_sets, g.w_max, g.vehicles_per_set);
+        return B200MP_E_ARG;
+    }
+    if (g.step0 % g.ctrl_every != 0 || (g.store_stride > 0 && g.step0 % g.store_stride != 0)) {
+        set_error("track: step0 must be a multiple of ctrl_every and of store_stride");
+        return B200MP_E_ARG;
+    }
+    if (g.V == 0) return 0;
+    if (!g.state0 || !g.ctrl0 || !g.state_end || !g.ctrl_end || !g.wp_count || (g.w_max > 0 && !g.waypoints)) {
+        set_error("track: state0, ctrl0, waypoints, wp_count, state_end and ctrl_end must be non-NULL");
+        return B200MP_E_ARG;
+    }
+    if ((long long)g.n_sets * g.vehicles_per_set < g.V) {
+        set_error("track: n_sets * vehicles_per_set (%d * %d) does not cover V = %d", g.n_sets, g.vehicles_per_set, g.V);
+        return B200MP_E_ARG;
+    }
+    if (g.norm_mode < 0 || g.norm_mode > 2) {
+        set_error("track: norm_mode %d", g.norm_mode);
+        return B200MP_E_ARG;
+    }
+    if ((((size_t)g.waypoints) & 15) != 0) {
+        set_error("track: waypoints must be 16-byte aligned");
+        return B200MP_E_ARG;
+    }
+    DeviceState &ds = dev_state(device);
+    if (ds.n_sets < 1) {
+        set_error("track: no parameter table on device %d (call b200mp_set_params first)", device);
+        return B200MP_E_PARAMS;
+    }
+    for (int i = 1; i < 4; ++i)
+        if (ds.set0.B[i] != ds.set0.B[0] || ds.set0.C[i] != ds.set0.C[0] || ds.set0.D[i] != ds.set0.D[0]) {
+            set_error("track: parameter set 0 must carry one (B, C, D) for the four tyres (vehicle_model.py:41-54)");
+            return B200MP_E_PARAMS;
+        }
+    if (g.n_steps == 0) {
+        if (g.state_end != g.state0)
+            B200MP_CUDA(cudaMemcpyAsync(g.state_end, g.state0, sizeof(double) * 12 * (size_t)g.V, cudaMemcpyDeviceToDevice, st));
+        if (g.ctrl_end != g.ctrl0)
+            B200MP_CUDA(cudaMemcpyAsync(g.ctrl_end, g.ctrl0, sizeof(double) * 3 * (size_t)g.V, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    const size_t per = (size_t)g.n_sets * (size_t)(g.w_max > 0 ? g.w_max : 1);
+    void *scratch = nullptr;
+    int rc = ensure_scratch(device, sizeof(double) * (2 * per + (size_t)g.n_sets), &scratch);
+    if (rc) return rc;
+    TrackDev a;
+    a.V = g.V;
+    a.n_steps = g.n_steps;
+    a.step0 = g.step0;
+    a.ctrl_every = g.ctrl_every;
+    a.store_stride = (g.traj || g.log) ? g.store_stride : 0;
+    a.n_sets = g.n_sets;
+    a.w_max = g.w_max;
+    a.vps = g.vehicles_per_set;
+    a.blocks_per_set = (g.vehicles_per_set + kTrackBlock - 1) / kTrackBlock;
+    a.norm_mode = g.norm_mode;
+    a.dt = g.dt;
+    a.target_vel = g.target_vel;
+    a.k = g.k;
+    a.k_soft = g.k_soft;
+    a.max_steer = g.max_steer;
+    a.kp = g.kp;
+    a.ki = g.ki;
+    a.kd = g.kd;
+    a.lookahead = g.lookahead;
+    a.deadband = g.deadband;
+    a.alpha = g.steer_filter;
+    a.state0 = g.state0;
+    a.ctrl0 = g.ctrl0;
+    a.wp = (const double2 *)g.waypoints;
+    a.wp_count = g.wp_count;
+    a.seg = (double *)scratch;
+    a.head = (double *)scratch + per;
+    a.rmax = (double *)scratch + 2 * per;
+    a.traj = g.traj;
+    a.log = g.log;
+    a.state_end = g.state_end;
+    a.ctrl_end = g.ctrl_end;
+    a.target_idx = g.target_idx;
+    track_prepare_kernel<<<g.n_sets, 256, 0, st>>>(g.w_max, a.wp, g.wp_count, g.norm_mode, (double *)a.seg, (double *)a.head,
+                                                   (double *)a.rmax);
+    B200MP_CUDA(cudaGetLastError());
+    const DevParams<double> P0 = derive_params<double>(ds.set0);
+    const long long grid = (long long)g.n_sets * a.blocks_per_set;
+    if (grid > 0x7fffffffLL) {
+        set_error("track: grid too large");
+        return B200MP_E_ARG;
+    }
+    if (g.log)
+        track_kernel<true><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
+    else
+        track_kernel<false><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
+    B200MP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200mp

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import B200mpError, RolloutArgsC, VehicleParamsC, check
+from ._lib import B200mpError, RolloutArgsC, TrackArgsC, VehicleParamsC, check
 from .host_numerics import host_norm2_mode
 
 _PARAM_SCALARS = ("m", "a", "b", "Izz", "Jw", "hg", "T", "wL", "wR", "rw")
@@ -63,6 +63,31 @@ _UPLOADED = {}      # device -> (signature bytes, upload counter)
 def uploaded_token(device: int) -> int:
     """Counter that changes whenever a new parameter table is uploaded to ``device``."""
     return _UPLOADED.get(device, (None, 0))[1]
+
+
+@dataclass
+class TrackGains:
+    """Controller constants with the reference's values: Stanley ``k, k_soft, max_steer`` (drive.py:71-74, :57),
+    PID ``kp, ki, kd`` (drive.py:82-84), ``lookahead`` / ``deadband`` (stanley_controller.py:44-45) and the
+    steering filter coefficient ``1e-5 / (2*0.001)`` (drive.py:137)."""
+    k: float = 100.0
+    k_soft: float = 1.0
+    max_steer: float = float(np.deg2rad(30))
+    kp: float = 1000.0
+    ki: float = 100.0
+    kd: float = 0.0
+    lookahead: float = 5.0
+    deadband: float = 0.01
+    steer_filter: float = 1e-5 / (2 * 0.001)
+
+
+@dataclass
+class TrackResult:
+    state_end: torch.Tensor                      # [12, V]
+    ctrl_end: torch.Tensor                       # [3, V]  x_del, integral of speed error, previous speed
+    traj: Optional[torch.Tensor] = None          # [n_out, 10, V]
+    log: Optional[torch.Tensor] = None           # [n_out, 45, V]  the DataLog rows of drive.py:145-151
+    target_idx: Optional[torch.Tensor] = None    # [n_ctrl, V] int32
 
 
 @dataclass
@@ -247,6 +272,63 @@ class Engine:
                                                self._ptr(mu_t), self._ptr(dl), self._ptr(axay), self._ptr(ps),
                                                self._ptr(sd), self._ptr(misc), self._ptr(out)), "b200mp_planar_model_f64")
         return sd, misc, out
+
+    # ------------------------------------------------------------ closed loop
+    def track_closed_loop(self, state0, waypoints, dt: float, n_steps: int, target_vel: float = 25.0,
+                          gains: Optional[TrackGains] = None, ctrl0=None, wp_count=None, vehicles_per_set: Optional[int] = None,
+                          ctrl_every: int = 10, store_stride: int = 0, want_log: bool = False, want_target_idx: bool = False,
+                          step0: int = 0, norm_mode: Optional[int] = None) -> TrackResult:
+        """Batched Stanley + PID closed loop around the RK4 step (``b200mp_track_closed_loop_f64``): what
+        ``Car.drive`` does between two planner calls (drive.py:126-151), for V vehicles at once.
+
+        state0 ``[12,V]`` (or ``[10,V]``); waypoints ``[n_sets,W,2]`` or ``[W,2]`` (one shared list), ``wp_count``
+        the used length per set; vehicle r tracks set ``r // vehicles_per_set``.  ``ctrl0 [3,V]`` = steering-filter
+        state, integral of the speed error, previous speed (default ``[0, 0, U0]``, drive.py:47-54).  The uploaded
+        parameter set's ``D`` plays ``mu_max`` (set it to 1.0 for drive.py:142).  Asynchronous on the current stream."""
+        g = gains or TrackGains()
+        s0 = self.dev(state0)
+        if s0.dim() != 2 or s0.shape[0] not in (10, 12):
+            raise ValueError(f"state0 must be [12,V] or [10,V], got {tuple(s0.shape)}")
+        V = s0.shape[1]
+        if s0.shape[0] == 10:
+            s0 = torch.cat([s0, torch.zeros(2, V, dtype=torch.float64, device=self.tdev)])
+        wp = self.dev(waypoints)
+        if wp.dim() == 2:
+            wp = wp[None]
+        if wp.dim() != 3 or wp.shape[2] != 2:
+            raise ValueError("waypoints must be [n_sets, W, 2] or [W, 2]")
+        wp = wp.contiguous()
+        n_sets, W = wp.shape[0], wp.shape[1]
+        cnt = self.dev(wp_count if wp_count is not None else [W] * n_sets, torch.int32)
+        if cnt.numel() != n_sets:
+            raise ValueError("wp_count must have one entry per waypoint set")
+        vps = int(vehicles_per_set or max(1, -(-V // n_sets)))
+        if ctrl0 is None:
+            c0 = torch.zeros(3, V, dtype=torch.float64, device=self.tdev)
+            c0[2] = s0[0]
+        else:
+            c0 = self.dev(ctrl0)
+            if c0.shape != (3, V):
+                raise ValueError("ctrl0 must be [3, V]")
+        n_out = n_steps // store_stride if store_stride else 0
+        traj = self.empty(n_out, 10, V) if n_out else None
+        log = self.empty(n_out, 45, V) if (n_out and want_log) else None
+        n_ctrl = -(-n_steps // ctrl_every) if n_steps else 0
+        tid = self.empty(n_ctrl, V, dtype=torch.int32) if (want_target_idx and n_ctrl) else None
+        end, cend = self.empty(12, V), self.empty(3, V)
+        if norm_mode is None:
+            if self._norm2_mode is None:
+                self._norm2_mode = host_norm2_mode()
+            norm_mode = self._norm2_mode
+        p = lambda t: None if t is None else t.data_ptr()
+        a = TrackArgsC(V=V, n_steps=int(n_steps), step0=int(step0), ctrl_every=int(ctrl_every),
+                       store_stride=int(store_stride if n_out else 0), n_sets=n_sets, w_max=W, vehicles_per_set=vps,
+                       norm_mode=int(norm_mode), dt=float(dt), target_vel=float(target_vel), k=g.k, k_soft=g.k_soft,
+                       max_steer=g.max_steer, kp=g.kp, ki=g.ki, kd=g.kd, lookahead=g.lookahead, deadband=g.deadband,
+                       steer_filter=g.steer_filter, state0=p(s0), ctrl0=p(c0), waypoints=p(wp), wp_count=p(cnt),
+                       traj=p(traj), log=p(log), target_idx=p(tid), state_end=p(end), ctrl_end=p(cend))
+        check(self.lib.b200mp_track_closed_loop_f64(self.device, self._stream(), C.byref(a)), "b200mp_track_closed_loop_f64")
+        return TrackResult(state_end=end, ctrl_end=cend, traj=traj, log=log, target_idx=tid)
 
     # ------------------------------------------------------------- sampling MPC
     def mpc_sample_controls(self, B: int, n_seg: int, seed: int, rollout0: int = 0, delta_mean=0.0, delta_sigma=0.02,

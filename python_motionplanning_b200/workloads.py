@@ -152,3 +152,39 @@ def config5_sweep(n_sets=256, n_man=4096, seed=SEED, rw=RW_DEFAULT):
     torque = np.tile(tq, n_sets)[None, None, :]
     param_set = np.repeat(np.arange(n_sets, dtype=np.int32), n_man)
     return sets, state0, np.ascontiguousarray(delta), np.ascontiguousarray(torque), param_set
+
+
+def tracking_fleet(V: int = 4096, n_sets: int = 4, W: int = 3000, ds: float = 0.01, seed: int = SEED + 7):
+    """Closed-loop tracking workload: ``n_sets`` waypoint lists of ``W`` points at ``ds`` spacing
+    (what the planner hands the tracker: its best path re-interpolated at 1 cm, local_planner.py:390-419) --
+    clothoid-like arcs from random poses -- and ``V`` vehicles (``V // n_sets`` per list) starting near the head of
+    their list with a lateral / heading / speed offset.  Returns ``state0 [12,V]``, ``waypoints [n_sets,W,2]``."""
+    rng = np.random.default_rng(seed)
+    wp = np.empty((n_sets, W, 2))
+    vps = -(-V // n_sets)
+    state0 = np.zeros((12, V))
+    rw = 0.329 - (987.89 / 2 + 50) / 26290            # VehicleParameters().rw (vehicle_model.py:38)
+    for s in range(n_sets):
+        x0, y0, th0 = rng.uniform(-50, 50), rng.uniform(-50, 50), rng.uniform(-np.pi, np.pi)
+        k0, k1 = rng.uniform(-0.02, 0.02), rng.uniform(-0.02, 0.02)
+        arc = np.arange(W) * ds
+        th = th0 + k0 * arc + 0.5 * (k1 - k0) / (W * ds) * arc ** 2
+        wp[s, :, 0] = x0 + np.concatenate([[0.0], np.cumsum(np.cos(th[:-1]) * ds)])
+        wp[s, :, 1] = y0 + np.concatenate([[0.0], np.cumsum(np.sin(th[:-1]) * ds)])
+        lo, hi = s * vps, min(V, (s + 1) * vps)
+        n = hi - lo
+        if n <= 0:
+            continue
+        along = rng.uniform(0.0, 2.0, n)               # up to 2 m into the list
+        lat = rng.uniform(-1.0, 1.0, n)
+        i0 = np.minimum((along / ds).astype(int), W - 2)
+        yaw = th[i0] + rng.uniform(-0.1, 0.1, n)
+        U = rng.uniform(15.0, 30.0, n)
+        state0[0, lo:hi] = U
+        state0[1, lo:hi] = rng.uniform(-0.3, 0.3, n)
+        state0[2, lo:hi] = rng.uniform(-0.1, 0.1, n)
+        state0[3:7, lo:hi] = (U / rw)[None, :] * (1 + rng.uniform(-0.02, 0.02, (4, n)))
+        state0[7, lo:hi] = yaw
+        state0[8, lo:hi] = wp[s, i0, 0] - lat * np.sin(th[i0])
+        state0[9, lo:hi] = wp[s, i0, 1] + lat * np.cos(th[i0])
+    return state0, wp
