@@ -422,6 +422,20 @@ def secondary_metrics(eng, wl, np, torch):
     out["rollout_f32"] = {"value": B * N_STEPS / (ms32 * 1e-3), "unit": UNIT, "ms": ms32, "fp32_peak_tflops": peak32,
                           "frac_of_fp32_peak": B * N_STEPS / (ms32 * 1e-3) * ALG_FLOP_PER_STEP * 1e-12 / peak32}
     del tr32
+    # closed-loop tracking: 65,536 vehicles on 16 waypoint lists of 3,000 points, 500 sub-steps =
+    # 50 Stanley/PID updates each; same RK4 work per step as the headline metric plus the controllers
+    st0, wps = wl.tracking_fleet(V=B, n_sets=16)
+    st0_d, wps_d = eng.dev(st0), eng.dev(wps)
+    for name, kw in (("closed_loop_tracking", {}), ("closed_loop_tracking_datalog_stride10", {"store_stride": 10, "want_log": True})):
+        for k in range(3):
+            if k == 2:
+                ev0.record()
+            eng.track_closed_loop(st0_d, wps_d, DT, N_STEPS, 25.0, vehicles_per_set=B // 16, **kw)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        out[name] = {"value": B * N_STEPS / (ms * 1e-3), "unit": "closed-loop rollout-steps/s", "ms": ms,
+                     "vehicles": B, "waypoints_per_list": int(wps.shape[1]), "control_updates": N_STEPS // 10}
     # end-state-only FP64 (no trajectory writeback): separates compute from writeback
     s0, dl, tq = eng.dev(s0_h), eng.dev(d_h), eng.dev(t_h)
     for k in range(4):

@@ -11,18 +11,21 @@
 // The reference scans every waypoint (~3,000 at 1 cm spacing) with np.linalg.norm on each control update
 // and then walks forward summing segment lengths until the look-ahead distance is reached.  Here:
 //   * a prepare kernel evaluates, once per waypoint set, everything that does not depend on the vehicle:
-//     segment lengths (same closed form as the host's norm, so the walk adds the same doubles), segment
-//     headings, and the radius of every 32-waypoint chunk around its first waypoint;
-//   * the nearest-waypoint search is exact but sub-linear: the squared distance to every chunk's first
-//     waypoint gives an upper bound UB on the minimum; a chunk whose first waypoint is farther than
-//     UB + Rmax cannot contain the minimum (triangle inequality, with 1e-12 relative slack for rounding);
-//     the surviving chunks are searched on the squared distance in the host's rounding sequence
-//     (sqrt_rn is monotone, so the smallest square has the smallest rounded norm) and the reference's
-//     first-strict-minimum index is recovered by looking, among squares within 4 ulp of the minimum, for
-//     the first one whose rounded square root equals the minimum's;
-//   * the look-ahead walk adds the precomputed segment lengths in the reference's order, starting from
-//     the rounded minimum distance, so target indices are bit-identical to the reference's.
-// Waypoints, segment data and chunk data are read through L1 (a set is ~100 KB; vehicles of a CTA share it).
+//     segment lengths (same closed form as the host's norm, so the walk adds the same doubles), their
+//     running sum (a search key only), segment headings, and the largest radius of the 8-waypoint "fine"
+//     and 256-waypoint "coarse" chunks about their first waypoints;
+//   * the nearest-waypoint search is exact but sub-linear: the distance to the previous update's nearest
+//     waypoint (or to the coarse chunk heads) is an upper bound UB on the minimum; a chunk whose first
+//     waypoint is farther than UB + (chunk radius) cannot contain the minimum (triangle inequality, with
+//     1e-12 relative slack for rounding); coarse chunks are culled first, the fine chunks of a surviving
+//     coarse chunk form one 32-bit mask, and the surviving waypoints are compared on the squared distance
+//     in the host's rounding sequence (sqrt_rn is monotone).  The reference's "first strict minimum of the
+//     rounded norms" is reproduced by a branch-free scan plus an exact replay when any two squares came
+//     within 1e-15 of each other (ties, duplicate waypoints);
+//   * the look-ahead walk is a binary search on the running sum with a rigorous rounding bound; only when
+//     the bound cannot decide the index (|sum - lookahead| < ~1e-10) are the segment lengths added one by
+//     one from the rounded minimum distance as the reference does.  Target indices are bit-identical.
+// Waypoints and per-set tables are read through L1 (a set is ~120 KB; the vehicles of a CTA share one set).
 #include <math.h>
 
 #include "b200mp_internal.h"
@@ -30,7 +33,8 @@
 namespace b200mp {
 
 constexpr int kTrackBlock = 64;
-constexpr int kChunk = 32;
+constexpr int kFine = 8;             // waypoints per fine chunk
+constexpr int kCoarse = 32 * kFine;  // one coarse chunk = 32 fine chunks = one 32-bit candidate mask
 constexpr double kPi = 3.141592653589793;
 
 struct TrackDev {
@@ -39,7 +43,7 @@ struct TrackDev {
     const double *state0, *ctrl0;
     const double2 *wp;
     const int *wp_count;
-    const double *seg, *head, *rmax;
+    const double *seg, *head, *cum, *rmax, *clean;
     double *traj, *log, *state_end, *ctrl_end;
     int *target_idx;
 };
@@ -66,100 +70,187 @@ __device__ __forceinline__ double py_mod(double a, double b)
 
 __global__ void __launch_bounds__(256)
 track_prepare_kernel(int w_max, const double2 *__restrict__ wp, const int *__restrict__ wp_count, int norm_mode,
-                     double *__restrict__ seg, double *__restrict__ head, double *__restrict__ rmax)
+                     double *__restrict__ seg, double *__restrict__ head, double *__restrict__ cum,
+                     double *__restrict__ rmax, double *__restrict__ clean)
 {
     const int set = blockIdx.x;
     const int W = wp_count[set];
     const double2 *w = wp + (size_t)set * w_max;
-    double *sg = seg + (size_t)set * w_max, *hd = head + (size_t)set * w_max;
-    double r = 0.0;
+    double *sg = seg + (size_t)set * w_max, *hd = head + (size_t)set * w_max, *cm = cum + (size_t)set * w_max;
+    double r = 0.0, rc = 0.0;
+    int ok = 1;
     for (int i = threadIdx.x; i < W; i += blockDim.x) {
         const double2 p = w[i];
+        double sl = 0.0;
         if (i > 0) {
             const double2 q = w[i - 1];
-            sg[i] = __dsqrt_rn(host_sq(__dsub_rn(p.x, q.x), __dsub_rn(p.y, q.y), norm_mode));   // stanley_controller.py:72-74
-        } else {
-            sg[i] = 0.0;
+            sl = __dsqrt_rn(host_sq(__dsub_rn(p.x, q.x), __dsub_rn(p.y, q.y), norm_mode));   // stanley_controller.py:72-74
         }
+        sg[i] = sl;
+        ok &= (sl >= 0.0 && sl < INFINITY);
         const double2 a = (i < W - 1) ? w[i + 1] : w[0];     // :105-116, the last waypoint wraps to the first
         const double2 b = (i < W - 1) ? p : w[W - 1];
         hd[i] = atan2(a.y - b.y, a.x - b.x);
-        const double2 c = w[i - (i % kChunk)];
-        const double dx = p.x - c.x, dy = p.y - c.y;
-        r = fmax(r, sqrt(dx * dx + dy * dy));                // NaN waypoints drop out (they never win a minimum)
+        const double2 cf = w[i - (i % kFine)], cc = w[i - (i % kCoarse)];
+        const double fx = p.x - cf.x, fy = p.y - cf.y, gx = p.x - cc.x, gy = p.y - cc.y;
+        r = fmax(r, sqrt(fx * fx + fy * fy));                // NaN waypoints drop out (they never win a minimum)
+        rc = fmax(rc, sqrt(gx * gx + gy * gy));
     }
-    __shared__ double sr[256];
+    __shared__ double sr[256], src[256];
+    __shared__ int sok;
+    if (threadIdx.x == 0) sok = 1;
     sr[threadIdx.x] = r;
+    src[threadIdx.x] = rc;
     __syncthreads();
+    if (!ok) atomicAnd(&sok, 0);
     for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) sr[threadIdx.x] = fmax(sr[threadIdx.x], sr[threadIdx.x + s]);
+        if (threadIdx.x < s) {
+            sr[threadIdx.x] = fmax(sr[threadIdx.x], sr[threadIdx.x + s]);
+            src[threadIdx.x] = fmax(src[threadIdx.x], src[threadIdx.x + s]);
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) rmax[set] = sr[0] * (1.0 + 1.0e-12) + 1.0e-300;
+    if (threadIdx.x == 0) {
+        rmax[2 * set] = sr[0] * (1.0 + 1.0e-12) + 1.0e-300;        // fine chunks about their first waypoint
+        rmax[2 * set + 1] = src[0] * (1.0 + 1.0e-12) + 1.0e-300;   // coarse chunks about theirs
+        // running arc length: only a SEARCH KEY for the look-ahead walk (the walk's own sums are re-derived
+        // from it with an error bound, see lookahead_index); a set with a NaN/Inf segment walks sequentially
+        double acc = 0.0;
+        for (int i = 0; i < W; ++i) {
+            acc += sg[i];
+            cm[i] = acc;
+        }
+        clean[set] = sok ? 1.0 : 0.0;
+    }
+}
+
+struct SetView {
+    const double2 *__restrict__ w;
+    const double *__restrict__ sg, *__restrict__ cm;
+    int W;
+    double rfine, rcoarse;
+    bool clean;
+};
+
+// first i in [lo, W) with base + (cm[i] - cm0) >= thr, else W   (cm is non-decreasing)
+__device__ __forceinline__ int first_reaching(const double *__restrict__ cm, int lo, int W, double base, double cm0, double thr)
+{
+    int a = lo, b = W;
+    while (a < b) {
+        const int m = (a + b) >> 1;
+        if (base + (cm[m] - cm0) >= thr) b = m; else a = m + 1;
+    }
+    return a;
 }
 
 // get_lookahead_index (stanley_controller.py:56-76): exact nearest waypoint, then the look-ahead walk.
-__device__ __noinline__ int lookahead_index(const double2 *__restrict__ w, const double *__restrict__ sg, int W, double rmax,
-                                            double x, double y, double lookahead, int mode)
+// hint = a waypoint index near the vehicle (the previous update's nearest index) or -1.
+__device__ __forceinline__ int lookahead_index(const SetView &sv, double x, double y, double lookahead, int mode, int hint,
+                                            int *nearest)
 {
-    const int n_chunks = (W + kChunk - 1) / kChunk;
-    // A: upper bound on the minimum from the chunk heads
-    double qmin = INFINITY;
-    for (int c = 0; c < n_chunks; ++c) {
-        const double2 p = w[c * kChunk];
+    const double2 *__restrict__ w = sv.w;
+    const int W = sv.W;
+    const int n_coarse = (W + kCoarse - 1) / kCoarse;
+    // upper bound on the minimum distance: any waypoint will do; the coarse chunk heads when there is no hint
+    double qub = INFINITY;
+    if (hint >= 0 && hint < W) {
+        const double2 p = w[hint];
         const double dx = p.x - x, dy = p.y - y;
-        qmin = fmin(qmin, dx * dx + dy * dy);
+        qub = dx * dx + dy * dy;
     }
-    const double ub = sqrt(qmin) * (1.0 + 1.0e-12);
-    const double reach = (ub + rmax) * (ub + rmax) * (1.0 + 1.0e-12);
-    // B: smallest square (host rounding sequence) over the chunks that can hold the minimum
-    double qbest = INFINITY;
-    int ibest = 0, c_first = n_chunks;
-    for (int c = 0; c < n_chunks; ++c) {
-        const double2 p = w[c * kChunk];
-        const double dx = p.x - x, dy = p.y - y;
-        if (dx * dx + dy * dy > reach) continue;             // NaN compares false: such a chunk is searched
-        if (c < c_first) c_first = c;
-        const int i1 = min(W, (c + 1) * kChunk);
-        for (int i = c * kChunk; i < i1; ++i) {
-            const double2 v = w[i];
-            const double q = host_sq(__dsub_rn(v.x, x), __dsub_rn(v.y, y), mode);
-            if (q < qbest) {
-                qbest = q;
-                ibest = i;
-            }
+    if (!(qub < INFINITY)) {
+        for (int c = 0; c < n_coarse; ++c) {
+            const double2 p = w[c * kCoarse];
+            qub = fmin(qub, (p.x - x) * (p.x - x) + (p.y - y) * (p.y - y));
         }
     }
-    int min_idx = 0;
-    double min_dist = INFINITY;
-    if (qbest < INFINITY) {
-        // C: the reference keeps the FIRST index whose rounded norm equals the minimum (strict '<' update)
-        min_dist = __dsqrt_rn(qbest);
-        min_idx = ibest;
-        const double qtie = qbest * (1.0 + 1.0e-15);
-        for (int c = c_first; c * kChunk < ibest; ++c) {
-            const double2 p = w[c * kChunk];
+    const double ub = sqrt(qub) * (1.0 + 1.0e-12);
+    const double reach_c = (ub + sv.rcoarse) * (ub + sv.rcoarse) * (1.0 + 1.0e-12);
+    const double reach = (ub + sv.rfine) * (ub + sv.rfine) * (1.0 + 1.0e-12);
+
+    // The reference updates on `dist < min_dist` with dist = sqrt_rn(q).  sqrt_rn is monotone, so a square that is
+    // larger than the running minimum by more than a few ulp never updates and one that is smaller by more than a
+    // few ulp always does (the rounded roots differ); the scan below is branch-free on that basis and only notes
+    // whether any square ever fell inside the +-1e-15 band around the running minimum, in which case (rare: an
+    // exact or near tie) the chunks are re-scanned comparing rounded roots one by one.  A chunk whose first
+    // waypoint is farther than ub + (chunk radius) cannot hold the minimum or a tie with it (NaN compares false:
+    // such a chunk is searched).
+    double qbest = INFINITY;
+    int ibest = 0;
+    bool near_tie = false;
+    for (int g = 0; g < n_coarse; ++g) {
+        {
+            const double2 p = w[g * kCoarse];
             const double dx = p.x - x, dy = p.y - y;
-            if (dx * dx + dy * dy > reach) continue;
-            const int i1 = min(ibest, (c + 1) * kChunk);
-            bool found = false;
-            for (int i = c * kChunk; i < i1; ++i) {
+            if (dx * dx + dy * dy > reach_c) continue;
+        }
+        const int base = g * kCoarse;
+        const int gn = min(32, (W - base + kFine - 1) / kFine);
+        unsigned mask = 0;
+#pragma unroll 8
+        for (int c = 0; c < gn; ++c) {
+            const double2 p = w[base + c * kFine];
+            const double dx = p.x - x, dy = p.y - y;
+            mask |= (dx * dx + dy * dy > reach ? 0u : 1u) << c;
+        }
+        while (mask) {
+            const int i0 = base + (__ffs(mask) - 1) * kFine;
+            mask &= mask - 1;
+#pragma unroll
+            for (int k = 0; k < kFine; ++k) {
+                const int i = min(i0 + k, W - 1);               // the last chunk may be short: re-reading W-1 is harmless
                 const double2 v = w[i];
                 const double q = host_sq(__dsub_rn(v.x, x), __dsub_rn(v.y, y), mode);
-                if (q <= qtie && __dsqrt_rn(q) == min_dist) {
-                    min_idx = i;
-                    found = true;
-                    break;
+                const bool better = q < qbest * (1.0 - 1.0e-15);
+                near_tie |= !better && q <= qbest * (1.0 + 1.0e-15) && q < INFINITY && i0 + k < W;
+                qbest = better ? q : qbest;
+                ibest = better ? i : ibest;
+            }
+        }
+    }
+    if (near_tie) {   // exact replay of the reference's comparison sequence over the same chunks
+        qbest = INFINITY;
+        ibest = 0;
+        double dbest = INFINITY;
+        for (int c = 0; c * kFine < W; ++c) {
+            const double2 pc = w[(c * kFine / kCoarse) * kCoarse], p = w[c * kFine];
+            if ((pc.x - x) * (pc.x - x) + (pc.y - y) * (pc.y - y) > reach_c) continue;
+            if ((p.x - x) * (p.x - x) + (p.y - y) * (p.y - y) > reach) continue;
+            const int i1 = min(W, (c + 1) * kFine);
+            for (int i = c * kFine; i < i1; ++i) {
+                const double2 v = w[i];
+                const double q = host_sq(__dsub_rn(v.x, x), __dsub_rn(v.y, y), mode);
+                if (q < qbest) {
+                    const double d = __dsqrt_rn(q);
+                    if (d < dbest) {
+                        dbest = d;
+                        qbest = q;
+                        ibest = i;
+                    }
                 }
             }
-            if (found) break;
         }
+    }
+    const int min_idx = (qbest < INFINITY) ? ibest : 0;
+    const double min_dist = (qbest < INFINITY) ? __dsqrt_rn(qbest) : INFINITY;
+    *nearest = min_idx;
+
+    // look-ahead walk (:68-75): la = first i >= min_idx whose running sum T_i (T_min_idx = min_dist, T_i = fl(T_{i-1} +
+    // seg_i)) reaches the look-ahead distance, else W - 1.  T_i differs from A_i = min_dist + (cum_i - cum_min_idx) by
+    // at most err (rounding of at most W additions each side), so when the first index reaching lookahead - err and
+    // the first reaching lookahead + err coincide that index is the walk's; otherwise (or with a NaN/Inf segment) walk.
+    if (sv.clean && min_dist < INFINITY) {
+        const double cm0 = sv.cm[min_idx];
+        const double err = 4.5e-16 * (double)(W + 2) * (sv.cm[W - 1] + min_dist + fabs(lookahead));
+        const int lo = first_reaching(sv.cm, min_idx, W, min_dist, cm0, lookahead - err);
+        const int hi = first_reaching(sv.cm, lo, W, min_dist, cm0, lookahead + err);
+        if (lo == hi) return min(lo, W - 1);
     }
     double total = min_dist;
     int la = min_idx;
-    for (int i = min_idx + 1; i < W; ++i) {                  // :68-75
+    for (int i = min_idx + 1; i < W; ++i) {
         if (total >= lookahead) break;
-        total = __dadd_rn(total, sg[i]);
+        total = __dadd_rn(total, sv.sg[i]);
         la = i;
     }
     return la;
@@ -175,9 +266,17 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
     if (local >= a.vps || r >= a.V) return;
     const size_t V = (size_t)a.V;
     const double2 *w = a.wp + (size_t)set * a.w_max;
-    const double *sg = a.seg + (size_t)set * a.w_max, *hd = a.head + (size_t)set * a.w_max;
+    const double *hd = a.head + (size_t)set * a.w_max;
     const int W = a.wp_count[set];
-    const double rmax = a.rmax[set];
+    SetView sv;
+    sv.w = w;
+    sv.sg = a.seg + (size_t)set * a.w_max;
+    sv.cm = a.cum + (size_t)set * a.w_max;
+    sv.W = W;
+    sv.rfine = a.rmax[2 * set];
+    sv.rcoarse = a.rmax[2 * set + 1];
+    sv.clean = a.clean[set] != 0.0;
+    int nearest = -1;
 
     double y[10], ax, ay;
 #pragma unroll
@@ -201,7 +300,7 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
             int ce = 0;
             double raw;
             if (W > 0) {
-                ce = lookahead_index(w, sg, W, rmax, px, py, a.lookahead, a.norm_mode);
+                ce = lookahead_index(sv, px, py, a.lookahead, a.norm_mode, nearest, &nearest);
                 double sn, cs;
                 sincos(yaw, &sn, &cs);
                 const double2 t = w[ce];
@@ -320,7 +419,7 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     }
     const size_t per = (size_t)g.n_sets * (size_t)(g.w_max > 0 ? g.w_max : 1);
     void *scratch = nullptr;
-    int rc = ensure_scratch(device, sizeof(double) * (2 * per + (size_t)g.n_sets), &scratch);
+    int rc = ensure_scratch(device, sizeof(double) * (3 * per + 3 * (size_t)g.n_sets), &scratch);
     if (rc) return rc;
     TrackDev a;
     a.V = g.V;
@@ -350,14 +449,16 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     a.wp_count = g.wp_count;
     a.seg = (double *)scratch;
     a.head = (double *)scratch + per;
-    a.rmax = (double *)scratch + 2 * per;
+    a.cum = (double *)scratch + 2 * per;
+    a.rmax = (double *)scratch + 3 * per;
+    a.clean = (double *)scratch + 3 * per + 2 * (size_t)g.n_sets;
     a.traj = g.traj;
     a.log = g.log;
     a.state_end = g.state_end;
     a.ctrl_end = g.ctrl_end;
     a.target_idx = g.target_idx;
     track_prepare_kernel<<<g.n_sets, 256, 0, st>>>(g.w_max, a.wp, g.wp_count, g.norm_mode, (double *)a.seg, (double *)a.head,
-                                                   (double *)a.rmax);
+                                                   (double *)a.cum, (double *)a.rmax, (double *)a.clean);
     B200MP_CUDA(cudaGetLastError());
     const DevParams<double> P0 = derive_params<double>(ds.set0);
     const long long grid = (long long)g.n_sets * a.blocks_per_set;

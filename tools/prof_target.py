@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Short single-GPU program for ncu captures: a few launches of one hot-path kernel at full size.
 
-    python tools/prof_target.py rollout|rollout_f32|collision|collision_clear|mpc [--launches 3]
+    python tools/prof_target.py rollout|rollout_f32|collision|collision_clear|mpc|track|track_log [--launches 3]
 """
 import argparse
 import os
@@ -37,6 +37,12 @@ def main():
         for _ in range(a.launches):
             eng.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"], w["offsets"], w["radii"],
                                       want_clearance=a.what.endswith("clear"))
+    elif a.what in ("track", "track_log"):
+        st0, wps = wl.tracking_fleet(V=65536, n_sets=16)
+        s, w = eng.dev(st0), eng.dev(wps)
+        for _ in range(a.launches):
+            eng.track_closed_loop(s, w, wl.DT, 100, 25.0, vehicles_per_set=4096,
+                                  **({"store_stride": 10, "want_log": True} if a.what.endswith("log") else {}))
     elif a.what == "mpc":
         cfg = wl.config4_mpc(B=1 << 20)
         d, t = eng.mpc_sample_controls(cfg["B"], 100, cfg["seed"])
