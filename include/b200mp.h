@@ -212,6 +212,24 @@ typedef struct B200mpTrackArgs {
 #define B200MP_N_LOG 45 /* columns of the reference's DataLog (drive.py:44, plots.py:19-27) */
 int b200mp_track_closed_loop_f64(int device, void *stream, const B200mpTrackArgs *args);
 
+/* Conformal-lattice path generation: PathOptimizer.sample_spiral + thetaf (reference
+ * libs/motionplanner/path_optimizer.py:109-174) followed by transform_paths (libs/motionplanner/local_planner.py:
+ * 424-470) for P spirals at once.
+ *   kappa1, kappa2, sf   dev [P]: the optimisation parameters p = [p1, p2, sf] of each spiral
+ *   ego_x, ego_y, ego_yaw dev [P] (or [1] with ego_broadcast != 0), or all NULL for ego-frame output
+ *   px, py               dev [P][n_samples-1] path points (cumulative trapezoid has no initial value)
+ *   pyaw                 dev [P][n_samples-1] or NULL: heading of the sample BEFORE each point + ego_yaw (the
+ *                        reference's 49/50 length quirk, kept because collision_check reads yaw_j with point_j)
+ *   pcos, psin           dev [P][n_samples-1] or NULL: cos / sin of pyaw evaluated on the device, ready for
+ *                        b200mp_collision_check_f64 (<= 1-2 ulp from numpy's: flags then agree with the host-trig
+ *                        path except for obstacle points within ~1e-15 of a circle)
+ *   end_xy               dev [2][P] or NULL: (x[-1], y[-1]) of every path for b200mp_select_best_f64
+ * n_samples = 50 is the reference's (np.linspace default).  Parity: 1e-12 relative (CUDA vs numpy cos/sin/pow). */
+int b200mp_sample_lattice_f64(int device, void *stream, int P, int n_samples, const double *kappa1,
+                              const double *kappa2, const double *sf, const double *ego_x, const double *ego_y,
+                              const double *ego_yaw, int ego_broadcast, double *px, double *py, double *pyaw,
+                              double *pcos, double *psin, double *end_xy);
+
 /* Measured pipe peak for the roofline denominator: runs a register-resident FMA chain kernel
  * (dtype_bits 64 or 32) `reps` times, synchronises, and returns the best TFLOP/s (FMA = 2 flop). */
 int b200mp_fma_peak(int device, int dtype_bits, int reps, double *tflops_out);

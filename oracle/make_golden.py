@@ -339,6 +339,31 @@ def gen_tracking(frames=200, every=8):
     print(f"tracking_frames.npz: {len(kept)} of {frames} frames, W<= {W}, {time.time()-t0:.0f}s")
 
 
+# ------------------------------------------------------------------ spiral sampling + frame transform (N1)
+def gen_lattice(n=96):
+    """Literal ``PathOptimizer.sample_spiral`` (path_optimizer.py:131-174) and ``transform_paths``
+    (local_planner.py:424-470) on random optimisation parameters / ego poses."""
+    ref = ref_loader.load()
+    po = ref.path_optimizer.PathOptimizer()
+    rng = np.random.default_rng(wl.SEED + 11)
+    k1, k2 = rng.uniform(-0.05, 0.05, n), rng.uniform(-0.05, 0.05, n)
+    sf = rng.uniform(20.0, 40.0, n)
+    ego = np.stack([rng.uniform(0, 100, n), rng.uniform(0, 100, n), rng.uniform(-np.pi, np.pi, n)], 1)
+    k1[:4], k2[:4] = 0.0, [0.0, 0.01, -0.02, 0.0]        # straight and one-sided cases
+    x, y, t, gx, gy, gt = [], [], [], [], [], []
+    for i in range(n):
+        sp = po.sample_spiral([k1[i], k2[i], sf[i]])
+        assert (len(sp[0]), len(sp[1]), len(sp[2])) == (49, 49, 50)
+        tp = ref.local_planner.transform_paths([sp], list(ego[i]) + [25.0])[0]
+        assert (len(tp[0]), len(tp[1]), len(tp[2])) == (49, 49, 49)
+        x.append(sp[0]); y.append(sp[1]); t.append(sp[2])
+        gx.append(tp[0]); gy.append(tp[1]); gt.append(tp[2])
+    np.savez_compressed(os.path.join(GOLDEN, "lattice_paths.npz"), kappa1=k1, kappa2=k2, sf=sf, ego=ego,
+                        x=np.array(x), y=np.array(y), t=np.array(t), gx=np.array(gx), gy=np.array(gy), gt=np.array(gt),
+                        **_host_facts())
+    print(f"lattice_paths.npz: {n} spirals")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -355,6 +380,8 @@ def main():
         gen_collision()
     if a.only in (None, "closedloop"):
         gen_closedloop(a.frames)
+    if a.only in (None, "lattice"):
+        gen_lattice()
     if a.only in (None, "tracking"):
         gen_tracking(min(a.frames, 200))
 

@@ -261,6 +261,16 @@ int b200mp_track_closed_loop_f64(int device, void *stream, const B200mpTrackArgs
     return launch_track_f64(device, (cudaStream_t)stream, *args);
 }
 
+int b200mp_sample_lattice_f64(int device, void *stream, int P, int n_samples, const double *kappa1,
+                              const double *kappa2, const double *sf, const double *ego_x, const double *ego_y,
+                              const double *ego_yaw, int ego_broadcast, double *px, double *py, double *pyaw,
+                              double *pcos, double *psin, double *end_xy)
+{
+    B200MP_ENTER(device);
+    return launch_lattice_f64(device, (cudaStream_t)stream, P, n_samples, kappa1, kappa2, sf, ego_x, ego_y, ego_yaw,
+                              ego_broadcast, px, py, pyaw, pcos, psin, end_xy);
+}
+
 int b200mp_fma_peak(int device, int dtype_bits, int reps, double *tflops_out)
 {
     B200MP_ENTER(device);

@@ -81,6 +81,9 @@ int launch_mpc_sample_f64(cudaStream_t st, int B, int n_seg, unsigned long long 
                           double delta_mean, double delta_sigma, double delta_clip, double torque_mean,
                           double torque_sigma, double *delta, double *torque);
 int run_fma_peak(int dtype_bits, int reps, double *tflops_out);
+int launch_lattice_f64(int device, cudaStream_t st, int P, int n_samples, const double *k1, const double *k2,
+                       const double *sf, const double *ego_x, const double *ego_y, const double *ego_yaw,
+                       int ego_broadcast, double *px, double *py, double *pyaw, double *pcos, double *psin, double *end_xy);
 int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &a);
 
 }  // namespace b200mp

@@ -394,6 +394,42 @@ class Engine:
                                                   self._ptr(clr)), "b200mp_collision_check_f64")
         return (free, clr) if want_clearance else free
 
+    def sample_lattice(self, kappa1, kappa2, sf, ego=None, n_samples: int = 50, want_trig: bool = True,
+                       want_end: bool = True):
+        """Spiral sampling + frame transform on the device (``b200mp_sample_lattice_f64``): for P optimisation
+        parameter triples ``[p1, p2, sf]`` what ``PathOptimizer.sample_spiral`` (path_optimizer.py:131-174) followed by
+        ``transform_paths`` (local_planner.py:424-470) return.  ``ego`` = ``(x, y, yaw)`` scalars (one pose for the
+        whole lattice), ``[3,P]`` per path, or ``None`` for ego-frame output.  Returns a dict of device tensors
+        ``px, py, pyaw [P, n_samples-1]`` (+ ``pcos, psin`` and ``end_xy [2,P]``), ready for
+        ``collision_check_batch(px, py, None, obstacles, ..., trig=(pcos, psin))``."""
+        k1, k2, s_f = self.dev(kappa1).reshape(-1), self.dev(kappa2).reshape(-1), self.dev(sf).reshape(-1)
+        P = k1.numel()
+        if k2.numel() != P or s_f.numel() != P:
+            raise ValueError("kappa1, kappa2 and sf must have the same length")
+        exs = eys = eyw = None
+        bcast = 0
+        if ego is not None:
+            e = self.dev(np.asarray(ego, dtype=np.float64) if not isinstance(ego, torch.Tensor) else ego)
+            if e.numel() == 3:
+                e = e.reshape(3, 1)
+                bcast = 1
+            if e.shape[0] != 3 or e.shape[1] not in (1, P):
+                raise ValueError("ego must be (x, y, yaw) or [3, P]")
+            e = e.contiguous()
+            exs, eys, eyw = e[0], e[1], e[2]
+        n = n_samples - 1
+        out = {"px": self.empty(P, n), "py": self.empty(P, n), "pyaw": self.empty(P, n)}
+        if want_trig:
+            out["pcos"], out["psin"] = self.empty(P, n), self.empty(P, n)
+        if want_end:
+            out["end_xy"] = self.empty(2, P)
+        check(self.lib.b200mp_sample_lattice_f64(self.device, self._stream(), P, int(n_samples), self._ptr(k1), self._ptr(k2),
+                                                 self._ptr(s_f), self._ptr(exs), self._ptr(eys), self._ptr(eyw), bcast,
+                                                 self._ptr(out["px"]), self._ptr(out["py"]), self._ptr(out["pyaw"]),
+                                                 self._ptr(out.get("pcos")), self._ptr(out.get("psin")),
+                                                 self._ptr(out.get("end_xy"))), "b200mp_sample_lattice_f64")
+        return out
+
     def set_collision_mode(self, mode: str) -> str:
         """``"auto"`` (FP32 screen + exact FP64 recheck of undecided pairs; default) or ``"fp64"`` (all-FP64
         kernel).  Both give bit-identical flags; process-wide.  Returns the previous mode."""

@@ -1,0 +1,68 @@
+"""GPU parity of device-side lattice generation (K6: sample_spiral + transform_paths) and of the fully
+device-resident lattice pipeline (spiral parameters -> paths -> collision flags -> best index)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from python_motionplanning_b200 import workloads as wl
+from python_motionplanning_b200.host_numerics import host_norm2_mode
+
+pytestmark = pytest.mark.gpu
+OFF, RAD, W = list(wl.CIRCLE_OFFSETS), list(wl.CIRCLE_RADII), wl.PATH_SELECT_WEIGHT
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def _close(a, ref, tol=1e-12):
+    return (np.abs(a - ref) / np.maximum(np.abs(ref), 1.0)).max() < tol
+
+
+def test_lattice_vs_literal_reference(engine, golden):
+    g = golden("lattice_paths.npz")
+    ego = g["ego"].T.copy()
+    r = engine.sample_lattice(g["kappa1"], g["kappa2"], g["sf"], ego=ego)
+    assert _close(_np(r["px"]), g["gx"]) and _close(_np(r["py"]), g["gy"]) and _close(_np(r["pyaw"]), g["gt"])
+    assert _close(_np(r["pcos"]), np.cos(g["gt"])) and _close(_np(r["psin"]), np.sin(g["gt"]))
+    assert _close(_np(r["end_xy"]), np.stack([g["gx"][:, -1], g["gy"][:, -1]]))
+    # ego frame (no transform): the raw sample_spiral output; heading j is the sample before point j
+    r0 = engine.sample_lattice(g["kappa1"], g["kappa2"], g["sf"], ego=None, want_trig=False, want_end=False)
+    assert _close(_np(r0["px"]), g["x"]) and _close(_np(r0["py"]), g["y"]) and _close(_np(r0["pyaw"]), g["t"][:, :49])
+    # one pose for the whole lattice (the planner's case: 7 goal states from one ego state)
+    e0 = g["ego"][5]
+    rb = engine.sample_lattice(g["kappa1"], g["kappa2"], g["sf"], ego=tuple(e0), want_trig=False)
+    gx, gy, gt = wl.transform_to_global(g["x"], g["y"], g["t"], np.full(96, e0[0]), np.full(96, e0[1]), np.full(96, e0[2]))
+    assert _close(_np(rb["px"]), gx) and _close(_np(rb["py"]), gy) and _close(_np(rb["pyaw"]), gt)
+
+
+def test_device_resident_lattice_pipeline_cfg3(engine):
+    """Config 3 generated on the device from its 4,096 spiral parameter triples, checked and scored without the
+    paths ever visiting the host: flags and chosen index equal the host pipeline's on this batch."""
+    w = wl.config3_lattice()
+    par = w["spiral_params"]
+    r = engine.sample_lattice(par[0], par[1], par[2], ego=w["ego"])
+    assert _close(_np(r["px"]), w["px"], 1e-11) and _close(_np(r["py"]), w["py"], 1e-11) and _close(_np(r["pyaw"]), w["pyaw"])
+    free = engine.collision_check_batch(r["px"], r["py"], None, w["obstacles"], OFF, RAD, trig=(r["pcos"], r["psin"]))
+    ref, _, _ = c_oracle.collision_check(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD)
+    mism = int((_np(free).astype(bool) != ref).sum())
+    print(f"device-generated lattice: {mism}/{len(ref)} flags differ from the host-generated pipeline")
+    assert mism <= 2                      # an obstacle point within ~1e-12 of a circle may fall either way
+    mode = host_norm2_mode()
+    best = engine.select_best_path_index_batch(r["end_xy"][0], r["end_xy"][1], free, w["goal"], W, norm_mode=mode)
+    want, _ = c_oracle.select_best(_np(r["end_xy"])[0], _np(r["end_xy"])[1], _np(free), w["goal"], W, mode)
+    assert best == want
+    if mism == 0:
+        want_host, _ = c_oracle.select_best(w["px"][:, -1], w["py"][:, -1], ref, w["goal"], W, mode)
+        print(f"best index device pipeline {best}, host pipeline {want_host}")
+
+
+def test_lattice_edge_cases(engine):
+    z = engine.sample_lattice(np.zeros(0), np.zeros(0), np.zeros(0), ego=(0.0, 0.0, 0.0))
+    assert z["px"].shape == (0, 49)
+    r = engine.sample_lattice([0.0], [0.0], [30.0], ego=(1.0, 2.0, 0.0), n_samples=4)      # straight line, 3 points
+    assert np.allclose(_np(r["px"])[0], [11.0, 21.0, 31.0]) and np.allclose(_np(r["py"])[0], 2.0)
+    big = engine.sample_lattice(np.linspace(-0.05, 0.05, 1000), np.zeros(1000), np.full(1000, 25.0), n_samples=200)
+    assert big["px"].shape == (1000, 199) and np.isfinite(_np(big["px"])).all()
+    with pytest.raises(ValueError):
+        engine.sample_lattice([0.0], [0.0, 1.0], [30.0])
