@@ -254,11 +254,19 @@ template <> struct Math<double> {
     }
 };
 
+// FP32 twin (K1f).  Same structure as the FP64 routines -- branch-free polynomials, hardware reciprocal /
+// reciprocal-square-root seeds -- with single-precision targets (1-2 ulp, tools/gen_poly.py --f32):
+//   * coefficients are literals, i.e. immediate operands of the FFMA;
+//   * 1/x and 1/sqrt(x) are the MUFU.RCP / MUFU.RSQ results themselves (1-2 ulp);
+//   * CUDA's sinf/atanf/sincosf carry range-reduction slow paths (Payne-Hanek) and quadrant selects that made
+//     the FP32 kernel only 1.2x faster than the FP64 one; the model's arguments are bounded (see above).
 template <> struct Math<float> {
     static B200MP_HD float rcp(float x)
     {
 #if defined(__CUDA_ARCH__)
-        return __frcp_rn(x);
+        float y;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
 #else
         return 1.0f / x;
 #endif
@@ -266,18 +274,11 @@ template <> struct Math<float> {
     static B200MP_HD float rsqrt(float q)
     {
 #if defined(__CUDA_ARCH__)
-        return rsqrtf(q);
+        float y;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(q));
+        return y;
 #else
         return 1.0f / ::sqrtf(q);
-#endif
-    }
-    static B200MP_HD void sincos(float x, float *s, float *c)
-    {
-#if defined(__CUDA_ARCH__)
-        ::sincosf(x, s, c);
-#else
-        *s = ::sinf(x);
-        *c = ::cosf(x);
 #endif
     }
     static B200MP_HD float mul_rn(float a, float b)
@@ -288,10 +289,105 @@ template <> struct Math<float> {
         return a * b;
 #endif
     }
+    static B200MP_HD float abs(float x) { return ::fabsf(x); }
+    static B200MP_HD int bits(float x)
+    {
+#if defined(__CUDA_ARCH__)
+        return __float_as_int(x);
+#else
+        int b;
+        memcpy(&b, &x, 4);
+        return b;
+#endif
+    }
+    static B200MP_HD float from_bits(int b)
+    {
+#if defined(__CUDA_ARCH__)
+        return __int_as_float(b);
+#else
+        float x;
+        memcpy(&x, &b, 4);
+        return x;
+#endif
+    }
+    // sin(r) = r + r*u*P(u), u = r*r, |r| <= pi/2 (5 coefficients, ~1 ulp of 1)
+    static B200MP_HD float sin_poly(float r)
+    {
+        const float u = r * r;
+        float p = -2.4061034054057018e-08f;
+        p = fmaf(p, u, 2.753562739599147e-06f);
+        p = fmaf(p, u, -0.00019841075118165463f);
+        p = fmaf(p, u, 0.00833333283662796f);
+        p = fmaf(p, u, -0.1666666716337204f);
+        return fmaf(r * u, p, r);
+    }
+    // nearest multiple of pi removed (two-term Cody-Waite, exact products through the FMA); k = its parity source
+    static B200MP_HD float reduce_pi(float y, int *k)
+    {
+        const float magic = 12582912.0f;                      // 1.5 * 2^23
+        const float t = fmaf(y, 0.31830987334251404f, magic);
+        const float kf = t - magic;
+        float r = fmaf(-kf, 3.1415927410125732f, y);
+        r = fmaf(-kf, -8.742277657347586e-08f, r);
+        *k = bits(t);
+        return r;
+    }
+    static B200MP_HD float sin(float y)
+    {
+#if B200MP_POLY
+        int k;
+        const float r = reduce_pi(y, &k);
+        return from_bits(bits(sin_poly(r)) ^ (k << 31));
+#else
+        return ::sinf(y);
+#endif
+    }
+    static B200MP_HD float atan(float x)
+    {
+#if B200MP_POLY
+        const float ax = ::fabsf(x);
+        const bool lo = ax < 0.4142135679721832f, hi = ax > 2.4142136573791504f;
+        const float num = lo ? ax : (hi ? -1.0f : ax - 1.0f);
+        const float den = lo ? 1.0f : (hi ? ax : ax + 1.0f);
+        const float off = lo ? 0.0f : (hi ? 1.5707963705062866f : 0.7853981852531433f);
+        const float t = num * rcp(den);
+        const float u = t * t;
+        float q = -0.06430986523628235f;
+        q = fmaf(q, u, 0.10737381130456924f);
+        q = fmaf(q, u, -0.14263364672660828f);
+        q = fmaf(q, u, 0.1999952346086502f);
+        q = fmaf(q, u, -0.3333333134651184f);
+        const float res = off + fmaf(t * u, q, t);
+        return ::copysignf(res, x);
+#else
+        return ::atanf(x);
+#endif
+    }
     static B200MP_HD bool sincos_core(float x, float *s, float *c)
     {
-        sincos(x, s, c);
+#if B200MP_POLY
+        int k;
+        const float r = reduce_pi(x, &k);
+        const float a = (1.5707963705062866f - ::fabsf(r)) + -4.371138828673793e-08f;
+        *s = from_bits(bits(sin_poly(r)) ^ (k << 31));
+        *c = from_bits(bits(sin_poly(a)) ^ (k << 31));
+        return ::fabsf(x) <= 8192.0f;                         // beyond: k*pi_lo is no longer negligible in FP32
+#else
+        *s = ::sinf(x);
+        *c = ::cosf(x);
         return true;
+#endif
+    }
+    static B200MP_HD void sincos(float x, float *s, float *c)
+    {
+        if (!sincos_core(x, s, c)) {
+#if defined(__CUDA_ARCH__)
+            ::sincosf(x, s, c);
+#else
+            *s = ::sinf(x);
+            *c = ::cosf(x);
+#endif
+        }
     }
     static B200MP_HD bool rotate_core(float sa, float ca, float e, float *s, float *c)
     {
@@ -302,17 +398,10 @@ template <> struct Math<float> {
         *c = fmaf(ca, ce, -(sa * se));
         return ::fabsf(e) <= 0.015625f;
     }
-    static B200MP_HD float sin(float x) { return ::sinf(x); }
-    static B200MP_HD float atan(float x) { return ::atanf(x); }
-    static B200MP_HD float abs(float x) { return ::fabsf(x); }
     static B200MP_HD bool rotate_small(float sa, float ca, float e, float *s, float *c)
     {
         if (!(::fabsf(e) <= 0.015625f)) return false;
-        const float u = e * e;
-        const float se = fmaf(e * u, -1.0f / 6, e);
-        const float ce = fmaf(u, fmaf(u, 1.0f / 24, -0.5f), 1.0f);
-        *s = fmaf(sa, ce, ca * se);
-        *c = fmaf(ca, ce, -(sa * se));
+        rotate_core(sa, ca, e, s, c);
         return true;
     }
 };

@@ -178,8 +178,9 @@ def test_param_sweep_cfg5_small_f64_and_f32_drift(engine):
     drift = rel_err(t32, ref["traj"])
     report = {n: float(drift[n - 1].max()) for n in (1, 10, 100, 500)}
     print("FP32 drift (max rel, floor 1) at steps 1/10/100/500:", report)
-    # stated, measured bound: FP32 stays within 2e-3 of FP64 over 500 steps on this sweep
-    assert report[500] < 2e-3 and report[1] < 1e-5
+    # stated, measured bound (profiles/r01_fp32_drift_cfg5.json: full config 5 measures 2.6e-5 max / 1.2e-5
+    # p99 over the 10 states after 500 steps, 1.4e-7 after one): FP32 stays within 2e-4 of FP64 over 500 steps
+    assert report[500] < 2e-4 and report[1] < 1e-6
 
 
 def test_mpc_controls_cost_argmin(engine):

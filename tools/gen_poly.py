@@ -95,5 +95,54 @@ def main():
     print("pi/2 hi lo", repr(float(half_pi)), repr(float(half_pi - mp.mpf(float(half_pi)))))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--f32" not in __import__("sys").argv:
     main()
+
+
+def main_f32():
+    """FP32 schemes of Math<float>: coefficients rounded to float, evaluated in float32 arithmetic."""
+    f32 = np.float32
+    half_pi = mp.pi / 2
+    fs = lambda u: (mp.sin(mp.sqrt(u)) / mp.sqrt(u) - 1) / u if u > 0 else mp.mpf(-1) / 6
+    fa = lambda u: (mp.atan(mp.sqrt(u)) / mp.sqrt(u) - 1) / u if u > 0 else mp.mpf(-1) / 3
+
+    def h32(coefs, u):
+        acc = np.full_like(u, f32(float(coefs[-1])))
+        for c in coefs[-2::-1]:
+            acc = (acc * u + f32(float(c))).astype(f32)
+        return acc
+
+    for n in (4, 5, 6):
+        P = cheb_fit(fs, mp.mpf(0), (half_pi * mp.mpf("1.01")) ** 2, n)
+        r = np.linspace(-float(half_pi), float(half_pi), 40001).astype(f32)
+        u = (r * r).astype(f32)
+        approx = (r + (r * u).astype(f32) * h32(P, u)).astype(f32)
+        exact = np.array([float(mp.sin(mp.mpf(float(x)))) for x in r])
+        err = np.abs(approx.astype(np.float64) - exact)
+        print(f"f32 sin half-pi n={n}: max abs err {err.max():.3e} ({err.max() / 2 ** -24:.2f} ulp of 1)")
+        if n == 5:
+            print("   kSinHalfPiF = {" + ", ".join(repr(float(f32(float(c)))) + "f" for c in P) + "}")
+    tmax = mp.tan(mp.pi / 8) * mp.mpf("1.005")
+    for n in (4, 5, 6):
+        Q = cheb_fit(fa, mp.mpf(0), tmax ** 2, n)
+        t = np.linspace(1e-4, float(tmax), 40001).astype(f32)
+        u = (t * t).astype(f32)
+        approx = (t + (t * u).astype(f32) * h32(Q, u)).astype(f32)
+        exact = np.array([float(mp.atan(mp.mpf(float(x)))) for x in t])
+        rel = np.abs(approx.astype(np.float64) - exact) / exact
+        print(f"f32 atan pi/8 n={n}: max rel err {rel.max():.3e} ({rel.max() / 2 ** -24:.2f} ulp)")
+        if n == 5:
+            print("   kAtanPi8F = {" + ", ".join(repr(float(f32(float(c)))) + "f" for c in Q) + "}")
+    pi_hi = f32(float(mp.pi))
+    pi_lo = f32(float(mp.pi - mp.mpf(float(pi_hi))))
+    hp_hi = f32(float(half_pi))
+    hp_lo = f32(float(half_pi - mp.mpf(float(hp_hi))))
+    print("f32 pi hi/lo", repr(float(pi_hi)), repr(float(pi_lo)), " pi/2 hi/lo", repr(float(hp_hi)), repr(float(hp_lo)),
+          " 1/pi", repr(float(f32(float(1 / mp.pi)))), " pi/4", repr(float(f32(float(mp.pi / 4)))),
+          " tan(pi/8)", repr(float(f32(float(mp.tan(mp.pi / 8))))), " tan(3pi/8)", repr(float(f32(float(mp.tan(3 * mp.pi / 8))))))
+
+
+if __name__ == "__main__":
+    import sys
+    if "--f32" in sys.argv:
+        main_f32()
