@@ -39,10 +39,13 @@ def test_struct_layouts_match_header(tmp_path):
     """Compile the header as plain C and compare sizeof/offsetof with the ctypes mirrors."""
     fields_p = [f[0] for f in _lib.VehicleParamsC._fields_]
     fields_r = [f[0] for f in _lib.RolloutArgsC._fields_]
+    fields_t = [f[0] for f in _lib.TrackArgsC._fields_]
     prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){',
-            'printf("%zu\\n", sizeof(B200mpVehicleParams));', 'printf("%zu\\n", sizeof(B200mpRolloutArgs));']
+            'printf("%zu\\n", sizeof(B200mpVehicleParams));', 'printf("%zu\\n", sizeof(B200mpRolloutArgs));',
+            'printf("%zu\\n", sizeof(B200mpTrackArgs));']
     prog += [f'printf("%zu\\n", offsetof(B200mpVehicleParams, {f}));' for f in fields_p]
     prog += [f'printf("%zu\\n", offsetof(B200mpRolloutArgs, {f}));' for f in fields_r]
+    prog += [f'printf("%zu\\n", offsetof(B200mpTrackArgs, {f}));' for f in fields_t]
     prog += ['return 0;}']
     src = tmp_path / "layout.c"
     src.write_text("\n".join(prog))
@@ -50,8 +53,10 @@ def test_struct_layouts_match_header(tmp_path):
     subprocess.run(["gcc", "-std=c11", str(src), "-o", str(exe)], check=True)
     out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     assert out[0] == C.sizeof(_lib.VehicleParamsC) and out[1] == C.sizeof(_lib.RolloutArgsC)
+    assert out[2] == C.sizeof(_lib.TrackArgsC)
     want = [getattr(_lib.VehicleParamsC, f).offset for f in fields_p] + [getattr(_lib.RolloutArgsC, f).offset for f in fields_r]
-    assert out[2:] == want
+    want += [getattr(_lib.TrackArgsC, f).offset for f in fields_t]
+    assert out[3:] == want
 
 
 def test_no_cpu_fallback_without_gpu():
