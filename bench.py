@@ -422,6 +422,34 @@ def secondary_metrics(eng, wl, np, torch):
     out["rollout_f32"] = {"value": B * N_STEPS / (ms32 * 1e-3), "unit": UNIT, "ms": ms32, "fp32_peak_tflops": peak32,
                           "frac_of_fp32_peak": B * N_STEPS / (ms32 * 1e-3) * ALG_FLOP_PER_STEP * 1e-12 / peak32}
     del tr32
+    # device-resident lattice pipeline: 4,096 goal states -> optimised spirals -> sampled and
+    # transformed paths -> collision flags -> best index; nothing but the goal states and obstacles is uploaded
+    par = w["spiral_params"]
+    k1d, k2d, sfd, egod = eng.dev(par[0]), eng.dev(par[1]), eng.dev(par[2]), eng.dev(w["ego"])
+    lat0 = eng.sample_lattice(k1d, k2d, sfd, ego=None, want_trig=False)          # ego-frame end states as goal states
+    tf_goal = eng.dev(3.0 * (par[0] + par[1]) * par[2] / 8.0)
+    def pipeline(optimise):
+        if optimise:
+            o = eng.optimize_spirals(lat0["end_xy"][0], lat0["end_xy"][1], tf_goal)
+            a1, a2, a3 = o["p"][0], o["p"][1], o["p"][2]
+        else:
+            a1, a2, a3 = k1d, k2d, sfd
+        lt = eng.sample_lattice(a1, a2, a3, ego=egod)
+        fr = eng.collision_check_batch(lt["px"], lt["py"], None, obs, w["offsets"], w["radii"], trig=(lt["pcos"], lt["psin"]))
+        return eng.select_best_path_index_batch(lt["end_xy"][0], lt["end_xy"][1], fr, w["goal"], w["weight"]), fr
+    for name, optimise in (("lattice_pipeline_sample_check_select", False), ("lattice_pipeline_optimise_sample_check_select", True)):
+        for _ in range(3):
+            pipeline(optimise)
+        ts = []
+        for _ in range(10):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            bi, fr = pipeline(optimise)
+            ts.append(time.perf_counter() - t0)             # select_best returns a host int: the call synchronises
+        sec = statistics.median(ts)
+        out[name] = {"ms": sec * 1e3, "paths_per_s": P / sec, "value": tests / sec, "unit": "circle-point tests/s (nominal)",
+                     "best_index": bi, "free_fraction": float(fr.float().mean().item()),
+                     "includes": "all kernels + the device->host read of the chosen index; no host trig, no path upload"}
     # closed-loop tracking: 65,536 vehicles on 16 waypoint lists of 3,000 points, 500 sub-steps =
     # 50 Stanley/PID updates each; same RK4 work per step as the headline metric plus the controllers
     st0, wps = wl.tracking_fleet(V=B, n_sets=16)

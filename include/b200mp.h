@@ -230,6 +230,21 @@ int b200mp_sample_lattice_f64(int device, void *stream, int P, int n_samples, co
                               const double *ego_yaw, int ego_broadcast, double *px, double *py, double *pyaw,
                               double *pcos, double *psin, double *end_xy);
 
+/* Batched cubic-spiral optimisation: for P goal states (xf, yf, tf) in the vehicle frame the
+ * problem PathOptimizer.optimize_spiral poses (reference libs/motionplanner/path_optimizer.py:31-88, objective and
+ * gradient :183-530): minimise fbe + 25 (fxf + fyf) + 30 ftf over p = [p1, p2, sf] from [0, 0, |goal|] within
+ * p1, p2 in [-0.5, 0.5], sf >= |goal|.  The reference solves it with scipy's L-BFGS-B (not part of its sources); this
+ * is a projected Levenberg-Marquardt iteration to a 1e-13 projected-gradient tolerance: the same minimiser, resolved
+ * further than L-BFGS-B stops (parity: parameters within ~1e-6, objective never above the reference's result).
+ *   xf, yf, tf  dev [P]
+ *   p_out       dev [3][P]  (p1, p2, sf): the kappa1 / kappa2 / sf inputs of b200mp_sample_lattice_f64
+ *   f_out       dev [P] objective at p_out, or NULL;  iters_out dev [P] int, or NULL
+ *   valid_out   dev [P] bytes or NULL: the planner's acceptance test on the spiral sampled with n_samples points,
+ *               norm([x_end - xf, y_end - yf, t_end - tf]) <= 0.1 (local_planner.py:317-323) */
+int b200mp_optimize_spirals_f64(int device, void *stream, int P, int n_samples, const double *xf, const double *yf,
+                                const double *tf, double *p_out, double *f_out, int *iters_out,
+                                unsigned char *valid_out);
+
 /* Measured pipe peak for the roofline denominator: runs a register-resident FMA chain kernel
  * (dtype_bits 64 or 32) `reps` times, synchronises, and returns the best TFLOP/s (FMA = 2 flop). */
 int b200mp_fma_peak(int device, int dtype_bits, int reps, double *tflops_out);

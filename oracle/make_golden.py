@@ -364,6 +364,68 @@ def gen_lattice(n=96):
     print(f"lattice_paths.npz: {n} spirals")
 
 
+# --------------------------------------------------------------------------- spiral optimisation (N2)
+def gen_spiral_opt(n_eval=256, n_goals=192):
+    """Literal ``PathOptimizer.objective`` / ``objective_grad`` (path_optimizer.py:183-530) at random points, and the
+    literal ``optimize_spiral`` (scipy L-BFGS-B, :31-88) on planner-like and wider goal states: the optimiser's final
+    parameters are captured from the ``sample_spiral`` call it ends with."""
+    ref = ref_loader.load()
+    po = ref.path_optimizer.PathOptimizer()
+    rng = np.random.default_rng(wl.SEED + 13)
+    ev_p = np.stack([rng.uniform(-0.2, 0.2, n_eval), rng.uniform(-0.2, 0.2, n_eval), rng.uniform(5.0, 60.0, n_eval)], 1)
+    ev_goal = np.stack([rng.uniform(5.0, 50.0, n_eval), rng.uniform(-12.0, 12.0, n_eval), rng.uniform(-0.8, 0.8, n_eval)], 1)
+    ev_f, ev_g = np.empty(n_eval), np.empty((n_eval, 3))
+    for i in range(n_eval):
+        po._xf, po._yf, po._tf = ev_goal[i]
+        ev_f[i] = po.objective(list(ev_p[i]))
+        ev_g[i] = po.objective_grad(list(ev_p[i]))
+    # goal states: the planner's own pattern (30 m look-ahead, 7 lateral offsets of 2 m, small heading, local_planner.py
+    # :154-275) plus a wider random set
+    goals = []
+    for k in range(n_goals // 2):
+        gt = rng.uniform(-0.35, 0.35)
+        gx, gy = rng.uniform(20.0, 40.0), rng.uniform(-3.0, 3.0)
+        off = (k % 7 - 3) * 2.0
+        goals.append([gx + off * np.cos(gt + np.pi / 2), gy + off * np.sin(gt + np.pi / 2), gt])
+    for k in range(n_goals - len(goals)):
+        goals.append([rng.uniform(8.0, 60.0), rng.uniform(-15.0, 15.0), rng.uniform(-1.0, 1.0)])
+    goals = np.array(goals)
+    captured = {}
+    orig = po.sample_spiral
+
+    def spy(p):
+        captured["p"] = np.array(p, float)
+        return orig(p)
+
+    po.sample_spiral = spy
+    res_p, res_f, res_end = np.empty((n_goals, 3)), np.empty(n_goals), np.empty((n_goals, 3))
+    t0 = time.time()
+    for i, g in enumerate(goals):
+        sp = po.optimize_spiral(g[0], g[1], g[2])
+        res_p[i] = captured["p"]
+        res_f[i] = po.objective(list(captured["p"]))
+        res_end[i] = [sp[0][-1], sp[1][-1], sp[2][-1]]
+    el = time.time() - t0
+    valid = np.array([np.linalg.norm(res_end[i] - goals[i]) <= 0.1 for i in range(n_goals)])     # local_planner.py:317-323
+    # get_goal_state_set (local_planner.py:154-275) on random ego states / goal waypoints of a curved waypoint list
+    lp = ref.local_planner.LocalPlanner(30, 7, 2, [-1.0, 1.0, 3.0], [1.5] * 3, 10, 1.0, 1.5, 2.0, 3.5)
+    th = np.linspace(0.0, 1.2, 400)
+    wps = np.stack([60.0 * np.sin(th), 60.0 * (1 - np.cos(th)), np.full(400, 25.0)], 1)
+    gs_in, gs_out = [], []
+    for k in range(48):
+        gi = int(rng.integers(1, 400)) if k else 399                     # includes the last index (backward difference)
+        ego = [wps[max(gi - 60, 0), 0] + rng.uniform(-2, 2), wps[max(gi - 60, 0), 1] + rng.uniform(-2, 2),
+               rng.uniform(-np.pi, np.pi), 25.0]
+        out = lp.get_goal_state_set(gi, list(wps[gi]), wps.tolist(), ego)
+        gs_in.append([gi] + ego[:3])
+        gs_out.append(out)
+    np.savez_compressed(os.path.join(GOLDEN, "spiral_opt.npz"), goalset_waypoints=wps, goalset_in=np.array(gs_in),
+                        goalset_out=np.array(gs_out), eval_p=ev_p, eval_goal=ev_goal, eval_f=ev_f, eval_grad=ev_g,
+                        goals=goals, res_p=res_p, res_f=res_f, res_end=res_end, valid=valid,
+                        literal_spirals_per_s=n_goals / el, **_host_facts())
+    print(f"spiral_opt.npz: {n_eval} objective/gradient evaluations, {n_goals} optimisations in {el:.1f}s, valid {valid.mean():.2f}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -380,6 +442,8 @@ def main():
         gen_collision()
     if a.only in (None, "closedloop"):
         gen_closedloop(a.frames)
+    if a.only in (None, "spiral_opt"):
+        gen_spiral_opt()
     if a.only in (None, "lattice"):
         gen_lattice()
     if a.only in (None, "tracking"):

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "b200mp_select_best_f64": (_i, [_i, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp]),
     "b200mp_track_closed_loop_f64": (_i, [_i, _vp, C.POINTER(TrackArgsC)]),
     "b200mp_sample_lattice_f64": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200mp_optimize_spirals_f64": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200mp_fma_peak": (_i, [_i, _i, _i, _dp]),
     "b200mp_shutdown": (_i, []),
 }

@@ -271,6 +271,13 @@ int b200mp_sample_lattice_f64(int device, void *stream, int P, int n_samples, co
                               ego_broadcast, px, py, pyaw, pcos, psin, end_xy);
 }
 
+int b200mp_optimize_spirals_f64(int device, void *stream, int P, int n_samples, const double *xf, const double *yf,
+                                const double *tf, double *p_out, double *f_out, int *iters_out, unsigned char *valid_out)
+{
+    B200MP_ENTER(device);
+    return launch_spiral_opt_f64(device, (cudaStream_t)stream, P, n_samples, xf, yf, tf, p_out, f_out, iters_out, valid_out);
+}
+
 int b200mp_fma_peak(int device, int dtype_bits, int reps, double *tflops_out)
 {
     B200MP_ENTER(device);

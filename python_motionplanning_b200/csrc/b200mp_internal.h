@@ -84,6 +84,8 @@ int run_fma_peak(int dtype_bits, int reps, double *tflops_out);
 int launch_lattice_f64(int device, cudaStream_t st, int P, int n_samples, const double *k1, const double *k2,
                        const double *sf, const double *ego_x, const double *ego_y, const double *ego_yaw,
                        int ego_broadcast, double *px, double *py, double *pyaw, double *pcos, double *psin, double *end_xy);
+int launch_spiral_opt_f64(int device, cudaStream_t st, int P, int n_samples, const double *xf, const double *yf,
+                          const double *tf, double *p_out, double *f_out, int *it_out, unsigned char *valid_out);
 int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &a);
 
 }  // namespace b200mp

@@ -126,4 +126,214 @@ int launch_lattice_f64(int device, cudaStream_t st, int P, int n_samples, const 
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// K7: batched cubic-spiral optimisation -- the problem PathOptimizer.optimize_spiral poses
+// (reference libs/motionplanner/path_optimizer.py:31-88) with the objective of :183-530,
+//     J(p1, p2, sf) = fbe + 25 (fxf + fyf) + 30 ftf,
+//     theta(u) = sf g(u),  g(u) = p1 G1(u) + p2 G2(u),  G1 = 4.5u^2 - 7.5u^3 + 3.375u^4,  G2 = -2.25u^2 + 6u^3 - 3.375u^4
+//     x = sf/24 sum_i w_i cos theta(i/8),  y likewise with sin  (8-panel Simpson, w = 1 4 2 4 2 4 2 4 1)
+//     fxf = (xf - x)^2, fyf = (yf - y)^2, ftf = (tf - theta(1))^2, fbe = sf (324 p1^2 + 324 p2^2 - 81 p1 p2)/840
+// (the reference's fxf/fyf/ftf/fbe and *_grad are machine-generated expansions of exactly these), start
+// [0, 0, |goal|], bounds p1, p2 in [-0.5, 0.5], sf >= |goal|.  The reference hands the problem to scipy's L-BFGS-B
+// (ftol 2.2e-9, gtol 1e-5), which is not part of its sources; here one thread per goal state runs a projected
+// Levenberg-Marquardt iteration (model Hessian 2 J^T W J + Hessian(fbe), active bounds frozen, step accepted when J
+// decreases) to a projected-gradient tolerance of 1e-13: the same minimiser, resolved further than L-BFGS-B stops.
+// The planner's acceptance test (|end - goal| <= 0.1 on the SAMPLED spiral, local_planner.py:317-323) is evaluated
+// in the same thread with the sampler's trapezoid.
+struct SpiralEval {
+    double f, r[3], J[3][3], g[3];
+};
+
+__device__ __forceinline__ double spiral_objective(double p1, double p2, double sf, double xf, double yf, double tf,
+                                                   SpiralEval *e)
+{
+    const double w[9] = {1, 4, 2, 4, 2, 4, 2, 4, 1};
+    double sc = 0, ss = 0, s1 = 0, s2 = 0, sg = 0, c1 = 0, c2 = 0, cg = 0, g_end = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const double u = i * 0.125, u2 = u * u;
+        const double G1 = u2 * (4.5 + u * (-7.5 + 3.375 * u)), G2 = u2 * (-2.25 + u * (6.0 - 3.375 * u));
+        const double g = p1 * G1 + p2 * G2;
+        double sn, cs;
+        sincos(sf * g, &sn, &cs);
+        sc += w[i] * cs;
+        ss += w[i] * sn;
+        if (e) {
+            s1 += w[i] * sn * G1;
+            s2 += w[i] * sn * G2;
+            sg += w[i] * sn * g;
+            c1 += w[i] * cs * G1;
+            c2 += w[i] * cs * G2;
+            cg += w[i] * cs * g;
+        }
+        g_end = g;
+    }
+    const double k = sf / 24.0;
+    const double ex = xf - k * sc, ey = yf - k * ss, et = tf - sf * g_end;
+    const double q = (324.0 * p1 * p1 + 324.0 * p2 * p2 - 81.0 * p1 * p2) / 840.0;
+    const double f = sf * q + 25.0 * (ex * ex + ey * ey) + 30.0 * et * et;
+    if (e) {
+        e->f = f;
+        e->r[0] = ex; e->r[1] = ey; e->r[2] = et;
+        e->J[0][0] = sf * k * s1;  e->J[0][1] = sf * k * s2;  e->J[0][2] = -(sc / 24.0 - k * sg);
+        e->J[1][0] = -sf * k * c1; e->J[1][1] = -sf * k * c2; e->J[1][2] = -(ss / 24.0 + k * cg);
+        e->J[2][0] = -sf * 0.375;  e->J[2][1] = -sf * 0.375;  e->J[2][2] = -g_end;
+        const double wt[3] = {25.0, 25.0, 30.0};
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            e->g[j] = 2.0 * (wt[0] * ex * e->J[0][j] + wt[1] * ey * e->J[1][j] + wt[2] * et * e->J[2][j]);
+        e->g[0] += sf * (648.0 * p1 - 81.0 * p2) / 840.0;
+        e->g[1] += sf * (648.0 * p2 - 81.0 * p1) / 840.0;
+        e->g[2] += q;
+    }
+    return f;
+}
+
+// solves A x = b for the free variables (others get x = 0); returns false when a pivot vanishes
+__device__ __forceinline__ bool solve3_masked(double A[3][3], const double b[3], const bool fr[3], double x[3])
+{
+    double M[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) M[i][j] = (fr[i] && fr[j]) ? A[i][j] : (i == j ? 1.0 : 0.0);
+        M[i][3] = fr[i] ? b[i] : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int piv = c;
+#pragma unroll
+        for (int r = c + 1; r < 3; ++r)
+            if (fabs(M[r][c]) > fabs(M[piv][c])) piv = r;
+        if (!(fabs(M[piv][c]) > 0.0)) return false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double t = M[c][j];
+            M[c][j] = M[piv][j];
+            M[piv][j] = t;
+        }
+#pragma unroll
+        for (int r = c + 1; r < 3; ++r) {
+            const double m = M[r][c] / M[c][c];
+#pragma unroll
+            for (int j = c; j < 4; ++j) M[r][j] -= m * M[c][j];
+        }
+    }
+    x[2] = M[2][3] / M[2][2];
+    x[1] = (M[1][3] - M[1][2] * x[2]) / M[1][1];
+    x[0] = (M[0][3] - M[0][1] * x[1] - M[0][2] * x[2]) / M[0][0];
+    return true;
+}
+
+__global__ void __launch_bounds__(64)
+spiral_opt_kernel(int P, int n_samples, const double *__restrict__ gxf, const double *__restrict__ gyf,
+                  const double *__restrict__ gtf, double *__restrict__ p_out, double *__restrict__ f_out,
+                  int *__restrict__ it_out, unsigned char *__restrict__ valid_out)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P) return;
+    const double xf = gxf[r], yf = gyf[r], tf = gtf[r];
+    const double sf0 = sqrt(xf * xf + yf * yf);               // the straight-line distance bounds sf from below (:58, :74)
+    const double lo[3] = {-0.5, -0.5, sf0}, hi[3] = {0.5, 0.5, INFINITY};
+    double p[3] = {0.0, 0.0, sf0};
+    SpiralEval e;
+    double f = spiral_objective(p[0], p[1], p[2], xf, yf, tf, &e);
+    double lam = 1.0e-3;
+    int it = 0;
+    for (; it < 100; ++it) {
+        bool fr[3];
+        double pgmax = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            fr[j] = !((p[j] <= lo[j] && e.g[j] > 0.0) || (p[j] >= hi[j] && e.g[j] < 0.0));
+            if (fr[j]) pgmax = fmax(pgmax, fabs(e.g[j]));
+        }
+        if (!(pgmax > 1.0e-13 * fmax(1.0, fabs(f)))) break;
+        double H[3][3];
+        const double wt[3] = {25.0, 25.0, 30.0};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                H[i][j] = 2.0 * (wt[0] * e.J[0][i] * e.J[0][j] + wt[1] * e.J[1][i] * e.J[1][j] + wt[2] * e.J[2][i] * e.J[2][j]);
+        const double h01 = -81.0 * p[2] / 840.0, h02 = (648.0 * p[0] - 81.0 * p[1]) / 840.0, h12 = (648.0 * p[1] - 81.0 * p[0]) / 840.0;
+        H[0][0] += 648.0 * p[2] / 840.0;
+        H[1][1] += 648.0 * p[2] / 840.0;
+        H[0][1] += h01; H[1][0] += h01;
+        H[0][2] += h02; H[2][0] += h02;
+        H[1][2] += h12; H[2][1] += h12;
+        bool improved = false;
+        for (int tries = 0; tries < 30; ++tries) {
+            double A[3][3], nb[3], step[3], q[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) A[i][j] = H[i][j];
+                A[i][i] += lam * fmax(H[i][i], 1.0e-12);
+                nb[i] = -e.g[i];
+            }
+            if (!solve3_masked(A, nb, fr, step)) {
+                lam *= 10.0;
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) q[j] = fmin(fmax(p[j] + step[j], lo[j]), hi[j]);
+            const double fq = spiral_objective(q[0], q[1], q[2], xf, yf, tf, nullptr);
+            if (fq < f) {
+                p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
+                lam = fmax(lam * 0.2, 1.0e-12);
+                improved = true;
+                break;
+            }
+            lam *= 10.0;
+        }
+        if (!improved) break;
+        f = spiral_objective(p[0], p[1], p[2], xf, yf, tf, &e);
+    }
+    p_out[r] = p[0];
+    p_out[(size_t)P + r] = p[1];
+    p_out[2 * (size_t)P + r] = p[2];
+    if (f_out) f_out[r] = f;
+    if (it_out) it_out[r] = it;
+    if (valid_out) {
+        // the planner accepts a spiral when its SAMPLED end state is within 0.1 of the goal (local_planner.py:317-323)
+        const double S = p[2];
+        const double b2 = -((0.0 - 9.0 * p[0]) + 9.0 * p[1] / 2.0) / S / 2, c3 = ((0.0 - 45.0 * p[0] / 2.0) + 18.0 * p[1]) / (S * S) / 3,
+                     d4 = -((0.0 - 27.0 * p[0] / 2.0) + 27.0 * p[1] / 2.0) / (S * S * S) / 4;
+        const double step = S / (double)(n_samples - 1);
+        double s_prev = 0, c_prev = 1, n_prev = 0, X = 0, Y = 0, t = 0;
+        for (int j = 1; j < n_samples; ++j) {
+            const double s = (j == n_samples - 1) ? S : (double)j * step;
+            const double s2 = s * s;
+            t = (b2 * s2 + c3 * (s2 * s)) + d4 * (s2 * s2);
+            double cn, sn;
+            sincos(t, &sn, &cn);
+            X += (s - s_prev) * (cn + c_prev) / 2.0;
+            Y += (s - s_prev) * (sn + n_prev) / 2.0;
+            s_prev = s; c_prev = cn; n_prev = sn;
+        }
+        const double dx = X - xf, dy = Y - yf, dt = t - tf;
+        valid_out[r] = !(sqrt(dx * dx + dy * dy + dt * dt) > 0.1) ? 1 : 0;
+    }
+}
+
+int launch_spiral_opt_f64(int device, cudaStream_t st, int P, int n_samples, const double *xf, const double *yf,
+                          const double *tf, double *p_out, double *f_out, int *it_out, unsigned char *valid_out)
+{
+    (void)device;
+    if (P < 0 || n_samples < 2) {
+        set_error("optimize_spirals: bad sizes P=%d n_samples=%d", P, n_samples);
+        return B200MP_E_ARG;
+    }
+    if (P == 0) return 0;
+    if (!xf || !yf || !tf || !p_out) {
+        set_error("optimize_spirals: xf, yf, tf and p_out must be non-NULL");
+        return B200MP_E_ARG;
+    }
+    spiral_opt_kernel<<<(P + 63) / 64, 64, 0, st>>>(P, n_samples, xf, yf, tf, p_out, f_out, it_out, valid_out);
+    B200MP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace b200mp

@@ -430,6 +430,41 @@ class Engine:
                                                  self._ptr(out.get("end_xy"))), "b200mp_sample_lattice_f64")
         return out
 
+    def optimize_spirals(self, xf, yf, tf, n_samples: int = 50):
+        """Batched ``PathOptimizer.optimize_spiral`` (path_optimizer.py:31-88) for P goal states in the vehicle frame
+        (``b200mp_optimize_spirals_f64``).  Returns device tensors ``p [3,P]`` (p1, p2, sf), ``objective [P]``,
+        ``iterations [P]`` (int32) and ``valid [P]`` (uint8: the planner's acceptance test, local_planner.py:317-323)."""
+        x, y, t = self.dev(xf).reshape(-1), self.dev(yf).reshape(-1), self.dev(tf).reshape(-1)
+        P = x.numel()
+        if y.numel() != P or t.numel() != P:
+            raise ValueError("xf, yf and tf must have the same length")
+        out = {"p": self.empty(3, P), "objective": self.empty(P), "iterations": self.empty(P, dtype=torch.int32),
+               "valid": self.empty(P, dtype=torch.uint8)}
+        check(self.lib.b200mp_optimize_spirals_f64(self.device, self._stream(), P, int(n_samples), self._ptr(x), self._ptr(y),
+                                                   self._ptr(t), self._ptr(out["p"]), self._ptr(out["objective"]),
+                                                   self._ptr(out["iterations"]), self._ptr(out["valid"])),
+              "b200mp_optimize_spirals_f64")
+        return out
+
+    def plan_lattice(self, goals_local, ego, obstacles, offsets: Sequence[float], radii: Sequence[float], goal_xy,
+                     weight: float, n_samples: int = 50):
+        """The planner's numeric core on the device, end to end (local_planner.py:367-379): optimise one spiral per
+        goal state (vehicle frame ``goals_local [3,P]`` = xf, yf, tf), sample and transform the spirals with ``ego`` =
+        (x, y, yaw), test them against ``obstacles [M,2]`` and select the best path index.  Paths whose optimisation fails
+        the planner's acceptance test are treated as colliding (the reference drops them from the list, :317-323, so
+        the returned index refers to the FULL goal list).  Returns ``(best_index or None, dict of device tensors)``."""
+        g = self.dev(goals_local)
+        if g.dim() != 2 or g.shape[0] != 3:
+            raise ValueError("goals_local must be [3, P]")
+        opt = self.optimize_spirals(g[0], g[1], g[2], n_samples)
+        lat = self.sample_lattice(opt["p"][0], opt["p"][1], opt["p"][2], ego=ego, n_samples=n_samples)
+        free = self.collision_check_batch(lat["px"], lat["py"], None, obstacles, offsets, radii, trig=(lat["pcos"], lat["psin"]))
+        free = free & opt["valid"]
+        best = self.select_best_path_index_batch(lat["end_xy"][0], lat["end_xy"][1], free, goal_xy, weight)
+        lat.update(opt)
+        lat["free"] = free
+        return best, lat
+
     def set_collision_mode(self, mode: str) -> str:
         """``"auto"`` (FP32 screen + exact FP64 recheck of undecided pairs; default) or ``"fp64"`` (all-FP64
         kernel).  Both give bit-identical flags; process-wide.  Returns the previous mode."""
