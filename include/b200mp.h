@@ -147,6 +147,16 @@ int b200mp_collision_check_f64(int device, void *stream, int P, int n_pts, int n
                                const double *psin, const double *pyaw, int yaw_stride, int M, const double *obs,
                                unsigned char *free_out, double *min_clear);
 
+/* How the fast-path rollout / tracking kernels (FP64, one tyre triple, no logging, no per-rollout mu_max) evaluate the
+ * combined-slip friction D sin(C atan(B s)) / s (vehicle_model.py:296-348).  AUTO (default): from a table of
+ * degree-12 polynomials in 1 + (B s)^2 built on the host by b200mp_set_params (long double, audited to <= 3e-16
+ * relative), no square root / reciprocal / atan / sin in the kernel; slips beyond the table and non-finite values
+ * repeat the step on the closed form.  CLOSED_FORM: always the sqrt / atan / sin sequence (A/B checks).  Both are
+ * within the 1e-9 parity contract with ~1e-13 to spare.  Process-wide; returns the previous mode, or B200MP_E_ARG. */
+#define B200MP_FRICTION_AUTO 0
+#define B200MP_FRICTION_CLOSED_FORM 1
+int b200mp_set_friction_mode(int mode);
+
 /* Arithmetic of the boolean-only collision test (min_clear == NULL).  AUTO (default): every circle/point
  * pair is screened in FP32 with a proven error bound and only undecided pairs repeat the exact FP64
  * sequence above -- the flags are bit-identical to FP64_ONLY for every input, the FP64 pipe is simply not

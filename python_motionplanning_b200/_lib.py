@@ -61,6 +61,7 @@ PROTOTYPES = {
     "b200mp_mpc_sample_controls_f64": (_i, [_i, _vp, _i, _i, _ull, _ll, _d, _d, _d, _d, _d, _vp, _vp]),
     "b200mp_argmin_f64": (_i, [_i, _vp, _ll, _vp, _ll, _vp, _vp]),
     "b200mp_collision_check_f64": (_i, [_i, _vp, _i, _i, _i, _dp, _dp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "b200mp_set_friction_mode": (_i, [_i]),
     "b200mp_set_collision_mode": (_i, [_i]),
     "b200mp_select_best_f64": (_i, [_i, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp]),
     "b200mp_track_closed_loop_f64": (_i, [_i, _vp, C.POINTER(TrackArgsC)]),

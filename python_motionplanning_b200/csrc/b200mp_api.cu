@@ -33,6 +33,8 @@ int cuda_fail(cudaError_t e, const char *what)
 static DeviceState g_states[kMaxDevices];
 static std::mutex g_mutex;
 
+static std::atomic<int> g_friction_mode{B200MP_FRICTION_AUTO};
+int friction_mode() { return g_friction_mode.load(std::memory_order_relaxed); }
 static std::atomic<int> g_collision_mode{B200MP_COLLISION_AUTO};
 int collision_mode() { return g_collision_mode.load(std::memory_order_relaxed); }
 
@@ -168,6 +170,22 @@ int b200mp_set_params(int device, const B200mpVehicleParams *host_sets, int n_se
         if (e == cudaSuccess) {
             memcpy(&ds.set0, &host_sets[0], sizeof(HostParams));
             ds.n_sets = n_sets;
+            // friction table of set 0 (fast-path kernels); skipped when the four tyres differ or the fit is not at
+            // rounding level (then the closed-form path is used)
+            const HostParams &h = ds.set0;
+            bool uniform = true;
+            for (int i = 1; i < 4; ++i) uniform = uniform && h.B[i] == h.B[0] && h.C[i] == h.C[0] && h.D[i] == h.D[0];
+            ds.mu_table_B2 = 0.0;
+            if (uniform && h.B[0] > 0.0 && h.C[0] > 0.0 && h.C[0] < 4.0 && h.D[0] == h.D[0]) {
+                static double host_table[kMuTableDoubles];
+                ds.mu_table_err = build_mu_table(h.B[0], h.C[0], h.D[0], host_table);
+                if (ds.mu_table_err < 1.0e-15) {
+                    if (!ds.mu_table) e = cudaMalloc((void **)&ds.mu_table, sizeof(host_table));
+                    if (e == cudaSuccess) e = cudaMemcpy(ds.mu_table, host_table, sizeof(host_table), cudaMemcpyHostToDevice);
+                    if (e == cudaSuccess) ds.mu_table_B2 = h.B[0] * h.B[0];
+                }
+            }
+            if (e != cudaSuccess) rc = cuda_fail(e, "set_params (friction table)");
         } else {
             rc = cuda_fail(e, "set_params");
         }
@@ -230,6 +248,16 @@ int b200mp_collision_check_f64(int device, void *stream, int P, int n_pts, int n
     B200MP_ENTER(device);
     return launch_collision_f64(device, (cudaStream_t)stream, P, n_pts, n_circ, off, rad, px, py, pcos, psin, pyaw,
                                 yaw_stride, M, obs, free_out, min_clear);
+}
+
+int b200mp_set_friction_mode(int mode)
+{
+    g_err[0] = 0;
+    if (mode != B200MP_FRICTION_AUTO && mode != B200MP_FRICTION_CLOSED_FORM) {
+        set_error("set_friction_mode: unknown mode %d", mode);
+        return B200MP_E_ARG;
+    }
+    return g_friction_mode.exchange(mode);
 }
 
 int b200mp_set_collision_mode(int mode)
@@ -296,12 +324,13 @@ int b200mp_shutdown(void)
     (void)cudaGetDevice(&prev);
     for (int d = 0; d < n && d < kMaxDevices; ++d) {
         DeviceState &ds = g_states[d];
-        if (!ds.table64 && !ds.table32 && !ds.scratch && !ds.sched_ring) continue;
+        if (!ds.table64 && !ds.table32 && !ds.scratch && !ds.sched_ring && !ds.mu_table) continue;
         if (cudaSetDevice(d) != cudaSuccess) continue;
         (void)cudaDeviceSynchronize();
         if (ds.table64) (void)cudaFree(ds.table64);
         if (ds.table32) (void)cudaFree(ds.table32);
         if (ds.scratch) (void)cudaFree(ds.scratch);
+        if (ds.mu_table) (void)cudaFree(ds.mu_table);
         if (ds.sched_ring) {
             (void)cudaFree(ds.sched_ring);
             for (int i = 0; i < kSchedSlots; ++i) (void)cudaEventDestroy(ds.sched_event[i]);

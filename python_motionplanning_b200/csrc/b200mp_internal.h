@@ -29,6 +29,10 @@ struct DeviceState {
     HostParams set0{};
     DevParams<double> *table64 = nullptr;
     DevParams<float> *table32 = nullptr;
+    // tabulated friction function of parameter set 0 (vehicle_rhs.cuh: build_mu_table), when its four tyres are equal
+    double *mu_table = nullptr;
+    double mu_table_B2 = 0.0;
+    double mu_table_err = 0.0;
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     // ring of small work-queue areas for time-sliced rollout launches (one per launch in flight)
@@ -43,6 +47,8 @@ int ensure_scratch(int device, size_t bytes, void **out);
 // records `*done` on its stream after the launch that uses the area.
 int acquire_sched_slot(int device, void **area, cudaEvent_t *done);
 
+// B200MP_FRICTION_* (process-wide, b200mp_set_friction_mode)
+int friction_mode();
 // B200MP_COLLISION_* (process-wide, b200mp_set_collision_mode)
 int collision_mode();
 

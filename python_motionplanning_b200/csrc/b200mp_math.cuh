@@ -116,6 +116,27 @@ template <> struct Math<double> {
         return (int)(uint32_t)b;
 #endif
     }
+    static B200MP_HD int hi_word(double x)
+    {
+#if defined(__CUDA_ARCH__)
+        return __double2hiint(x);
+#else
+        uint64_t b;
+        memcpy(&b, &x, 8);
+        return (int)(uint32_t)(b >> 32);
+#endif
+    }
+    static B200MP_HD double from_words(int hi, int lo)
+    {
+#if defined(__CUDA_ARCH__)
+        return __hiloint2double(hi, lo);
+#else
+        const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+        double x;
+        memcpy(&x, &b, 8);
+        return x;
+#endif
+    }
     static B200MP_HD double xor_sign(double x, int bit0_source)
     {
         // flips the sign of x when bit 0 of bit0_source is set
@@ -290,6 +311,8 @@ template <> struct Math<float> {
 #endif
     }
     static B200MP_HD float abs(float x) { return ::fabsf(x); }
+    static B200MP_HD int hi_word(double) { return 0; }             // the tabulated path is FP64 only
+    static B200MP_HD double from_words(int, int) { return 0.0; }
     static B200MP_HD int bits(float x)
     {
 #if defined(__CUDA_ARCH__)

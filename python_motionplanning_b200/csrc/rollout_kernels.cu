@@ -50,6 +50,8 @@ template <typename R> struct RolloutDev {
     R *traj, *aux, *state_end, *cost;
     const R *cost_in, *cost_ref;
     R w_u, u_ref;
+    const double *mu_table;   // [kMuTableDoubles] friction table of set 0 (TAB kernels), B^2 beside it
+    double mu_B2;
 };
 
 // Launch shape.  65,536 rollouts (config 2) are 2,048 warps = 13.8 per SM: with <= 144 registers per
@@ -73,12 +75,20 @@ constexpr bool kRolloutSpeculative = B200MP_RK4_SPECULATIVE != 0;
 #endif
 
 // SLICED = false: one CTA = one rollout block for the whole launch (no queue code in the kernel at all).
-template <typename R, bool REAR0, bool GENERIC, bool AUX, bool SLICED>
+template <typename R, bool REAR0, bool GENERIC, bool AUX, bool SLICED, bool TAB>
 __global__ void B200MP_ROLLOUT_BOUNDS
 rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constant__ DevParams<R> P0,
                    const __grid_constant__ SliceSched sc)
 {
     __shared__ int s_item;
+    __shared__ __align__(16) double s_mu[TAB ? kMuTableDoubles : 2];
+    MuTableView T;
+    T.c = s_mu;
+    T.B2 = a.mu_B2;
+    if (TAB) {
+        for (int i = threadIdx.x; i < kMuTableDoubles; i += kRolloutBlock) s_mu[i] = a.mu_table[i];
+        __syncthreads();
+    }
     const size_t B = (size_t)a.B;
     int item = blockIdx.x;
     {
@@ -165,7 +175,7 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
 #pragma unroll 1
                 for (; n < seg_end; ++n) {
                     R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
-                    rk4_step<R, REAR0, AUX, !GENERIC, kRolloutSpeculative && !GENERIC && !AUX>(P, D, c, a.dt, y, ax, ay, sdot, outs);
+                    rk4_step<R, REAR0, AUX, !GENERIC, (kRolloutSpeculative && !GENERIC && !AUX) || TAB, TAB>(P, D, c, a.dt, y, ax, ay, sdot, outs, T);
                     if (a.cost) {
                         const size_t g = (size_t)(a.step0 + n);
                         const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;
@@ -331,16 +341,19 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
                         ds.set0.D[i] == ds.set0.D[0];
     const bool generic = g.mu != nullptr || g.param_set != nullptr || !uniform_tyres;
     const bool aux = g.aux != nullptr;
-    if (aux) {
-        // logging mode (state_dot + outputs): one generic instantiation per steer layout
-        return rear0 ? start_rollout<R>(rk4_rollout_kernel<R, true, true, true, false>, rk4_rollout_kernel<R, true, true, true, true>, device, st, a, P0)
-                     : start_rollout<R>(rk4_rollout_kernel<R, false, true, true, false>, rk4_rollout_kernel<R, false, true, true, true>, device, st, a, P0);
-    }
-    if (rear0)
-        return generic ? start_rollout<R>(rk4_rollout_kernel<R, true, true, false, false>, rk4_rollout_kernel<R, true, true, false, true>, device, st, a, P0)
-                       : start_rollout<R>(rk4_rollout_kernel<R, true, false, false, false>, rk4_rollout_kernel<R, true, false, false, true>, device, st, a, P0);
-    return generic ? start_rollout<R>(rk4_rollout_kernel<R, false, true, false, false>, rk4_rollout_kernel<R, false, true, false, true>, device, st, a, P0)
-                   : start_rollout<R>(rk4_rollout_kernel<R, false, false, false, false>, rk4_rollout_kernel<R, false, false, false, true>, device, st, a, P0);
+    // tabulated friction: FP64 fast path only, when set_params could build the table of set 0
+    const bool tab = sizeof(R) == 8 && !generic && !aux && ds.mu_table && ds.mu_table_B2 > 0.0 &&
+                     friction_mode() == B200MP_FRICTION_AUTO;
+    a.mu_table = ds.mu_table;
+    a.mu_B2 = ds.mu_table_B2;
+#define B200MP_START(REAR0, GENERIC, AUX, TAB) \
+    start_rollout<R>(rk4_rollout_kernel<R, REAR0, GENERIC, AUX, false, TAB>, rk4_rollout_kernel<R, REAR0, GENERIC, AUX, true, TAB>, device, st, a, P0)
+    if (aux)   // logging mode (state_dot + outputs): one generic instantiation per steer layout
+        return rear0 ? B200MP_START(true, true, true, false) : B200MP_START(false, true, true, false);
+    if (generic) return rear0 ? B200MP_START(true, true, false, false) : B200MP_START(false, true, false, false);
+    if (tab) return rear0 ? B200MP_START(true, false, false, (sizeof(R) == 8)) : B200MP_START(false, false, false, (sizeof(R) == 8));
+    return rear0 ? B200MP_START(true, false, false, false) : B200MP_START(false, false, false, false);
+#undef B200MP_START
 }
 
 int launch_rollout_f64(int device, cudaStream_t st, const B200mpRolloutArgs &a) { return launch_rollout<double>(device, st, a); }

@@ -46,6 +46,8 @@ struct TrackDev {
     const double *seg, *head, *cum, *rmax, *clean;
     double *traj, *log, *state_end, *ctrl_end;
     int *target_idx;
+    const double *mu_table;   // friction table of parameter set 0 (vehicle_rhs.cuh), used by the no-log kernel
+    double mu_B2;
 };
 
 __device__ __forceinline__ double host_sq(double v0, double v1, int mode)
@@ -256,10 +258,18 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
     return la;
 }
 
-template <bool LOG>
+template <bool LOG, bool TAB>
 __global__ void __launch_bounds__(kTrackBlock)
 track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevParams<double> P0)
 {
+    __shared__ __align__(16) double s_mu[TAB ? kMuTableDoubles : 2];
+    MuTableView T;
+    T.c = s_mu;
+    T.B2 = a.mu_B2;
+    if (TAB) {
+        for (int i = threadIdx.x; i < kMuTableDoubles; i += kTrackBlock) s_mu[i] = a.mu_table[i];
+        __syncthreads();
+    }
     const int set = blockIdx.x / a.blocks_per_set;
     const int local = (blockIdx.x - set * a.blocks_per_set) * kTrackBlock + threadIdx.x;
     const int r = set * a.vps + local;
@@ -337,7 +347,7 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
 #pragma unroll 1
         for (; n < n_end; ++n) {
             double sdot[LOG ? 10 : 1], outs[LOG ? 18 : 1];
-            rk4_step<double, true, LOG, true, !LOG>(P0, P0.Dc, c, a.dt, y, ax, ay, sdot, outs);
+            rk4_step<double, true, LOG, true, !LOG, TAB>(P0, P0.Dc, c, a.dt, y, ax, ay, sdot, outs, T);
             if (a.store_stride > 0 && --until_store == 0) {
                 until_store = a.store_stride;
                 if (tp) {
@@ -466,10 +476,15 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
         set_error("track: grid too large");
         return B200MP_E_ARG;
     }
+    a.mu_table = ds.mu_table;
+    a.mu_B2 = ds.mu_table_B2;
+    const bool tab = ds.mu_table && ds.mu_table_B2 > 0.0 && friction_mode() == B200MP_FRICTION_AUTO;
     if (g.log)
-        track_kernel<true><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
+        track_kernel<true, false><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
+    else if (tab)
+        track_kernel<false, true><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
     else
-        track_kernel<false><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
+        track_kernel<false, false><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
     B200MP_CUDA(cudaGetLastError());
     return 0;
 }

@@ -62,6 +62,111 @@ template <typename R> inline DevParams<R> derive_params(const HostParams &p)
     return d;
 }
 
+// ---- tabulated combined-slip friction (fast path) -------------------------------------------------
+// Per wheel and stage the model needs  mu/s = D sin(C atan(B s)) / s  with s = sqrt(sx^2 + sy^2)
+// (vehicle_model.py:296-348): a square root, a reciprocal, an atan and a sin, ~45 FP64 instructions even
+// with the custom routines of b200mp_math.cuh -- 60 % of the kernel.  As a function of
+//     x = 1 + (B s)^2 = 1 + B^2 (sx^2 + sy^2)
+// the quantity  G(x) = D B sin(C atan(sqrt(x-1))) / sqrt(x-1)  (so that mu_x = sx G, mu_y = sy G) is analytic
+// on x > 0 (sin(C atan t)/t is even in t; the nearest singularity is x = 0), needs neither the square
+// root nor the reciprocal, and is 0/0-free at zero slip (G(1) = D B C).  For ONE tyre (B, C, D) it is
+// tabulated on the host when the parameter set is uploaded: 32 intervals per binade of x (bounded by the
+// five leading mantissa bits, so the interval index and midpoint come from the bit pattern of x), a
+// degree-7 polynomial in (x - midpoint) per interval from a Chebyshev interpolant computed in long double.
+// The three highest coefficients contribute < 1e-9 of G and are stored and evaluated in FP32 (the FP32 pipe
+// is idle in this kernel); the five lower ones in FP64.  One row is 52 bytes (56 with padding; a 56-byte
+// stride keeps rows 16 apart on distinct shared-memory banks).  The relative error, measured on the host
+// against the long-double reference, is <= 3e-16 (rounding level).  The table covers x < 2^14 (B s < 128,
+// i.e. slip beyond 6 for any realistic B); anything outside, NaN included, clears the speculative step's
+// `ok` flag and the step is repeated on the closed-form path.
+// Cost per wheel-stage from q = sx^2 + sy^2 on: 10 FP64 instructions + 2 conversions instead of 49.
+constexpr int kMuBits = 5;                                // leading mantissa bits used for the interval index
+constexpr int kMuPerBinade = 1 << kMuBits;                // 32
+constexpr int kMuBinades = 14;
+constexpr int kMuIntervals = kMuPerBinade * kMuBinades;   // 448 rows = 25 KB
+constexpr int kMuCoef = 8;                                // degree 7
+constexpr int kMuCoefD = 5;                               // degrees 0..4 in FP64, 5..7 in FP32
+constexpr int kMuStride = 7;                              // row stride in doubles: 5 doubles + 3 floats + 4 bytes padding
+constexpr int kMuTableDoubles = kMuIntervals * kMuStride;
+
+struct MuTableView {
+    const double *c;   // [kMuIntervals][kMuStride]: c4 c3 c2 c1 c0 (FP64), then c7 c6 c5 (FP32); shared memory in the kernels
+    double B2;         // B^2
+};
+
+// Double-precision evaluation of one table row exactly as the device does it (host audit + hostsim).
+B200MP_HD double mu_table_eval(const double *row, double t)
+{
+    const float *cf = reinterpret_cast<const float *>(row + kMuCoefD);
+    const float tf = (float)t;
+    const float tail = fmaf(fmaf(cf[0], tf, cf[1]), tf, cf[2]);
+    double g = (double)tail;
+#pragma unroll
+    for (int j = 0; j < kMuCoefD; ++j) g = fma(g, t, row[j]);
+    return g;
+}
+
+// Host: fills table[kMuTableDoubles] for one tyre; returns the measured max relative error of the device
+// evaluation scheme against the long-double reference.
+inline double build_mu_table(double B, double C, double D, double *table)
+{
+    typedef long double L;
+    const L pi = 3.14159265358979323846264338327950288L;
+    auto G = [&](L x) -> L {
+        const L u = x - 1.0L;
+        if (u <= 0.0L) return (L)D * (L)B * (L)C;
+        const L r = sqrtl(u);
+        return (L)D * (L)B * sinl((L)C * atanl(r)) / r;
+    };
+    const int n = kMuCoef;
+    double worst = 0.0;
+    for (int k = 0; k < kMuIntervals; ++k) {
+        const int e = k / kMuPerBinade, m = k % kMuPerBinade;
+        const L lo = ldexpl(1.0L + (L)m / kMuPerBinade, e), hi = ldexpl(1.0L + (L)(m + 1) / kMuPerBinade, e);
+        const L mid = 0.5L * (lo + hi), half = 0.5L * (hi - lo);
+        L f[kMuCoef], c[kMuCoef];
+        for (int i = 0; i < n; ++i) f[i] = G(mid + half * cosl(pi * (2 * i + 1) / (2 * n)));
+        for (int j = 0; j < n; ++j) {
+            L acc = 0;
+            for (int i = 0; i < n; ++i) acc += f[i] * cosl(pi * j * (2 * i + 1) / (2 * n));
+            c[j] = acc * 2 / n;
+        }
+        c[0] /= 2;
+        // Chebyshev series in tau = (x - mid)/half -> monomials in tau -> monomials in (x - mid)
+        L T0[kMuCoef] = {0}, T1[kMuCoef] = {0}, mono[kMuCoef] = {0};
+        T0[0] = 1;
+        T1[1] = 1;
+        for (int j = 0; j < n; ++j) mono[j] = c[0] * T0[j] + c[1] * T1[j];
+        for (int d = 2; d < n; ++d) {
+            L T2[kMuCoef];
+            for (int j = 0; j < n; ++j) T2[j] = (j > 0 ? 2 * T1[j - 1] : 0) - T0[j];
+            for (int j = 0; j < n; ++j) {
+                mono[j] += c[d] * T2[j];
+                T0[j] = T1[j];
+                T1[j] = T2[j];
+            }
+        }
+        L scale = 1;
+        for (int j = 0; j < n; ++j) {
+            mono[j] /= scale;
+            scale *= half;
+        }
+        double *row = table + k * kMuStride;
+        for (int j = 0; j < kMuCoefD; ++j) row[j] = (double)mono[kMuCoefD - 1 - j];          // c4 .. c0
+        float *cf = reinterpret_cast<float *>(row + kMuCoefD);
+        for (int j = 0; j < n - kMuCoefD; ++j) cf[j] = (float)mono[n - 1 - j];               // c7 c6 c5
+        cf[n - kMuCoefD] = 0.0f;
+        for (int i = 0; i <= 32; ++i) {                   // audit: the device scheme vs the long-double function
+            const double x = (double)(lo + (hi - lo) * i / 32.0L * 0.999999L);
+            const double g = mu_table_eval(row, x - (double)mid);
+            const L ref = G((L)x);
+            const double err = (double)fabsl(((L)g - ref) / ref);
+            if (err > worst) worst = err;
+        }
+    }
+    return worst;
+}
+
 // Controls of one zero-order-hold segment, with the steer trigonometry already evaluated.
 template <typename R> struct WheelCtrl {
     R cd[4], sd[4], tq[4];
@@ -93,9 +198,9 @@ B200MP_HD void normal_loads(const DevParams<R> &P, R ax_prev, R ay_prev, R Fz[4]
 
 // Tyre of wheel I: slips -> combined-slip Pacejka friction -> forces in the chassis frame.
 // TY1: all four tyres share one (B, C) pair -- read entry 0 so the kernel carries 2 constants, not 8.
-template <typename R, int I, bool REAR0, bool TY1>
+template <typename R, int I, bool REAR0, bool TY1, bool TAB>
 B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd, R sd, R Fz,
-                            R &fx, R &fy, R &fxt, R &fyt, R &s)
+                            R &fx, R &fy, R &fxt, R &fyt, R &s, const MuTableView &T, bool &ok)
 {
     constexpr int J = TY1 ? 0 : I;
     typedef Math<R> M;
@@ -113,12 +218,28 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
     const R sx = (M::mul_rn(P.rw, w) - vx) * r;
     const R sy = -vy * M::abs(r);        // :290-293
     const R q = sx * sx + sy * sy;       // :296-299
-    const bool slipping = q != (R)0;
-    const R rs = M::rsqrt(q);
-    s = slipping ? q * rs : (R)0;        // sqrt(q); rsqrt(0) = inf must not leak into s
-    const R mu = D * M::sin(P.Cc[J] * M::atan(P.Bc[J] * s));   // :303-306
-    const R g = slipping ? mu * rs : (R)0;                     // :309-348 (zero slip -> zero friction)
-    const R gF = g * Fz;                 // :351-360  mu_x*Fz = sx*(mu/s)*Fz
+    R gF;
+    if (TAB) {
+        // tabulated G(x) = D B sin(C atan(B s)) / (B s), x = 1 + (B s)^2: no sqrt, no reciprocal, no atan, no sin
+        const double x = fma((double)q, T.B2, 1.0);
+        const int hi = M::hi_word(x);
+        const int kraw = (hi - 0x3FF00000) >> (20 - kMuBits);         // exponent + leading mantissa bits
+        ok &= (unsigned)kraw < (unsigned)kMuIntervals;                // NaN / Inf / beyond the table: repeat the step exactly
+        const int k = kraw < 0 ? 0 : (kraw >= kMuIntervals ? kMuIntervals - 1 : kraw);
+        const int keep = (int)(0xFFFFFFFFu << (20 - kMuBits));
+        const double t = x - M::from_words((hi & keep) | (1 << (19 - kMuBits)), 0);   // x - interval midpoint
+        const double g = mu_table_eval(T.c + k * kMuStride, t);
+        s = (R)0;                        // the combined slip itself is not formed on this path (logging uses the other)
+        gF = (R)g * Fz;
+    } else {
+        (void)J;
+        const bool slipping = q != (R)0;
+        const R rs = M::rsqrt(q);
+        s = slipping ? q * rs : (R)0;    // sqrt(q); rsqrt(0) = inf must not leak into s
+        const R mu = D * M::sin(P.Cc[J] * M::atan(P.Bc[J] * s));   // :303-306
+        const R g = slipping ? mu * rs : (R)0;                     // :309-348 (zero slip -> zero friction)
+        gF = g * Fz;                     // :351-360  mu_x*Fz = sx*(mu/s)*Fz
+    }
     fxt = sx * gF;
     fyt = sy * gF;
     if (REAR0 && I >= 2) {
@@ -134,19 +255,21 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
 // which gets the four stage headings of a step from one sincos plus small-angle rotations).
 // k[10] receives the derivative of the full 10-state (k[7] = wz, k[8] = x_dot, k[9] = y_dot).
 // out (AUX only) = the reference's 18 "outputs".
-template <typename R, bool REAR0, bool AUX, bool TY1>
+template <typename R, bool REAR0, bool AUX, bool TY1, bool TAB = false>
 B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R sy, R cy, const WheelCtrl<R> &c,
-                          const R Fz[4], R k[10], R &axc, R &ayc, R *out)
+                          const R Fz[4], R k[10], R &axc, R &ayc, R *out, const MuTableView &T = MuTableView(),
+                          bool *okp = nullptr)
 {
+    bool ok = true;
     const R U = y8[0], V = y8[1], wz = y8[2];
     const R hw = P.halfT * wz;                       // :261-271
     const R vxL = U - hw, vxR = U + hw;
     const R vyF = V + P.a * wz, vyR = V - P.b * wz;
     R fx[4], fy[4], fxt[4], fyt[4], s[4];
-    wheel_forces<R, 0, REAR0, TY1>(P, D[TY1 ? 0 : 0], vxL, vyF, y8[3], c.cd[0], c.sd[0], Fz[0], fx[0], fy[0], fxt[0], fyt[0], s[0]);
-    wheel_forces<R, 1, REAR0, TY1>(P, D[TY1 ? 0 : 1], vxR, vyF, y8[4], c.cd[1], c.sd[1], Fz[1], fx[1], fy[1], fxt[1], fyt[1], s[1]);
-    wheel_forces<R, 2, REAR0, TY1>(P, D[TY1 ? 0 : 2], vxL, vyR, y8[5], c.cd[2], c.sd[2], Fz[2], fx[2], fy[2], fxt[2], fyt[2], s[2]);
-    wheel_forces<R, 3, REAR0, TY1>(P, D[TY1 ? 0 : 3], vxR, vyR, y8[6], c.cd[3], c.sd[3], Fz[3], fx[3], fy[3], fxt[3], fyt[3], s[3]);
+    wheel_forces<R, 0, REAR0, TY1, TAB>(P, D[TY1 ? 0 : 0], vxL, vyF, y8[3], c.cd[0], c.sd[0], Fz[0], fx[0], fy[0], fxt[0], fyt[0], s[0], T, ok);
+    wheel_forces<R, 1, REAR0, TY1, TAB>(P, D[TY1 ? 0 : 1], vxR, vyF, y8[4], c.cd[1], c.sd[1], Fz[1], fx[1], fy[1], fxt[1], fyt[1], s[1], T, ok);
+    wheel_forces<R, 2, REAR0, TY1, TAB>(P, D[TY1 ? 0 : 2], vxL, vyR, y8[5], c.cd[2], c.sd[2], Fz[2], fx[2], fy[2], fxt[2], fyt[2], s[2], T, ok);
+    wheel_forces<R, 3, REAR0, TY1, TAB>(P, D[TY1 ? 0 : 3], vxR, vyR, y8[6], c.cd[3], c.sd[3], Fz[3], fx[3], fy[3], fxt[3], fyt[3], s[3], T, ok);
 
     const R Vwz = V * wz, Uwz = U * wz;
     const R U_dot = P.inv_m * (fx[0] + fx[1] + fx[2] + fx[3]) + Vwz;     // :376-378
@@ -163,6 +286,7 @@ B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R 
     k[9] = U * sy + V * cy;
     axc = U_dot - Vwz;                                                    // :413-414
     ayc = V_dot + Uwz;
+    if (TAB && okp) *okp = *okp && ok;
     if (AUX) {
         for (int i = 0; i < 4; ++i) {                                     // :420-423
             out[i] = fx[i];
@@ -182,10 +306,11 @@ B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R 
 // SPEC = true: the heading trigonometry uses the branch-free "core" forms and the step is one basic
 // block; nothing is committed and false is returned when an argument left their range (the caller then
 // repeats the step with SPEC = false, which branches to the library where needed).
-template <typename R, bool REAR0, bool AUX, bool TY1, bool SPEC>
+template <typename R, bool REAR0, bool AUX, bool TY1, bool SPEC, bool TAB = false>
 B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtrl<R> &c, R h, R y[10], R &ax, R &ay,
-                             R *sdot, R *outs)
+                             R *sdot, R *outs, const MuTableView &T = MuTableView())
 {
+    static_assert(!TAB || (SPEC && !AUX), "the tabulated friction path is speculative and does not log the slip");
     typedef Math<R> M;
     R Fz[4];
     normal_loads(P, ax, ay, Fz);
@@ -200,7 +325,7 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     else
         M::sincos(y[7], &s0, &c0);
 
-    planar_rhs<R, REAR0, AUX, TY1>(P, D, y, s0, c0, c, Fz, k, axc, ayc, o);
+    planar_rhs<R, REAR0, AUX, TY1, TAB>(P, D, y, s0, c0, c, Fz, k, axc, ayc, o, T, &ok);
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] = k[i];
 #pragma unroll
@@ -214,7 +339,7 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     else if (!M::rotate_small(s0, c0, h2 * k[7], &sj, &cj))
         M::sincos(ys[7], &sj, &cj);
 
-    planar_rhs<R, REAR0, AUX, TY1>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o);
+    planar_rhs<R, REAR0, AUX, TY1, TAB>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o, T, &ok);
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] += (R)2 * k[i];
 #pragma unroll
@@ -228,7 +353,7 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     else if (!M::rotate_small(s0, c0, h2 * k[7], &sj, &cj))
         M::sincos(ys[7], &sj, &cj);
 
-    planar_rhs<R, REAR0, AUX, TY1>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o);
+    planar_rhs<R, REAR0, AUX, TY1, TAB>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o, T, &ok);
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] += (R)2 * k[i];
 #pragma unroll
@@ -242,7 +367,7 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     else if (!M::rotate_small(s0, c0, h * k[7], &sj, &cj))
         M::sincos(ys[7], &sj, &cj);
 
-    planar_rhs<R, REAR0, AUX, TY1>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o);
+    planar_rhs<R, REAR0, AUX, TY1, TAB>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o, T, &ok);
     if (SPEC && !ok) return false;
     const R h6 = (R)(1.0 / 6) * h;       // :438  state + 1/6*h*(K1+2K2+2K3+K4)
     const R sixth = (R)(1.0 / 6);
@@ -277,12 +402,12 @@ void rk4_step_checked(const DevParams<R> &P, const R *D, const WheelCtrl<R> &c, 
 
 // SPEC: run the straight-line speculative form first (used by the register-lean fast-path kernels; the
 // generic / logging instantiations are already at the register ceiling and keep the branching form).
-template <typename R, bool REAR0, bool AUX, bool TY1, bool SPEC>
+template <typename R, bool REAR0, bool AUX, bool TY1, bool SPEC, bool TAB = false>
 B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> &c, R h, R y[10], R &ax, R &ay,
-                        R *sdot, R *outs)
+                        R *sdot, R *outs, const MuTableView &T = MuTableView())
 {
     if (SPEC) {
-        if (!rk4_step_impl<R, REAR0, AUX, TY1, true>(P, D, c, h, y, ax, ay, sdot, outs)) {
+        if (!rk4_step_impl<R, REAR0, AUX, TY1, true, TAB>(P, D, c, h, y, ax, ay, sdot, outs, T)) {
             R axay[2] = {ax, ay};
             rk4_step_checked<R, REAR0, AUX, TY1>(P, D, c, h, y, axay, sdot, outs);
             ax = axay[0];

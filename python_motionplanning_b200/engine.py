@@ -465,6 +465,18 @@ class Engine:
         lat["free"] = free
         return best, lat
 
+    def set_friction_mode(self, mode: str) -> str:
+        """``"auto"`` (default: the fast-path FP64 kernels evaluate the combined-slip friction from the host-built
+        polynomial table of the uploaded tyre) or ``"closed_form"`` (always sqrt / atan / sin).  Process-wide; returns
+        the previous mode."""
+        names = {"auto": 0, "closed_form": 1}
+        if mode not in names:
+            raise ValueError(f"friction mode must be one of {sorted(names)}")
+        prev = self.lib.b200mp_set_friction_mode(names[mode])
+        if prev < 0:
+            check(prev, "b200mp_set_friction_mode")
+        return "closed_form" if prev == 1 else "auto"
+
     def set_collision_mode(self, mode: str) -> str:
         """``"auto"`` (FP32 screen + exact FP64 recheck of undecided pairs; default) or ``"fp64"`` (all-FP64
         kernel).  Both give bit-identical flags; process-wide.  Returns the previous mode."""

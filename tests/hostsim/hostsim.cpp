@@ -9,6 +9,9 @@
 
 using namespace b200mp;
 
+static int g_use_table = 0;          // hostsim_set_table(1): FP64 no-log runs take the tabulated friction path
+static double g_table_err = 0.0;
+
 template <typename R, bool REAR0, bool AUX>
 static void run(int B, int n_steps, double dt, int hold, const double *state0, const double *delta, const double *torque,
                 int tch, const double *mu, const HostParams *params, const int *param_set, int store_stride,
@@ -23,6 +26,15 @@ static void run(int B, int n_steps, double dt, int hold, const double *state0, c
         ax = (R)state0[(size_t)10 * B + r];
         ay = (R)state0[(size_t)11 * B + r];
         WheelCtrl<R> c;
+        static double table[kMuTableDoubles];
+        MuTableView T;
+        T.c = table;
+        const bool tab = g_use_table && !AUX && sizeof(R) == 8 && !mu;
+        if (tab) {
+            const HostParams &hp = params[param_set ? param_set[r] : 0];
+            g_table_err = build_mu_table(hp.B[0], hp.C[0], hp.D[0], table);
+            T.B2 = hp.B[0] * hp.B[0];
+        }
         for (int n = 0; n < n_steps; ++n) {
             const size_t seg = n / hold;
             if (n % hold == 0) {
@@ -32,7 +44,10 @@ static void run(int B, int n_steps, double dt, int hold, const double *state0, c
                 for (int i = 0; i < 4; ++i) c.tq[i] = (R)torque[(seg * tch + (tch == 1 ? 0 : i)) * B + r];
             }
             R sdot[10], outs[18];
-            rk4_step<R, REAR0, AUX, false, !AUX>(P, D, c, (R)dt, y, ax, ay, sdot, outs);   // !AUX: speculative form + checked fallback
+            if (tab)
+                rk4_step<R, REAR0, false, false, true, (sizeof(R) == 8)>(P, D, c, (R)dt, y, ax, ay, sdot, outs, T);
+            else
+                rk4_step<R, REAR0, AUX, false, !AUX>(P, D, c, (R)dt, y, ax, ay, sdot, outs);   // !AUX: speculative form + checked fallback
             if (store_stride > 0 && (n + 1) % store_stride == 0) {
                 const size_t o = (size_t)((n + 1) / store_stride - 1);
                 if (traj) for (int k = 0; k < 10; ++k) traj[(o * 10 + k) * B + r] = (double)y[k];
@@ -46,6 +61,12 @@ static void run(int B, int n_steps, double dt, int hold, const double *state0, c
         state_end[(size_t)10 * B + r] = (double)ax;
         state_end[(size_t)11 * B + r] = (double)ay;
     }
+}
+
+extern "C" double hostsim_set_table(int on)
+{
+    g_use_table = on;
+    return g_table_err;
 }
 
 extern "C" void hostsim_rollout(int use_f32, int B, int n_steps, double dt, int hold, const double *state0,

@@ -15,6 +15,14 @@ pytestmark = pytest.mark.gpu
 DT = 1e-4
 
 
+@pytest.fixture(autouse=True, params=["auto", "closed_form"])
+def friction_mode(request, engine):
+    """Every test runs with the tabulated friction path of the fast kernels and with the closed form."""
+    prev = engine.set_friction_mode(request.param)
+    yield request.param
+    engine.set_friction_mode(prev)
+
+
 def _params(D=1.0):
     p = VehicleParameters()
     p.DFL = p.DFR = p.DRL = p.DRR = D

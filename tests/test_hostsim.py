@@ -72,3 +72,32 @@ def test_speculative_step_falls_back_out_of_range(hostsim):
     traj, _, end = _run(hostsim, 0, s0, d, t, par, N, 10, 20)
     assert rel_err(traj, ref["traj"]).max() < 1e-10      # sin/cos of 3e5: conditioning, not method
     assert rel_err(end, ref["state_end"]).max() < 1e-10
+
+
+def test_tabulated_friction_path_matches_oracle(hostsim):
+    """The fast-path kernels replace sqrt / reciprocal / atan / sin of the combined-slip friction by a host-built table of
+    polynomials in 1 + (B s)^2 (vehicle_rhs.cuh: build_mu_table).  Compiled for the host, the same code must reproduce
+    the oracle at rounding level, hand slips beyond the table to the closed form, and keep the zero-slip state exact."""
+    hostsim.hostsim_set_table.restype = C.c_double
+    B, N = 256, 300
+    s0, d, t = wl.config2_rollouts(B=B, n_steps=N)
+    s0 = s0.copy()
+    s0[3:7, :8] *= 3.5                      # wheels spinning at 3.5x: slip 2.5 is beyond the table (B s ~ 52)
+    s0[3:7, 8:16] = 0.0                     # locked wheels: slip -1
+    par = c_oracle.make_params(pn.VehicleParams())
+    par[0].D[:] = (1.0,) * 4
+    ref = c_oracle.rollout(s0, d, t, par, 1e-4, N, hold=10, store_stride=50)
+    hostsim.hostsim_set_table(1)
+    try:
+        traj, _, end = _run(hostsim, 0, s0, d, t, par, N, 10, 50)
+        err = hostsim.hostsim_set_table(1)
+        assert 0.0 < err < 1e-15, err       # the builder's own audit against long double
+        assert rel_err(traj, ref["traj"]).max() < 1e-12
+        assert rel_err(end, ref["state_end"]).max() < 1e-11
+        # zero-slip equilibrium stays exactly stationary (reference: state_dot = [0, .., 0, 25, 0])
+        z = np.zeros((12, 1))
+        z[0], z[3:7] = 25.0, 25.0 / 0.308309813617345
+        zt, _, zend = _run(hostsim, 0, z, np.zeros((1, 1, 1)), np.zeros((1, 1, 1)), par, 10, 10, 10)
+        assert zend[0, 0] == 25.0 and np.all(zend[1:3, 0] == 0.0) and np.all(zend[3:7, 0] == z[3, 0]) and zend[9, 0] == 0.0
+    finally:
+        hostsim.hostsim_set_table(0)

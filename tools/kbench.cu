@@ -13,6 +13,7 @@ int main(int argc, char **argv)
 {
     const int B = argc > 1 ? atoi(argv[1]) : 65536, N = argc > 2 ? atoi(argv[2]) : 500, hold = 10;
     const int stride = argc > 3 ? atoi(argv[3]) : 1;
+    if (argc > 5) b200mp_set_friction_mode(atoi(argv[5]));   // 1 = closed form
     B200mpVehicleParams p{};
     p.m = 987.89 + 869.93; p.b = 2.906 / 1.85; p.a = 2.906 - p.b; p.Izz = 0.5 * p.m * p.a * p.b; p.Jw = 1; p.hg = 0.55419;
     p.T = 1.536; p.wL = p.wR = p.T / 2; p.rw = 0.329 - (987.89 / 2 + 50) / 26290;
@@ -21,13 +22,21 @@ int main(int argc, char **argv)
     const int nseg = (N + hold - 1) / hold;
     std::vector<double> s0((size_t)12 * B), dl((size_t)nseg * B), tq((size_t)nseg * B);
     unsigned long long seed = 12345;
+    const int coherent = argc > 6 ? atoi(argv[6]) : 0;   // 1: every rollout starts near one operating point (small slip)
     for (int r = 0; r < B; ++r) {
+        if (coherent) {
+            const double U = 25 + 0.5 * lcg(seed);
+            s0[0 * (size_t)B + r] = U; s0[1 * (size_t)B + r] = 0.05 * (lcg(seed) - 0.5); s0[2 * (size_t)B + r] = 0.02 * (lcg(seed) - 0.5);
+            for (int i = 0; i < 4; ++i) s0[(3 + i) * (size_t)B + r] = U / p.rw * (1 + 0.004 * (lcg(seed) - 0.5));
+            s0[7 * (size_t)B + r] = -3.14 + 6.28 * lcg(seed); s0[8 * (size_t)B + r] = -100 + 200 * lcg(seed); s0[9 * (size_t)B + r] = -100 + 200 * lcg(seed);
+            continue;
+        }
         const double U = 5 + 35 * lcg(seed);
         s0[0 * (size_t)B + r] = U; s0[1 * (size_t)B + r] = -1 + 2 * lcg(seed); s0[2 * (size_t)B + r] = -0.5 + lcg(seed);
         for (int i = 0; i < 4; ++i) s0[(3 + i) * (size_t)B + r] = U / p.rw * (1 + 0.1 * (lcg(seed) - 0.5));
         s0[7 * (size_t)B + r] = -3.14 + 6.28 * lcg(seed); s0[8 * (size_t)B + r] = -100 + 200 * lcg(seed); s0[9 * (size_t)B + r] = -100 + 200 * lcg(seed);
     }
-    for (size_t i = 0; i < dl.size(); ++i) { dl[i] = -0.1 + 0.2 * lcg(seed); tq[i] = -300 + 600 * lcg(seed); }
+    for (size_t i = 0; i < dl.size(); ++i) { dl[i] = (coherent ? 0.1 : 1.0) * (-0.1 + 0.2 * lcg(seed)); tq[i] = -300 + 600 * lcg(seed); }
     double *d_s0, *d_dl, *d_tq, *d_traj = nullptr, *d_end;
     cudaMalloc(&d_s0, s0.size() * 8); cudaMalloc(&d_dl, dl.size() * 8); cudaMalloc(&d_tq, tq.size() * 8); cudaMalloc(&d_end, (size_t)12 * B * 8);
     if (stride) cudaMalloc(&d_traj, (size_t)(N / stride) * 10 * B * 8);
