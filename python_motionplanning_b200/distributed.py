@@ -136,3 +136,77 @@ def collision_select_sharded(engine, px, py, pyaw, obstacles, offsets, radii, go
     best = engine.select_best_path_index_batch(engine.dev(px[:, -1].copy()), engine.dev(py[:, -1].copy()), free,
                                                goal_xy, weight)
     return free, best
+
+
+def gather_shards(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gather contiguous shards along the LAST dimension into ``[..., n_total]`` (any dtype): rank r holds columns
+    ``shard_range(n_total, r, G)``.  Used for path end points / per-vehicle results; payloads are a few KB."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    sizes = [shard_range(n_total, r, ws) for r in range(ws)]
+    width = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros(local.shape[:-1] + (width,), dtype=local.dtype, device=local.device)
+    pad[..., : local.shape[-1]] = local
+    buf = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(buf, pad.contiguous(), group=group)
+    return torch.cat([buf[r][..., : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=-1)
+
+
+def plan_lattice_sharded(engine, goals_local, ego, obstacles, offsets, radii, goal_xy, weight, n_samples: int = 50, group=None):
+    """``Engine.plan_lattice`` with the goal states sharded over the ranks: every rank optimises, samples and checks its
+    block of goal states (``goals_local`` is the FULL ``[3, P]`` array on every rank), then the flags and path end
+    points are all-gathered (P bytes + 16 P bytes) and the path selection runs replicated, so every rank returns the
+    same ``(best index or None, free[P], end_xy[2, P])``."""
+    rank, ws = world()
+    g = engine.dev(goals_local)
+    P = g.shape[1]
+    lo, hi = shard_range(P, rank, ws)
+    gl = g[:, lo:hi].contiguous()
+    opt = engine.optimize_spirals(gl[0], gl[1], gl[2], n_samples)
+    lat = engine.sample_lattice(opt["p"][0], opt["p"][1], opt["p"][2], ego=ego, n_samples=n_samples)
+    free_l = engine.collision_check_batch(lat["px"], lat["py"], None, obstacles, offsets, radii,
+                                          trig=(lat["pcos"], lat["psin"])) & opt["valid"]
+    free = gather_flags(free_l, P, group=group)
+    end_xy = gather_shards(lat["end_xy"], P, group=group)
+    best = engine.select_best_path_index_batch(end_xy[0].contiguous(), end_xy[1].contiguous(), free, goal_xy, weight)
+    return best, free, end_xy
+
+
+def track_sharded(engine, state0, waypoints, dt, n_steps, target_vel=25.0, wp_count=None, vehicles_per_set=None, gather=False,
+                  group=None, **kw):
+    """``Engine.track_closed_loop`` with whole waypoint sets sharded over the ranks (a set and its vehicles stay on one
+    GPU; vehicles are independent, so there is no data-path collective).  ``state0 [12, V]`` and ``waypoints
+    [n_sets, W, 2]`` are the FULL arrays on every rank.  Returns ``(TrackResult of the local block, (lo, hi) vehicle
+    range)``; with ``gather=True`` the end states are all-gathered to ``[12, V]`` on every rank."""
+    import numpy as np
+    rank, ws = world()
+    wp = np.asarray(waypoints) if not isinstance(waypoints, torch.Tensor) else waypoints
+    n_sets = wp.shape[0]
+    V = state0.shape[1]
+    vps = int(vehicles_per_set or -(-V // n_sets))
+    s_lo, s_hi = shard_range(n_sets, rank, ws)
+    lo, hi = min(V, s_lo * vps), min(V, s_hi * vps)
+    cnt = None if wp_count is None else wp_count[s_lo:s_hi]
+    st = state0[:, lo:hi]
+    if "ctrl0" in kw and kw["ctrl0"] is not None:
+        kw = dict(kw, ctrl0=kw["ctrl0"][:, lo:hi])
+    if hi - lo == 0 or s_hi - s_lo == 0:
+        res = None
+    else:
+        res = engine.track_closed_loop(st, wp[s_lo:s_hi], dt, n_steps, target_vel, wp_count=cnt, vehicles_per_set=vps, **kw)
+    if not gather:
+        return res, (lo, hi)
+    # uneven shards: pad to the widest block, gather, trim (vehicle blocks are contiguous in set order)
+    blocks = [(min(V, shard_range(n_sets, r, ws)[0] * vps), min(V, shard_range(n_sets, r, ws)[1] * vps)) for r in range(ws)]
+    width = max(b - a for a, b in blocks)
+    pad = torch.zeros(12, width, dtype=torch.float64, device=engine.tdev)
+    if res is not None:
+        pad[:, : hi - lo] = res.state_end
+    if ws > 1:
+        buf = [torch.empty_like(pad) for _ in range(ws)]
+        dist.all_gather(buf, pad, group=group)
+    else:
+        buf = [pad]
+    full = torch.cat([buf[r][:, : b - a] for r, (a, b) in enumerate(blocks)], dim=1)
+    return res, (lo, hi), full

@@ -97,3 +97,35 @@ def test_single_process_paths():
     f = torch.tensor([1, 0, 1], dtype=torch.uint8)
     assert D.gather_flags(f, 3) is f
     assert D.world() == (0, 1)
+
+
+def _gs_worker(rank, ws, port, full, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        n = full.shape[-1]
+        lo, hi = D.shard_range(n, rank, ws)
+        got = D.gather_shards(torch.from_numpy(full[..., lo:hi].copy()), n)
+        q.put((rank, got.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ws,n", [(2, 7), (2, 1), (3, 10)])
+def test_gather_shards_float_rows(ws, n):
+    """Path end points [2, P] split by columns across ranks come back in order on every rank (uneven shards too)."""
+    rng = np.random.default_rng(4)
+    full = rng.normal(size=(2, n))
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gs_worker, args=(r, ws, port, full, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, got in out:
+        assert np.array_equal(got, full)

@@ -68,6 +68,31 @@ def test_collision_sharded_equals_unsharded(engine):
     assert np.array_equal(free.cpu().numpy().astype(bool), ref)
 
 
+def test_sharded_lattice_and_tracking_single_process(engine):
+    """World size 1 paths of plan_lattice_sharded / track_sharded equal the plain engine calls; emulated shards of the
+    fleet (whole waypoint sets per rank) reproduce the unsharded end states bit for bit."""
+    p = VehicleParameters()
+    p.DFL = p.DFR = p.DRL = p.DRR = 1.0
+    engine.set_params(p)
+    rng = np.random.default_rng(9)
+    goals = np.stack([rng.uniform(22, 38, 200), rng.uniform(-6, 6, 200), rng.uniform(-0.3, 0.3, 200)])
+    w = wl.config3_lattice(P=8, M=2000)
+    obs = w["obstacles"] * 0.6 - 10.0
+    b1, out1 = engine.plan_lattice(goals, (12.0, -7.0, 0.4), obs, OFF, RAD, (45.0, 10.0), w["weight"])
+    b2, free2, end2 = D.plan_lattice_sharded(engine, goals, (12.0, -7.0, 0.4), obs, OFF, RAD, (45.0, 10.0), w["weight"])
+    assert b1 == b2 and torch.equal(free2, out1["free"]) and torch.equal(end2, out1["end_xy"])
+    st0, wps = wl.tracking_fleet(V=1000, n_sets=5)
+    one = engine.track_closed_loop(st0, wps, wl.DT, 40, vehicles_per_set=200)
+    res, (lo, hi), full = D.track_sharded(engine, st0, wps, wl.DT, 40, gather=True)
+    assert (lo, hi) == (0, 1000) and torch.equal(full, one.state_end)
+    for ws in (2, 3):
+        parts = []
+        for r in range(ws):
+            s_lo, s_hi = D.shard_range(5, r, ws)
+            parts.append(engine.track_closed_loop(st0[:, s_lo * 200:s_hi * 200], wps[s_lo:s_hi], wl.DT, 40, vehicles_per_set=200).state_end)
+        assert torch.equal(torch.cat(parts, dim=1), one.state_end)
+
+
 def test_nccl_two_ranks_when_available():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")

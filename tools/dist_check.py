@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Run under torchrun on >= 2 GPUs: the NCCL path of distributed.mpc_plan / collision_select_sharded,
+"""Run under torchrun on >= 2 GPUs: the NCCL path of distributed.mpc_plan / collision_select_sharded /
+plan_lattice_sharded / track_sharded,
 checked against the unsharded single-GPU result on every rank.  Prints DIST_CHECK_OK from rank 0."""
 import os
 import sys
@@ -40,6 +41,22 @@ def main():
     assert torch.equal(free, full)
     best1 = eng.select_best_path_index_batch(w["px"][:, -1].copy(), w["py"][:, -1].copy(), full, w["goal"][:2], w["weight"])
     assert best == best1
+    # sharded lattice planning (optimise -> sample -> check -> select) equals the single-GPU pipeline
+    rng = np.random.default_rng(9)
+    Pg = 1001
+    gt = rng.uniform(-0.3, 0.3, Pg)
+    goals = np.stack([rng.uniform(22, 38, Pg), rng.uniform(-6, 6, Pg), gt])
+    ego = (12.0, -7.0, 0.4)
+    obs = w["obstacles"] * 0.6 - 10.0
+    b_sh, free_sh, end_sh = D.plan_lattice_sharded(eng, goals, ego, obs, w["offsets"], w["radii"], (45.0, 10.0), w["weight"])
+    b_1, out1 = eng.plan_lattice(goals, ego, obs, w["offsets"], w["radii"], (45.0, 10.0), w["weight"])
+    assert b_sh == b_1 and torch.equal(free_sh, out1["free"]) and torch.equal(end_sh, out1["end_xy"])
+    # closed-loop fleet sharded by waypoint set equals the single-GPU run, bit for bit
+    st0, wps = wl.tracking_fleet(V=4096, n_sets=5)
+    res, (vlo, vhi), full_end = D.track_sharded(eng, st0, wps, wl.DT, 60, gather=True)
+    one = eng.track_closed_loop(st0, wps, wl.DT, 60, vehicles_per_set=-(-4096 // 5))
+    assert torch.equal(full_end, one.state_end)
+    assert res is None or torch.equal(res.state_end, one.state_end[:, vlo:vhi])
     dist.barrier()
     if rank == 0:
         print(f"DIST_CHECK_OK world={dist.get_world_size()} mpc index={plan['index']} cost={plan['cost']:.6e} best path={best}")
