@@ -18,6 +18,7 @@ bounded sample of the same workload.  The reference itself is pure Python and ca
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -387,7 +388,7 @@ def secondary_metrics(eng, wl, np, torch):
     far = eng.dev(w["obstacles"] + np.array([400.0, 0.0]))
     peak32 = eng.fma_peak(32, reps=3)
     for name, ob in (("collision_kernel", obs), ("collision_kernel_no_early_exit", far)):
-        for mode in ("auto", "fp64"):
+        for mode in ("auto", "screen", "fp64"):
             eng.set_collision_mode(mode)
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(13)]
             for e0, e1 in evs:
@@ -396,13 +397,22 @@ def secondary_metrics(eng, wl, np, torch):
                 e1.record()
             torch.cuda.synchronize()
             ms = statistics.median(e0.elapsed_time(e1) for e0, e1 in evs[3:])
-            key = name + ("" if mode == "auto" else "_fp64_only")
+            key = name + {"auto": "", "screen": "_screen_only", "fp64": "_fp64_only"}[mode]
             out[key] = {"ms": ms, "value": tests / (ms * 1e-3), "unit": "circle-point tests/s (nominal)",
                         "free_fraction": float(fr.float().mean().item()),
-                        "arithmetic": "FP32 screen (packed f32x2) + exact FP64 recheck of undecided pairs" if mode == "auto"
-                        else "all FP64"}
+                        "arithmetic": {"auto": "bounding-box broad phase over 32-point obstacle chunks + FP32 screen (packed f32x2) + "
+                                               "exact FP64 recheck of undecided pairs",
+                                       "screen": "FP32 screen (packed f32x2) + exact FP64 recheck of undecided pairs, every pair",
+                                       "fp64": "all FP64, every pair"}[mode]}
+            if mode == "auto":
+                st2 = (C.c_ulonglong * 2)()
+                eng.lib.b200mp_collision_stats(eng.device, eng._stream(), M, st2)
+                n_warps = -(-P * n // 32)
+                out[key]["broad_phase"] = {"warp_chunks_screened": int(st2[0]), "warp_chunks_total": n_warps * (-(-M // 32)),
+                                           "thread_chunks_rechecked_fp64": int(st2[1]),
+                                           "tests_executed": int(st2[0]) * 32 * 32 * 3}
         eng.set_collision_mode("auto")
-    k = out["collision_kernel_no_early_exit"]
+    k = out["collision_kernel_no_early_exit_screen_only"]
     # 4 FP32 lane-operations per test (2 subtractions, 1 multiply, 1 FMA = 5 flop) against the measured FP32 FMA peak
     k["roofline"] = {"bound": "fp32", "achieved": k["value"] * 5 * 1e-12, "peak": peak32, "unit": "TFLOP/s",
                      "frac": k["value"] * 5 * 1e-12 / peak32, "frac_of_fp32_lane_issue": k["value"] * 4 / (peak32 * 1e12 / 2),

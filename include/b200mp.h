@@ -162,9 +162,16 @@ int b200mp_set_friction_mode(int mode);
  * sequence above -- the flags are bit-identical to FP64_ONLY for every input, the FP64 pipe is simply not
  * spent on pairs single precision already decides.  FP64_ONLY forces the all-FP64 kernel (A/B checks).
  * Process-wide; returns the previous mode, or B200MP_E_ARG. */
-#define B200MP_COLLISION_AUTO 0
-#define B200MP_COLLISION_FP64_ONLY 1
+#define B200MP_COLLISION_AUTO 0        /* bounding-box broad phase over 32-point obstacle chunks + FP32 screen + exact recheck */
+#define B200MP_COLLISION_FP64_ONLY 1   /* every pair in FP64 */
+#define B200MP_COLLISION_SCREEN_ONLY 2 /* FP32 screen + exact recheck on every pair (no broad phase) */
 int b200mp_set_collision_mode(int mode);
+
+/* Broad-phase statistics of the LAST b200mp_collision_check_f64 call on `device` in AUTO mode with M obstacle points
+ * (synchronises `stream`): out2[0] = (warp, 32-point chunk) pairs that survived the bounding-box test and were
+ * screened point by point (x 32 path points x n_circ x 32 = circle/point tests executed), out2[1] = (thread, chunk)
+ * pairs repeated in FP64.  For honest "executed vs nominal" accounting in benchmarks. */
+int b200mp_collision_stats(int device, void *stream, int M, unsigned long long *out2);
 
 /* select_best_path_index on the path end points (collision_checker.py:134-203):
  *   score_i = norm([ex_i-gx, ey_i-gy]) + sum over colliding j (ascending) of weight*norm([ex_i-ex_j, ey_i-ey_j])

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "b200mp_collision_check_f64": (_i, [_i, _vp, _i, _i, _i, _dp, _dp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "b200mp_set_friction_mode": (_i, [_i]),
     "b200mp_set_collision_mode": (_i, [_i]),
+    "b200mp_collision_stats": (_i, [_i, _vp, _i, C.POINTER(C.c_ulonglong)]),
     "b200mp_select_best_f64": (_i, [_i, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp]),
     "b200mp_track_closed_loop_f64": (_i, [_i, _vp, C.POINTER(TrackArgsC)]),
     "b200mp_sample_lattice_f64": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -260,10 +260,20 @@ int b200mp_set_friction_mode(int mode)
     return g_friction_mode.exchange(mode);
 }
 
+int b200mp_collision_stats(int device, void *stream, int M, unsigned long long *out2)
+{
+    B200MP_ENTER(device);
+    if (!out2) {
+        set_error("collision_stats: out2 is NULL");
+        return B200MP_E_ARG;
+    }
+    return collision_stats(device, (cudaStream_t)stream, M, out2);
+}
+
 int b200mp_set_collision_mode(int mode)
 {
     g_err[0] = 0;
-    if (mode != B200MP_COLLISION_AUTO && mode != B200MP_COLLISION_FP64_ONLY) {
+    if (mode != B200MP_COLLISION_AUTO && mode != B200MP_COLLISION_FP64_ONLY && mode != B200MP_COLLISION_SCREEN_ONLY) {
         set_error("set_collision_mode: unknown mode %d", mode);
         return B200MP_E_ARG;
     }

@@ -74,6 +74,7 @@ int launch_collision_f64(int device, cudaStream_t st, int P, int n_pts, int n_ci
                          const double *rad, const double *px, const double *py, const double *pcos,
                          const double *psin, const double *pyaw, int yaw_stride, int M, const double *obs,
                          unsigned char *free_out, double *min_clear);
+int collision_stats(int device, cudaStream_t st, int M, unsigned long long out[2]);
 int launch_select_best_f64(int device, cudaStream_t st, int P, const double *ex, const double *ey,
                            const unsigned char *free_in, double gx, double gy, double weight, int norm_mode,
                            double *scores_out, int *best_out);

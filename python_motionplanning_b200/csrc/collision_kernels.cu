@@ -307,6 +307,196 @@ collision_filter_kernel(int n_items, int n_pts, const __grid_constant__ CircleSp
     if (hit) free_out[p] = 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K2 broad phase: the obstacle set of a planner is a handful of outlines (the reference samples boxes every
+// 0.2 m, env.py:93-127), i.e. consecutive obstacle points are spatially coherent.  A prepare kernel shifts the
+// points to the common origin in FP32 once per launch (instead of once per CTA and tile) and records the bounding
+// box of every 32 consecutive points.  In the main kernel one CTA walks ALL obstacle chunks: each lane of a warp
+// compares one chunk box with the warp's box (the union over its 32 path points of the circle centres grown by the
+// "cannot be a collision beyond this" radius sqrt(HI) of the FP32 screen), a ballot collects the overlapping chunks,
+// and only those are screened point by point (packed FP32, as above).  A culled pair has |o - c|_inf > sqrt(HI) in
+// the FP32 coordinates, which is exactly a pair the screen declares free, so the flags stay bit-identical to the
+// all-FP64 kernel; threads whose screen is not sharp (hi = NaN) make their warp's box infinite (nothing is culled)
+// and an undecided thread repeats, in exact FP64, the chunks that overlap ITS box.  On BASELINE config 3 about 2 %
+// of the chunks survive.
+struct ObsPrep {
+    float amax;                    // max |o - origin| over all obstacle points (FP32 coordinates)
+    int pad;
+    unsigned long long screened;   // (warp, chunk) pairs that survived the broad phase
+    unsigned long long rechecked;  // (thread, chunk) pairs repeated in FP64
+};
+
+__global__ void __launch_bounds__(128)
+obstacle_prepare_kernel(int M, const double2 *__restrict__ obs, float2 *__restrict__ pts, float4 *__restrict__ boxes,
+                        ObsPrep *__restrict__ prep)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;        // one warp = one chunk of 32 points
+    if ((i >> 5) >= (M + 31) / 32) return;                      // whole warps past the last chunk
+    const double2 org = obs[0];
+    float2 v = make_float2(INFINITY, INFINITY);                // padding: never below a threshold
+    float ax = 0.0f;
+    float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    if (i < M) {
+        const double2 o = obs[i];
+        v.x = (float)(o.x - org.x);
+        v.y = (float)(o.y - org.y);
+        ax = fmaxf(fabsf(v.x), fabsf(v.y));
+        // a point with a NaN coordinate never hits in either precision: it stays out of the box (fminf/fmaxf drop NaN);
+        // an Inf coordinate makes the box infinite, so its chunk is always examined
+        xmin = xmax = v.x;
+        ymin = ymax = v.y;
+        if (v.x != v.x || v.y != v.y) {
+            xmin = ymin = INFINITY;
+            xmax = ymax = -INFINITY;
+        }
+    }
+    pts[i] = v;                                                 // pts has room for the padded count
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, w));
+        xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, w));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, w));
+        ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, w));
+        ax = fmaxf(ax, __shfl_xor_sync(0xffffffffu, ax, w));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        boxes[i >> 5] = make_float4(xmin, ymin, xmax, ymax);
+        atomicMax((int *)&prep->amax, __float_as_int(ax));      // non-negative floats order as ints
+    }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kColBlock)
+collision_cull_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, const double *__restrict__ px,
+                      const double *__restrict__ py, const double *__restrict__ pcos, const double *__restrict__ psin,
+                      const double *__restrict__ pyaw, int yaw_stride, int M, const double2 *__restrict__ obs,
+                      const float2 *__restrict__ pts, const float4 *__restrict__ boxes, ObsPrep *prep,
+                      unsigned char *free_out)
+{
+    const int t = blockIdx.x * kColBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool active = t < n_items;
+    const int p = active ? t / n_pts : 0;
+    if (active && ((volatile unsigned char *)free_out)[p] == 0) active = false;   // path already known to collide
+    if (!__any_sync(0xffffffffu, active)) return;
+    const int n_chunks = (M + 31) >> 5;
+    // grid.y splits the chunk list (32 chunks = one ballot group per step) so that few paths x many obstacles still
+    // fill the GPU; a path's verdict is the AND over the slices (free_out is only ever cleared)
+    const int groups = (n_chunks + 31) >> 5;
+    const int g_per = (groups + gridDim.y - 1) / gridDim.y;
+    const int c_begin = blockIdx.y * g_per * 32, c_end = min(n_chunks, c_begin + g_per * 32);
+    if (c_begin >= c_end) return;
+    const double2 org = obs[0];
+
+    double cx[NC], cy[NC];
+    float fx[NC], fy[NC], lo[NC], hi[NC];
+    float bx0 = INFINITY, by0 = INFINITY, bx1 = -INFINITY, by1 = -INFINITY;   // this thread's reach box
+    if (active) {
+        const double x = px[t], y = py[t];
+        double c, s;
+        if (pcos) {
+            c = pcos[t];
+            s = psin[t];
+        } else {
+            sincos(pyaw[(size_t)p * yaw_stride + (t - p * n_pts)], &s, &c);
+        }
+        double ac = 0.0;
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            cx[k] = __dadd_rn(x, __dmul_rn(cs.off[k], c));
+            cy[k] = __dadd_rn(y, __dmul_rn(cs.off[k], s));
+            const double rx = cx[k] - org.x, ry = cy[k] - org.y;
+            fx[k] = (float)rx;
+            fy[k] = (float)ry;
+            bad |= !(fabs(rx) <= 1.0e30) | !(fabs(ry) <= 1.0e30);
+            ac = fmax(ac, fmax(fabs(rx), fabs(ry)));
+        }
+        const double u = 5.9604644775390625e-08;   // 2^-24
+        const double e0 = 2.0 * u * ((double)*(volatile float *)&prep->amax + ac) * 1.000001 + 1.0e-18;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const double r = cs.rad[k];
+            const bool sharp = !bad && e0 < 0.25 * r && r < 1.0e15;
+            const double a = (r * (1.0 - 9.094947017729282e-13) - e0) / (1.0 + 4.0 * u);
+            const double b = (r * (1.0 + 9.094947017729282e-13) + e0) / (1.0 - 4.0 * u);
+            lo[k] = sharp ? __double2float_rd(a * a * (1.0 - 1.0e-15)) : 0.0f;
+            hi[k] = sharp ? __double2float_ru(b * b * (1.0 + 1.0e-15)) : __int_as_float(0x7fc00000);
+            if (!(r > 0.0)) hi[k] = 0.0f;
+            // reach of circle k: beyond it q32 >= hi certainly (slack for the FP32 roundings of the box test itself)
+            const float reach = (hi[k] == hi[k]) ? __fmul_ru(__fsqrt_ru(hi[k]), 1.00001f) : INFINITY;
+            if (hi[k] != 0.0f) {
+                bx0 = fminf(bx0, __fsub_rd(fx[k], reach));
+                bx1 = fmaxf(bx1, __fadd_ru(fx[k], reach));
+                by0 = fminf(by0, __fsub_rd(fy[k], reach));
+                by1 = fmaxf(by1, __fadd_ru(fy[k], reach));
+                if (reach == INFINITY) {   // not sharp: every chunk must be examined (and rechecked exactly)
+                    bx0 = by0 = -INFINITY;
+                    bx1 = by1 = INFINITY;
+                }
+            }
+        }
+    }
+    // the warp's box
+    float wx0 = bx0, wy0 = by0, wx1 = bx1, wy1 = by1;
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) {
+        wx0 = fminf(wx0, __shfl_xor_sync(0xffffffffu, wx0, w));
+        wy0 = fminf(wy0, __shfl_xor_sync(0xffffffffu, wy0, w));
+        wx1 = fmaxf(wx1, __shfl_xor_sync(0xffffffffu, wx1, w));
+        wy1 = fmaxf(wy1, __shfl_xor_sync(0xffffffffu, wy1, w));
+    }
+    float mn[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) mn[k] = INFINITY;
+    const float4 *pts4 = reinterpret_cast<const float4 *>(pts);
+    for (int g = c_begin; g < c_end; g += 32) {
+        const int c = g + lane;
+        bool over = false;
+        if (c < c_end) {
+            const float4 b = boxes[c];
+            over = !(b.x > wx1 || b.z < wx0 || b.y > wy1 || b.w < wy0);   // an empty (all-NaN) box overlaps nothing
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, over);
+        if (mask && active && ((volatile unsigned char *)free_out)[p] == 0) active = false;
+        if (!__any_sync(0xffffffffu, active)) return;
+        if (mask && lane == 0) atomicAdd(&prep->screened, (unsigned long long)__popc(mask));
+        while (mask) {
+            const int ch = g + __ffs(mask) - 1;
+            mask &= mask - 1;
+            if (!active) continue;
+#pragma unroll 4
+            for (int o = 0; o < 16; ++o) {
+                const float4 ob = pts4[ch * 16 + o];                        // two points: (xa, ya, xb, yb)
+                const unsigned long long X = pack2(ob.x, ob.z), Y = pack2(ob.y, ob.w);
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    const unsigned long long dx = add2(X, pack2(-fx[k], -fx[k])), dy = add2(Y, pack2(-fy[k], -fy[k]));
+                    const unsigned long long q = fma2(dy, dy, mul2(dx, dx));
+                    mn[k] = fminf(mn[k], fminf(lo2(q), hi2(q)));
+                }
+            }
+        }
+    }
+    if (!active) return;
+    bool hit = false, undecided = false;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        hit |= mn[k] < lo[k];
+        undecided |= !(mn[k] >= hi[k]);
+    }
+    if (!hit && undecided) {
+        // exact FP64 sequence over the chunks that overlap this thread's own box (the others are certainly free)
+        for (int c = c_begin; c < c_end && !hit; ++c) {
+            const float4 b = boxes[c];
+            if (b.x > bx1 || b.z < bx0 || b.y > by1 || b.w < by0) continue;
+            hit = exact_tile_hit<NC>(cs, cx, cy, obs, c * 32, min(M, c * 32 + 32));
+            atomicAdd(&prep->rechecked, 1ULL);
+        }
+    }
+    if (hit) free_out[p] = 0;
+}
+
 __global__ void clearance_reduce_kernel(int P, int n_pts, const double *__restrict__ clear_pts, double *__restrict__ out)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -334,12 +524,47 @@ static int launch_collision_nc(int device, cudaStream_t st, int P, int n_pts, co
     } else if (collision_mode() == B200MP_COLLISION_FP64_ONLY) {
         collision_kernel<NC, false><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
                                                                M, (const double2 *)obs, free_out, nullptr);
-    } else {
+    } else if (collision_mode() == B200MP_COLLISION_SCREEN_ONLY || items * (long long)M < (1LL << 22)) {
+        // (also for small problems such as the planner's own 7 paths x 106 points: one launch, no prepare pass)
         const dim3 g2(grid, (M + kFTile - 1) / kFTile);
         collision_filter_kernel<NC><<<g2, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride, M,
                                                              (const double2 *)obs, free_out);
+    } else {
+        const int n_chunks = (M + 31) / 32;
+        const size_t pts_bytes = sizeof(float2) * 32 * (size_t)n_chunks, box_bytes = sizeof(float4) * (size_t)n_chunks;
+        void *scratch = nullptr;
+        int rc = ensure_scratch(device, pts_bytes + box_bytes + sizeof(ObsPrep), &scratch);
+        if (rc) return rc;
+        float2 *pts = (float2 *)scratch;
+        float4 *boxes = (float4 *)((char *)scratch + pts_bytes);
+        ObsPrep *prep = (ObsPrep *)((char *)scratch + pts_bytes + box_bytes);
+        B200MP_CUDA(cudaMemsetAsync(prep, 0, sizeof(ObsPrep), st));
+        obstacle_prepare_kernel<<<(n_chunks * 32 + 127) / 128, 128, 0, st>>>(M, (const double2 *)obs, pts, boxes, prep);
+        B200MP_CUDA(cudaGetLastError());
+        // enough CTAs for ~8 per SM even when there are few paths: split the chunk list (in ballot groups of 32 chunks)
+        const int groups = (n_chunks + 31) / 32;
+        int gy = (148 * 8 + grid - 1) / grid;
+        gy = gy < 1 ? 1 : (gy > groups ? groups : gy);
+        collision_cull_kernel<NC><<<dim3(grid, gy), kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
+                                                                     M, (const double2 *)obs, pts, boxes, prep, free_out);
     }
     B200MP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// last launch's broad-phase statistics (synchronises the stream)
+int collision_stats(int device, cudaStream_t st, int M, unsigned long long out[2])
+{
+    DeviceState &ds = dev_state(device);
+    out[0] = out[1] = 0;
+    if (!ds.scratch || M <= 0) return 0;
+    const int n_chunks = (M + 31) / 32;
+    const size_t off = sizeof(float2) * 32 * (size_t)n_chunks + sizeof(float4) * (size_t)n_chunks;
+    ObsPrep h;
+    B200MP_CUDA(cudaMemcpyAsync(&h, (char *)ds.scratch + off, sizeof(h), cudaMemcpyDeviceToHost, st));
+    B200MP_CUDA(cudaStreamSynchronize(st));
+    out[0] = h.screened;
+    out[1] = h.rechecked;
     return 0;
 }
 

@@ -478,15 +478,16 @@ class Engine:
         return "closed_form" if prev == 1 else "auto"
 
     def set_collision_mode(self, mode: str) -> str:
-        """``"auto"`` (FP32 screen + exact FP64 recheck of undecided pairs; default) or ``"fp64"`` (all-FP64
-        kernel).  Both give bit-identical flags; process-wide.  Returns the previous mode."""
-        names = {"auto": 0, "fp64": 1}
+        """``"auto"`` (bounding-box broad phase over 32-point obstacle chunks, FP32 screen, exact FP64 recheck of
+        undecided pairs; default), ``"screen"`` (the same without the broad phase) or ``"fp64"`` (all-FP64 kernel).
+        All give bit-identical flags; process-wide.  Returns the previous mode."""
+        names = {"auto": 0, "fp64": 1, "screen": 2}
         if mode not in names:
             raise ValueError(f"collision mode must be one of {sorted(names)}")
         prev = self.lib.b200mp_set_collision_mode(names[mode])
         if prev < 0:
             check(prev, "b200mp_set_collision_mode")
-        return "fp64" if prev == 1 else "auto"
+        return {0: "auto", 1: "fp64", 2: "screen"}[prev]
 
     def select_best_path_index_batch(self, end_x, end_y, free, goal_xy, weight: float, norm_mode: Optional[int] = None,
                                      want_scores: bool = False):

@@ -22,7 +22,7 @@ def _np(t):
     return t.cpu().numpy()
 
 
-@pytest.fixture(autouse=True, params=["auto", "fp64"])
+@pytest.fixture(autouse=True, params=["auto", "screen", "fp64"])
 def collision_mode(request, engine):
     """Every test runs through both arithmetic modes of the boolean kernel: the FP32-screened default and the
     all-FP64 kernel must give the same bits."""

@@ -45,8 +45,8 @@ int main(int argc, char **argv)
     cudaMemcpy(d_obs, obs.data(), obs.size() * 8, cudaMemcpyHostToDevice);
     const double off[3] = {-1.0, 1.0, 3.0}, rad[3] = {1.5, 1.5, 1.5};
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    std::vector<unsigned char> flags[2];
-    for (int mode = 1; mode >= 0; --mode) {
+    std::vector<unsigned char> flags[3];
+    for (int mode = 2; mode >= 0; --mode) {
         b200mp_set_collision_mode(mode);
         float best = 1e30f, sum = 0; const int reps = 10;
         for (int i = 0; i < 3 + reps; ++i) {
@@ -56,14 +56,15 @@ int main(int argc, char **argv)
             float ms; cudaEventElapsedTime(&ms, e0, e1);
             if (i >= 3) { sum += ms; if (ms < best) best = ms; }
         }
+        if (mode == 0) { unsigned long long st2[2]; b200mp_collision_stats(0, nullptr, M, st2); printf("   broad phase: %llu warp-chunks screened of %lld, %llu thread-chunks rechecked\n", st2[0], (long long)((P * n_pts + 31) / 32) * ((M + 31) / 32), st2[1]); }
         flags[mode].resize(P);
         cudaMemcpy(flags[mode].data(), d_free, P, cudaMemcpyDeviceToHost);
         int nfree = 0; for (unsigned char f : flags[mode]) nfree += f;
         const double tests = (double)P * n_pts * 3 * M;
-        printf("%s P=%d M=%d shift=%g  mean %.3f ms  best %.3f ms  %.3e nominal tests/s  free %d/%d  err=%s\n", mode ? "fp64_only" : "filtered ", P, M, shift,
+        printf("%s P=%d M=%d shift=%g  mean %.3f ms  best %.3f ms  %.3e nominal tests/s  free %d/%d  err=%s\n", mode == 1 ? "fp64_only" : (mode == 2 ? "screen   " : "cull     "), P, M, shift,
                sum / reps, best, tests / (sum / reps * 1e-3), nfree, P, cudaGetErrorString(cudaGetLastError()));
     }
-    int diff = 0; for (int p = 0; p < P; ++p) diff += flags[0][p] != flags[1][p];
+    int diff = 0; for (int p = 0; p < P; ++p) diff += (flags[0][p] != flags[1][p]) + (flags[2][p] != flags[1][p]);
     printf("flag mismatches filtered vs fp64_only: %d\n", diff);
     return diff != 0;
 }
