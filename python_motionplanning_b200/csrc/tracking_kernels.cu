@@ -44,6 +44,8 @@ struct TrackDev {
     const double2 *wp;
     const int *wp_count;
     const double *seg, *head, *cum, *rmax, *clean;
+    const double2 *heads;
+    int heads_stride;
     double *traj, *log, *state_end, *ctrl_end;
     int *target_idx;
     const double *mu_table;   // friction table of parameter set 0 (vehicle_rhs.cuh), used by the no-log kernel
@@ -73,11 +75,16 @@ __device__ __forceinline__ double py_mod(double a, double b)
 __global__ void __launch_bounds__(256)
 track_prepare_kernel(int w_max, const double2 *__restrict__ wp, const int *__restrict__ wp_count, int norm_mode,
                      double *__restrict__ seg, double *__restrict__ head, double *__restrict__ cum,
-                     double *__restrict__ rmax, double *__restrict__ clean)
+                     double *__restrict__ rmax, double *__restrict__ clean, double2 *__restrict__ heads, int heads_stride)
 {
     const int set = blockIdx.x;
     const int W = wp_count[set];
     const double2 *w = wp + (size_t)set * w_max;
+    // chunk heads gathered into one compact array per set (fine heads first, then coarse): the search reads 32
+    // consecutive heads from 4 cache lines instead of 32 lines 128 bytes apart
+    double2 *fh = heads + (size_t)set * heads_stride, *chd = fh + (w_max + kFine - 1) / kFine;
+    for (int i = threadIdx.x; i * kFine < W; i += blockDim.x) fh[i] = w[i * kFine];
+    for (int i = threadIdx.x; i * kCoarse < W; i += blockDim.x) chd[i] = w[i * kCoarse];
     double *sg = seg + (size_t)set * w_max, *hd = head + (size_t)set * w_max, *cm = cum + (size_t)set * w_max;
     double r = 0.0, rc = 0.0;
     int ok = 1;
@@ -127,6 +134,7 @@ track_prepare_kernel(int w_max, const double2 *__restrict__ wp, const int *__res
 }
 
 struct SetView {
+    const double2 *__restrict__ fh, *__restrict__ ch;   // compact fine / coarse chunk heads
     const double2 *__restrict__ w;
     const double *__restrict__ sg, *__restrict__ cm;
     int W;
@@ -134,10 +142,36 @@ struct SetView {
     bool clean;
 };
 
-// first i in [lo, W) with base + (cm[i] - cm0) >= thr, else W   (cm is non-decreasing)
-__device__ __forceinline__ int first_reaching(const double *__restrict__ cm, int lo, int W, double base, double cm0, double thr)
+// first i in [lo, W) with base + (cm[i] - cm0) >= thr, else W   (cm is non-decreasing).  `hint` is where the answer
+// was on the previous control update (a vehicle advances a few waypoints per update): the bracket is grown from
+// there by doubling, so the usual cost is 3-4 probes instead of log2(W).
+__device__ __forceinline__ int first_reaching(const double *__restrict__ cm, int lo, int W, double base, double cm0, double thr,
+                                              int hint)
 {
-    int a = lo, b = W;
+    int a = lo, b = W;      // invariant: every i < a fails the test, every i >= b passes it
+    if (hint > lo && hint < W) {
+        if (base + (cm[hint] - cm0) >= thr) {
+            b = hint;
+            for (int step = 1; b - step >= lo; step <<= 1) {
+                if (base + (cm[b - step] - cm0) >= thr) {
+                    b -= step;
+                } else {
+                    a = b - step + 1;
+                    break;
+                }
+            }
+        } else {
+            a = hint + 1;
+            for (int step = 1; a + step - 1 < W; step <<= 1) {
+                const int j = a + step - 1;
+                if (base + (cm[j] - cm0) >= thr) {
+                    b = j;
+                    break;
+                }
+                a = j + 1;
+            }
+        }
+    }
     while (a < b) {
         const int m = (a + b) >> 1;
         if (base + (cm[m] - cm0) >= thr) b = m; else a = m + 1;
@@ -148,7 +182,7 @@ __device__ __forceinline__ int first_reaching(const double *__restrict__ cm, int
 // get_lookahead_index (stanley_controller.py:56-76): exact nearest waypoint, then the look-ahead walk.
 // hint = a waypoint index near the vehicle (the previous update's nearest index) or -1.
 __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, double y, double lookahead, int mode, int hint,
-                                            int *nearest)
+                                            int la_hint, int *nearest)
 {
     const double2 *__restrict__ w = sv.w;
     const int W = sv.W;
@@ -162,7 +196,7 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
     }
     if (!(qub < INFINITY)) {
         for (int c = 0; c < n_coarse; ++c) {
-            const double2 p = w[c * kCoarse];
+            const double2 p = sv.ch[c];
             qub = fmin(qub, (p.x - x) * (p.x - x) + (p.y - y) * (p.y - y));
         }
     }
@@ -182,7 +216,7 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
     bool near_tie = false;
     for (int g = 0; g < n_coarse; ++g) {
         {
-            const double2 p = w[g * kCoarse];
+            const double2 p = sv.ch[g];
             const double dx = p.x - x, dy = p.y - y;
             if (dx * dx + dy * dy > reach_c) continue;
         }
@@ -191,7 +225,7 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
         unsigned mask = 0;
 #pragma unroll 8
         for (int c = 0; c < gn; ++c) {
-            const double2 p = w[base + c * kFine];
+            const double2 p = sv.fh[g * 32 + c];
             const double dx = p.x - x, dy = p.y - y;
             mask |= (dx * dx + dy * dy > reach ? 0u : 1u) << c;
         }
@@ -244,8 +278,10 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
     if (sv.clean && min_dist < INFINITY) {
         const double cm0 = sv.cm[min_idx];
         const double err = 4.5e-16 * (double)(W + 2) * (sv.cm[W - 1] + min_dist + fabs(lookahead));
-        const int lo = first_reaching(sv.cm, min_idx, W, min_dist, cm0, lookahead - err);
-        const int hi = first_reaching(sv.cm, lo, W, min_dist, cm0, lookahead + err);
+        const int lo = first_reaching(sv.cm, min_idx, W, min_dist, cm0, lookahead - err, la_hint);
+        // the usual case: the same index also reaches lookahead + err (one probe, the line is already in L1)
+        const int hi = (lo >= W || min_dist + (sv.cm[lo] - cm0) >= lookahead + err)
+                           ? lo : first_reaching(sv.cm, lo, W, min_dist, cm0, lookahead + err, -1);
         if (lo == hi) return min(lo, W - 1);
     }
     double total = min_dist;
@@ -280,13 +316,15 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
     const int W = a.wp_count[set];
     SetView sv;
     sv.w = w;
+    sv.fh = a.heads + (size_t)set * a.heads_stride;
+    sv.ch = sv.fh + (a.w_max + kFine - 1) / kFine;
     sv.sg = a.seg + (size_t)set * a.w_max;
     sv.cm = a.cum + (size_t)set * a.w_max;
     sv.W = W;
     sv.rfine = a.rmax[2 * set];
     sv.rcoarse = a.rmax[2 * set + 1];
     sv.clean = a.clean[set] != 0.0;
-    int nearest = -1;
+    int nearest = -1, la_prev = -1;
 
     double y[10], ax, ay;
 #pragma unroll
@@ -310,7 +348,8 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
             int ce = 0;
             double raw;
             if (W > 0) {
-                ce = lookahead_index(sv, px, py, a.lookahead, a.norm_mode, nearest, &nearest);
+                ce = lookahead_index(sv, px, py, a.lookahead, a.norm_mode, nearest, la_prev, &nearest);
+                la_prev = ce;
                 double sn, cs;
                 sincos(yaw, &sn, &cs);
                 const double2 t = w[ce];
@@ -428,8 +467,9 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
         return 0;
     }
     const size_t per = (size_t)g.n_sets * (size_t)(g.w_max > 0 ? g.w_max : 1);
+    const int heads_stride = (g.w_max + kFine - 1) / kFine + (g.w_max + kCoarse - 1) / kCoarse + 1;
     void *scratch = nullptr;
-    int rc = ensure_scratch(device, sizeof(double) * (3 * per + 3 * (size_t)g.n_sets), &scratch);
+    int rc = ensure_scratch(device, sizeof(double) * (3 * per + 4 * (size_t)g.n_sets + 2) + sizeof(double2) * (size_t)g.n_sets * (size_t)heads_stride, &scratch);
     if (rc) return rc;
     TrackDev a;
     a.V = g.V;
@@ -462,13 +502,16 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     a.cum = (double *)scratch + 2 * per;
     a.rmax = (double *)scratch + 3 * per;
     a.clean = (double *)scratch + 3 * per + 2 * (size_t)g.n_sets;
+    a.heads = (const double2 *)((double *)scratch + ((3 * per + 4 * (size_t)g.n_sets + 1) & ~(size_t)1));   // 16-byte aligned
+    a.heads_stride = heads_stride;
     a.traj = g.traj;
     a.log = g.log;
     a.state_end = g.state_end;
     a.ctrl_end = g.ctrl_end;
     a.target_idx = g.target_idx;
     track_prepare_kernel<<<g.n_sets, 256, 0, st>>>(g.w_max, a.wp, g.wp_count, g.norm_mode, (double *)a.seg, (double *)a.head,
-                                                   (double *)a.cum, (double *)a.rmax, (double *)a.clean);
+                                                   (double *)a.cum, (double *)a.rmax, (double *)a.clean,
+                                                   (double2 *)a.heads, heads_stride);
     B200MP_CUDA(cudaGetLastError());
     const DevParams<double> P0 = derive_params<double>(ds.set0);
     const long long grid = (long long)g.n_sets * a.blocks_per_set;
