@@ -68,6 +68,10 @@ constexpr int kRolloutBlock = B200MP_ROLLOUT_BLOCK;
 #define B200MP_RK4_SPECULATIVE 1
 #endif
 constexpr bool kRolloutSpeculative = B200MP_RK4_SPECULATIVE != 0;
+#ifndef B200MP_MU_CACHE_STEPS
+#define B200MP_MU_CACHE_STEPS 0   /* measured: keeping the rows live across steps costs 255 registers and 13 % */
+#endif
+constexpr bool kCacheAcrossSteps = B200MP_MU_CACHE_STEPS != 0;
 #if B200MP_ROLLOUT_MAXNREG > 0
 #define B200MP_ROLLOUT_BOUNDS __maxnreg__(B200MP_ROLLOUT_MAXNREG)
 #else
@@ -151,6 +155,8 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
             int until_store = a.store_stride;
 
             WheelCtrl<R> c;
+            MuRowCache rowc;
+            rowc.k[0] = rowc.k[1] = rowc.k[2] = rowc.k[3] = -1;
             int n = n_begin;
             while (n < n_end) {
                 const int seg = (a.step0 + n) / a.hold;
@@ -175,7 +181,8 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
 #pragma unroll 1
                 for (; n < seg_end; ++n) {
                     R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
-                    rk4_step<R, REAR0, AUX, !GENERIC, (kRolloutSpeculative && !GENERIC && !AUX) || TAB, TAB>(P, D, c, a.dt, y, ax, ay, sdot, outs, T);
+                    rk4_step<R, REAR0, AUX, !GENERIC, (kRolloutSpeculative && !GENERIC && !AUX) || TAB, TAB>(P, D, c, a.dt, y, ax, ay, sdot, outs, T,
+                                                                                                              (TAB && kCacheAcrossSteps) ? &rowc : nullptr);
                     if (a.cost) {
                         const size_t g = (size_t)(a.step0 + n);
                         const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;

@@ -88,6 +88,10 @@ constexpr int kMuCoef = 8;                                // degree 7
 constexpr int kMuCoefD = 5;                               // degrees 0..4 in FP64, 5..7 in FP32
 constexpr int kMuStride = 7;                              // row stride in doubles: 5 doubles + 3 floats + 4 bytes padding
 constexpr int kMuTableDoubles = kMuIntervals * kMuStride;
+#ifndef B200MP_MU_CACHE_ROWS
+#define B200MP_MU_CACHE_ROWS 1
+#endif
+constexpr bool kMuCacheRows = B200MP_MU_CACHE_ROWS != 0;
 
 struct MuTableView {
     const double *c;   // [kMuIntervals][kMuStride]: c4 c3 c2 c1 c0 (FP64), then c7 c6 c5 (FP32); shared memory in the kernels
@@ -105,6 +109,16 @@ B200MP_HD double mu_table_eval(const double *row, double t)
     for (int j = 0; j < kMuCoefD; ++j) g = fma(g, t, row[j]);
     return g;
 }
+
+// The table row of each wheel, kept in registers across the four stages of an RK4 step: the slip of a wheel moves
+// by far less than an interval (1/32 of a binade of x) between stages, so stages 2-4 reload a row only for the lanes
+// whose interval changed -- shared-memory traffic drops ~4x, and so do the bank conflicts of a warp whose rollouts
+// sit in many different intervals.
+struct MuRowCache {
+    int k[4];
+    double c[4][kMuCoefD];
+    float f[4][kMuCoef - kMuCoefD];
+};
 
 // Host: fills table[kMuTableDoubles] for one tyre; returns the measured max relative error of the device
 // evaluation scheme against the long-double reference.
@@ -198,9 +212,9 @@ B200MP_HD void normal_loads(const DevParams<R> &P, R ax_prev, R ay_prev, R Fz[4]
 
 // Tyre of wheel I: slips -> combined-slip Pacejka friction -> forces in the chassis frame.
 // TY1: all four tyres share one (B, C) pair -- read entry 0 so the kernel carries 2 constants, not 8.
-template <typename R, int I, bool REAR0, bool TY1, bool TAB>
+template <typename R, int I, bool REAR0, bool TY1, bool TAB, bool FIRST = true>
 B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd, R sd, R Fz,
-                            R &fx, R &fy, R &fxt, R &fyt, R &s, const MuTableView &T, bool &ok)
+                            R &fx, R &fy, R &fxt, R &fyt, R &s, const MuTableView &T, bool &ok, MuRowCache *RC = nullptr)
 {
     constexpr int J = TY1 ? 0 : I;
     typedef Math<R> M;
@@ -228,7 +242,25 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
         const int k = kraw < 0 ? 0 : (kraw >= kMuIntervals ? kMuIntervals - 1 : kraw);
         const int keep = (int)(0xFFFFFFFFu << (20 - kMuBits));
         const double t = x - M::from_words((hi & keep) | (1 << (19 - kMuBits)), 0);   // x - interval midpoint
-        const double g = mu_table_eval(T.c + k * kMuStride, t);
+        double g;
+        if (RC) {
+            if (FIRST || k != RC->k[I]) {                 // stage 1: always; later stages: only lanes that changed interval
+                const double *row = T.c + k * kMuStride;
+                const float *cf = reinterpret_cast<const float *>(row + kMuCoefD);
+#pragma unroll
+                for (int j = 0; j < kMuCoefD; ++j) RC->c[I][j] = row[j];
+#pragma unroll
+                for (int j = 0; j < kMuCoef - kMuCoefD; ++j) RC->f[I][j] = cf[j];
+                RC->k[I] = k;
+            }
+            const float tf = (float)t;
+            const float tail = fmaf(fmaf(RC->f[I][0], tf, RC->f[I][1]), tf, RC->f[I][2]);
+            g = (double)tail;
+#pragma unroll
+            for (int j = 0; j < kMuCoefD; ++j) g = fma(g, t, RC->c[I][j]);
+        } else {
+            g = mu_table_eval(T.c + k * kMuStride, t);
+        }
         s = (R)0;                        // the combined slip itself is not formed on this path (logging uses the other)
         gF = (R)g * Fz;
     } else {
@@ -255,10 +287,10 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
 // which gets the four stage headings of a step from one sincos plus small-angle rotations).
 // k[10] receives the derivative of the full 10-state (k[7] = wz, k[8] = x_dot, k[9] = y_dot).
 // out (AUX only) = the reference's 18 "outputs".
-template <typename R, bool REAR0, bool AUX, bool TY1, bool TAB = false>
+template <typename R, bool REAR0, bool AUX, bool TY1, bool TAB = false, bool FIRST = true>
 B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R sy, R cy, const WheelCtrl<R> &c,
                           const R Fz[4], R k[10], R &axc, R &ayc, R *out, const MuTableView &T = MuTableView(),
-                          bool *okp = nullptr)
+                          bool *okp = nullptr, MuRowCache *RC = nullptr)
 {
     bool ok = true;
     const R U = y8[0], V = y8[1], wz = y8[2];
@@ -266,10 +298,10 @@ B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R 
     const R vxL = U - hw, vxR = U + hw;
     const R vyF = V + P.a * wz, vyR = V - P.b * wz;
     R fx[4], fy[4], fxt[4], fyt[4], s[4];
-    wheel_forces<R, 0, REAR0, TY1, TAB>(P, D[TY1 ? 0 : 0], vxL, vyF, y8[3], c.cd[0], c.sd[0], Fz[0], fx[0], fy[0], fxt[0], fyt[0], s[0], T, ok);
-    wheel_forces<R, 1, REAR0, TY1, TAB>(P, D[TY1 ? 0 : 1], vxR, vyF, y8[4], c.cd[1], c.sd[1], Fz[1], fx[1], fy[1], fxt[1], fyt[1], s[1], T, ok);
-    wheel_forces<R, 2, REAR0, TY1, TAB>(P, D[TY1 ? 0 : 2], vxL, vyR, y8[5], c.cd[2], c.sd[2], Fz[2], fx[2], fy[2], fxt[2], fyt[2], s[2], T, ok);
-    wheel_forces<R, 3, REAR0, TY1, TAB>(P, D[TY1 ? 0 : 3], vxR, vyR, y8[6], c.cd[3], c.sd[3], Fz[3], fx[3], fy[3], fxt[3], fyt[3], s[3], T, ok);
+    wheel_forces<R, 0, REAR0, TY1, TAB, FIRST>(P, D[TY1 ? 0 : 0], vxL, vyF, y8[3], c.cd[0], c.sd[0], Fz[0], fx[0], fy[0], fxt[0], fyt[0], s[0], T, ok, RC);
+    wheel_forces<R, 1, REAR0, TY1, TAB, FIRST>(P, D[TY1 ? 0 : 1], vxR, vyF, y8[4], c.cd[1], c.sd[1], Fz[1], fx[1], fy[1], fxt[1], fyt[1], s[1], T, ok, RC);
+    wheel_forces<R, 2, REAR0, TY1, TAB, FIRST>(P, D[TY1 ? 0 : 2], vxL, vyR, y8[5], c.cd[2], c.sd[2], Fz[2], fx[2], fy[2], fxt[2], fyt[2], s[2], T, ok, RC);
+    wheel_forces<R, 3, REAR0, TY1, TAB, FIRST>(P, D[TY1 ? 0 : 3], vxR, vyR, y8[6], c.cd[3], c.sd[3], Fz[3], fx[3], fy[3], fxt[3], fyt[3], s[3], T, ok, RC);
 
     const R Vwz = V * wz, Uwz = U * wz;
     const R U_dot = P.inv_m * (fx[0] + fx[1] + fx[2] + fx[3]) + Vwz;     // :376-378
@@ -308,7 +340,7 @@ B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R 
 // repeats the step with SPEC = false, which branches to the library where needed).
 template <typename R, bool REAR0, bool AUX, bool TY1, bool SPEC, bool TAB = false>
 B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtrl<R> &c, R h, R y[10], R &ax, R &ay,
-                             R *sdot, R *outs, const MuTableView &T = MuTableView())
+                             R *sdot, R *outs, const MuTableView &T = MuTableView(), MuRowCache *RCX = nullptr)
 {
     static_assert(!TAB || (SPEC && !AUX), "the tabulated friction path is speculative and does not log the slip");
     typedef Math<R> M;
@@ -325,7 +357,13 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     else
         M::sincos(y[7], &s0, &c0);
 
-    planar_rhs<R, REAR0, AUX, TY1, TAB>(P, D, y, s0, c0, c, Fz, k, axc, ayc, o, T, &ok);
+    // rows cached across the stages (and, when the caller keeps the cache, across steps: RCX->k starts at -1)
+    MuRowCache rc_store;
+    MuRowCache *RC = (TAB && kMuCacheRows) ? (RCX ? RCX : &rc_store) : nullptr;
+    if (RCX)
+        planar_rhs<R, REAR0, AUX, TY1, TAB, false>(P, D, y, s0, c0, c, Fz, k, axc, ayc, o, T, &ok, RC);
+    else
+        planar_rhs<R, REAR0, AUX, TY1, TAB, true>(P, D, y, s0, c0, c, Fz, k, axc, ayc, o, T, &ok, RC);
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] = k[i];
 #pragma unroll
@@ -339,7 +377,7 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     else if (!M::rotate_small(s0, c0, h2 * k[7], &sj, &cj))
         M::sincos(ys[7], &sj, &cj);
 
-    planar_rhs<R, REAR0, AUX, TY1, TAB>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o, T, &ok);
+    planar_rhs<R, REAR0, AUX, TY1, TAB, false>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o, T, &ok, RC);
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] += (R)2 * k[i];
 #pragma unroll
@@ -353,7 +391,7 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     else if (!M::rotate_small(s0, c0, h2 * k[7], &sj, &cj))
         M::sincos(ys[7], &sj, &cj);
 
-    planar_rhs<R, REAR0, AUX, TY1, TAB>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o, T, &ok);
+    planar_rhs<R, REAR0, AUX, TY1, TAB, false>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o, T, &ok, RC);
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] += (R)2 * k[i];
 #pragma unroll
@@ -367,7 +405,7 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     else if (!M::rotate_small(s0, c0, h * k[7], &sj, &cj))
         M::sincos(ys[7], &sj, &cj);
 
-    planar_rhs<R, REAR0, AUX, TY1, TAB>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o, T, &ok);
+    planar_rhs<R, REAR0, AUX, TY1, TAB, false>(P, D, ys, sj, cj, c, Fz, k, axc, ayc, o, T, &ok, RC);
     if (SPEC && !ok) return false;
     const R h6 = (R)(1.0 / 6) * h;       // :438  state + 1/6*h*(K1+2K2+2K3+K4)
     const R sixth = (R)(1.0 / 6);
@@ -404,10 +442,10 @@ void rk4_step_checked(const DevParams<R> &P, const R *D, const WheelCtrl<R> &c, 
 // generic / logging instantiations are already at the register ceiling and keep the branching form).
 template <typename R, bool REAR0, bool AUX, bool TY1, bool SPEC, bool TAB = false>
 B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> &c, R h, R y[10], R &ax, R &ay,
-                        R *sdot, R *outs, const MuTableView &T = MuTableView())
+                        R *sdot, R *outs, const MuTableView &T = MuTableView(), MuRowCache *RCX = nullptr)
 {
     if (SPEC) {
-        if (!rk4_step_impl<R, REAR0, AUX, TY1, true, TAB>(P, D, c, h, y, ax, ay, sdot, outs, T)) {
+        if (!rk4_step_impl<R, REAR0, AUX, TY1, true, TAB>(P, D, c, h, y, ax, ay, sdot, outs, T, RCX)) {
             R axay[2] = {ax, ay};
             rk4_step_checked<R, REAR0, AUX, TY1>(P, D, c, h, y, axay, sdot, outs);
             ax = axay[0];
