@@ -177,7 +177,7 @@ int b200mp_set_params(int device, const B200mpVehicleParams *host_sets, int n_se
             for (int i = 1; i < 4; ++i) uniform = uniform && h.B[i] == h.B[0] && h.C[i] == h.C[0] && h.D[i] == h.D[0];
             ds.mu_table_B2 = 0.0;
             if (uniform && h.B[0] > 0.0 && h.C[0] > 0.0 && h.C[0] < 4.0 && h.D[0] == h.D[0]) {
-                static double host_table[kMuTableDoubles];
+                alignas(16) static double host_table[kMuTableDoubles];
                 ds.mu_table_err = build_mu_table(h.B[0], h.C[0], h.D[0], host_table);
                 if (ds.mu_table_err < 1.0e-15) {
                     if (!ds.mu_table) e = cudaMalloc((void **)&ds.mu_table, sizeof(host_table));

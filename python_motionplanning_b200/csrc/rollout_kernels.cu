@@ -19,10 +19,11 @@ namespace b200mp {
 // Time-sliced scheduling.  Every thread's work is identical, so a batch whose warp count is not a
 // multiple of what the GPU holds at once ends in a tail wave at low occupancy (65,536 rollouts at 12
 // warps per SM = 1.15 waves: the last 15 % of the blocks run alone for a full rollout).  Rollouts are
-// resumable, so instead the launch is cut into (block, time-chunk) items, one CTA each, claimed through
-// an atomic ticket in chunk-major order; item (b, c) starts once done[b] == c, carrying the state
-// through state_end (and the running cost through cost).  An item's predecessor was always claimed
-// earlier by a CTA that is already running, so waiting cannot deadlock.
+// resumable, so instead the launch is cut into (block, time-chunk) items which a grid of persistent CTAs
+// (as many as are resident at once) claims through an atomic ticket in chunk-major order; item (b, c)
+// starts once done[b] == c, carrying the state through state_end (and the running cost through cost).
+// An item's predecessor was always claimed earlier by a CTA that is running or done, so waiting cannot
+// deadlock.
 struct SliceSched {
     int *counter;   // next item to claim
     int *done;      // [n_blocks] chunks completed per rollout block
@@ -38,6 +39,11 @@ __device__ __forceinline__ int ld_acquire(const int *p)
 __device__ __forceinline__ void st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
 template <typename R> struct RolloutDev {
@@ -79,7 +85,9 @@ constexpr bool kCacheAcrossSteps = B200MP_MU_CACHE_STEPS != 0;
 #endif
 
 // SLICED = false: one CTA = one rollout block for the whole launch (no queue code in the kernel at all).
-template <typename R, bool REAR0, bool GENERIC, bool AUX, bool SLICED, bool TAB>
+// COST = false compiles the running-cost code out (it is otherwise carried as predicated-off instructions
+// through every step of a plain rollout).
+template <typename R, bool REAR0, bool GENERIC, bool AUX, bool SLICED, bool TAB, bool COST>
 __global__ void B200MP_ROLLOUT_BOUNDS
 rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constant__ DevParams<R> P0,
                    const __grid_constant__ SliceSched sc)
@@ -95,13 +103,16 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
     }
     const size_t B = (size_t)a.B;
     int item = blockIdx.x;
-    {
+    for (;;) {
         if (SLICED) {
-            // one CTA per (block, chunk) item; items are claimed through a ticket so that an item's
-            // predecessor is always held by a CTA that is already running (dispatch order is not relied on)
+            // persistent CTAs (one grid of resident CTAs, the friction table is staged once per CTA): (block, chunk)
+            // items are claimed through a ticket, so an item's predecessor was always claimed earlier, by a CTA
+            // that is running or done (dispatch order is not relied on) and that never waits on a later ticket
             if (threadIdx.x == 0) s_item = atomicAdd(sc.counter, 1);
             __syncthreads();
             item = s_item;
+            __syncthreads();   // s_item is rewritten by the next round
+            if (item >= sc.n_blocks * sc.n_chunks) break;
         }
         const int chunk_idx = SLICED ? item / sc.n_blocks : 0;
         const int blk = SLICED ? item - chunk_idx * sc.n_blocks : item;
@@ -142,7 +153,7 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
             const size_t rc = cb ? (size_t)r : 0;
             const size_t cB = cb ? B : 1;
             R J = (R)0;
-            if (a.cost) {
+            if (COST && a.cost) {
                 if (SLICED && chunk_idx > 0)
                     J = __ldcg(a.cost + r);
                 else if (a.cost_in)
@@ -171,11 +182,28 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
                         for (int i = 0; i < 4; ++i) dl[i] = a.delta[((size_t)seg * 4 + i) * cB + rc];
                     }
                     set_steer<R, REAR0>(c, dl);
+                    R tau[4];
                     if (a.torque_ch == 1) {
-                        c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = a.torque[(size_t)seg * cB + rc];
+                        tau[0] = tau[1] = tau[2] = tau[3] = a.torque[(size_t)seg * cB + rc];
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) c.tq[i] = a.torque[((size_t)seg * 4 + i) * cB + rc];
+                        for (int i = 0; i < 4; ++i) tau[i] = a.torque[((size_t)seg * 4 + i) * cB + rc];
+                    }
+                    set_torque(c, P, tau);
+                }
+                if (seg_end < n_end) {   // next segment's controls: start them towards L1 now, ten steps ahead of their use
+                    const size_t nx = (size_t)(seg + 1);
+                    if (REAR0) {
+                        prefetch_l1(a.delta + nx * cB + rc);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) prefetch_l1(a.delta + (nx * 4 + i) * cB + rc);
+                    }
+                    if (a.torque_ch == 1) {
+                        prefetch_l1(a.torque + nx * cB + rc);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) prefetch_l1(a.torque + (nx * 4 + i) * cB + rc);
                     }
                 }
 #pragma unroll 1
@@ -183,7 +211,7 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
                     R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
                     rk4_step<R, REAR0, AUX, !GENERIC, (kRolloutSpeculative && !GENERIC && !AUX) || TAB, TAB>(P, D, c, a.dt, y, ax, ay, sdot, outs, T,
                                                                                                               (TAB && kCacheAcrossSteps) ? &rowc : nullptr);
-                    if (a.cost) {
+                    if (COST && a.cost) {
                         const size_t g = (size_t)(a.step0 + n);
                         const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;
                         J = J + (ex * ex + ey * ey + a.w_u * (eu * eu));
@@ -209,13 +237,14 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
             for (int cidx = 0; cidx < 10; ++cidx) a.state_end[cidx * B + r] = y[cidx];
             a.state_end[10 * B + r] = ax;
             a.state_end[11 * B + r] = ay;
-            if (a.cost) a.cost[r] = J;
+            if (COST && a.cost) a.cost[r] = J;
         }
         if (SLICED && chunk_idx + 1 < sc.n_chunks) {   // publish the carried state of this block
             __threadfence();
             __syncthreads();
             if (threadIdx.x == 0) st_release(sc.done + blk, chunk_idx + 1);
         }
+        if (!SLICED) break;
     }
 }
 
@@ -265,7 +294,7 @@ static int start_rollout(K kernel, K kernel_sliced, int device, cudaStream_t st,
         B200MP_CUDA(cudaMemsetAsync(sched_mem, 0, sched_bytes, st));
         sc.counter = (int *)sched_mem;
         sc.done = (int *)sched_mem + 1;
-        grid = n_blocks * sc.n_chunks;
+        grid = n_blocks * sc.n_chunks < resident ? n_blocks * sc.n_chunks : resident;
     }
     if (sc.n_chunks > 1)
         kernel_sliced<<<grid, kRolloutBlock, 0, st>>>(a, P0, sc);
@@ -353,14 +382,17 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
                      friction_mode() == B200MP_FRICTION_AUTO;
     a.mu_table = ds.mu_table;
     a.mu_B2 = ds.mu_table_B2;
+#define B200MP_START2(REAR0, GENERIC, AUX, TAB, COST) \
+    start_rollout<R>(rk4_rollout_kernel<R, REAR0, GENERIC, AUX, false, TAB, COST>, rk4_rollout_kernel<R, REAR0, GENERIC, AUX, true, TAB, COST>, device, st, a, P0)
 #define B200MP_START(REAR0, GENERIC, AUX, TAB) \
-    start_rollout<R>(rk4_rollout_kernel<R, REAR0, GENERIC, AUX, false, TAB>, rk4_rollout_kernel<R, REAR0, GENERIC, AUX, true, TAB>, device, st, a, P0)
+    ((AUX) || g.cost ? B200MP_START2(REAR0, GENERIC, AUX, TAB, true) : B200MP_START2(REAR0, GENERIC, AUX, TAB, (AUX)))
     if (aux)   // logging mode (state_dot + outputs): one generic instantiation per steer layout
         return rear0 ? B200MP_START(true, true, true, false) : B200MP_START(false, true, true, false);
     if (generic) return rear0 ? B200MP_START(true, true, false, false) : B200MP_START(false, true, false, false);
     if (tab) return rear0 ? B200MP_START(true, false, false, (sizeof(R) == 8)) : B200MP_START(false, false, false, (sizeof(R) == 8));
     return rear0 ? B200MP_START(true, false, false, false) : B200MP_START(false, false, false, false);
 #undef B200MP_START
+#undef B200MP_START2
 }
 
 int launch_rollout_f64(int device, cudaStream_t st, const B200mpRolloutArgs &a) { return launch_rollout<double>(device, st, a); }
@@ -378,14 +410,15 @@ planar_model_kernel(int B, const double *__restrict__ state, const double *__res
     if (r >= B) return;
     const size_t Bs = (size_t)B;
     const DevParams<double> P = table[param_set ? param_set[r] : 0];
-    double y[10], D[4], dl[4], Fz[4], k[10], out[18], axc, ayc;
+    double y[10], D[4], dl[4], tau[4], Fz[4], k[10], out[18], axc, ayc;
     WheelCtrl<double> c;
     for (int i = 0; i < 10; ++i) y[i] = state[i * Bs + r];
     for (int i = 0; i < 4; ++i) {
         D[i] = mu ? mu[i * Bs + r] : P.Dc[i];
         dl[i] = delta[i * Bs + r];
-        c.tq[i] = torque[i * Bs + r];
+        tau[i] = torque[i * Bs + r];
     }
+    set_torque(c, P, tau);
     set_steer<double, false>(c, dl);
     normal_loads(P, axay[r], axay[Bs + r], Fz);
     double sy, cy;

@@ -379,7 +379,7 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
             x_del = __dadd_rn(__dmul_rn(1.0 - a.alpha, x_del), __dmul_rn(a.alpha, raw));       // drive.py:137
             delta = x_del;
             set_steer<double, true>(c, &delta);
-            c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = tau;
+            c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = tau * P0.inv_Jw;
             if (a.target_idx) a.target_idx[(size_t)(n / a.ctrl_every) * V + r] = ce;
         }
         const int n_end = min(a.n_steps, n + a.ctrl_every);

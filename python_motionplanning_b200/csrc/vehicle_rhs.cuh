@@ -27,6 +27,7 @@ constexpr double kGravity = 9.81;  // vehicle_model.py:230
 // Device-ready parameter set (derived on the host in double, reference operator order).
 template <typename R> struct DevParams {
     R inv_m, inv_Izz, inv_Jw, a, b, halfT, rw;
+    R rw_inv_Jw;   // rw / Jw: the wheel-spin equation is evaluated as tq/Jw - (rw/Jw) f, one FMA per wheel-stage
     R Fz0F, Fz0R, DfzxL, DfzxR, DfzyF, DfzyR;
     R Bc[4], Cc[4], Dc[4];
 };
@@ -48,6 +49,7 @@ template <typename R> inline DevParams<R> derive_params(const HostParams &p)
     d.b = (R)p.b;
     d.halfT = (R)(p.T / 2);
     d.rw = (R)p.rw;
+    d.rw_inv_Jw = (R)(p.rw / p.Jw);
     d.Fz0F = (R)(p.b / (p.a + p.b) * p.m * g / 2);                      // :245-248
     d.Fz0R = (R)(p.a / (p.a + p.b) * p.m * g / 2);
     d.DfzxL = (R)(p.m * p.hg * p.wR / ((p.a + p.b) * (p.wL + p.wR)));   // :250-253
@@ -70,54 +72,81 @@ template <typename R> inline DevParams<R> derive_params(const HostParams &p)
 // the quantity  G(x) = D B sin(C atan(sqrt(x-1))) / sqrt(x-1)  (so that mu_x = sx G, mu_y = sy G) is analytic
 // on x > 0 (sin(C atan t)/t is even in t; the nearest singularity is x = 0), needs neither the square
 // root nor the reciprocal, and is 0/0-free at zero slip (G(1) = D B C).  For ONE tyre (B, C, D) it is
-// tabulated on the host when the parameter set is uploaded: 32 intervals per binade of x (bounded by the
-// five leading mantissa bits, so the interval index and midpoint come from the bit pattern of x), a
-// degree-7 polynomial in (x - midpoint) per interval from a Chebyshev interpolant computed in long double.
-// The three highest coefficients contribute < 1e-9 of G and are stored and evaluated in FP32 (the FP32 pipe
-// is idle in this kernel); the five lower ones in FP64.  One row is 52 bytes (56 with padding; a 56-byte
-// stride keeps rows 16 apart on distinct shared-memory banks).  The relative error, measured on the host
-// against the long-double reference, is <= 3e-16 (rounding level).  The table covers x < 2^14 (B s < 128,
-// i.e. slip beyond 6 for any realistic B); anything outside, NaN included, clears the speculative step's
-// `ok` flag and the step is repeated on the closed-form path.
-// Cost per wheel-stage from q = sx^2 + sy^2 on: 10 FP64 instructions + 2 conversions instead of 49.
-constexpr int kMuBits = 5;                                // leading mantissa bits used for the interval index
-constexpr int kMuPerBinade = 1 << kMuBits;                // 32
+// tabulated on the host when the parameter set is uploaded: 64 intervals per binade of x (bounded by the
+// six leading mantissa bits, so the interval index and midpoint come from the bit pattern of x), a
+// degree-6 polynomial in t = x - midpoint per interval from a Chebyshev interpolant computed in long double:
+//     G ~ c0 + t (c1 + t (c2 + t (c3 + t [c4 + t c5 + t^2 c6])))   with the bracket evaluated in FP32 (2 FFMA) and the
+// rest in FP64 (4 DFMA).  The bracket's term is < 2^-28 of G, so its FP32 rounding stays below 2^-52 G; it runs on the
+// otherwise idle FP32 pipe.  (Measured: on this kernel the cost of a step is ~ 2 x FP64 instructions + 1 x all others,
+// so the variant that adds the FP32 part last -- shorter dependency chain, 3 more FP32 multiplies -- is slower.)  One row is 4 doubles + 3 floats (+ 4 bytes of padding) = 48 bytes = three
+// 128-bit shared-memory loads; a 48-byte stride maps 8 consecutive rows onto the 8 distinct 16-byte bank
+// groups.  The relative error, measured on the host against the long-double function on the exact device
+// scheme, is <= 4e-16 (rounding level).  The table covers x < 2^14 (B s < 128, i.e. slip beyond 6 for any
+// realistic B; 896 rows = 42 KB); anything outside, NaN included, clears the speculative step's `ok` flag
+// and the step is repeated on the closed-form path.
+// Cost per wheel-stage from q = sx^2 + sy^2 on: 7 FP64 instructions + 2 conversions instead of 49.
+constexpr int kMuBits = 6;                                // leading mantissa bits used for the interval index
+constexpr int kMuPerBinade = 1 << kMuBits;                // 64
 constexpr int kMuBinades = 14;
-constexpr int kMuIntervals = kMuPerBinade * kMuBinades;   // 448 rows = 25 KB
-constexpr int kMuCoef = 8;                                // degree 7
-constexpr int kMuCoefD = 5;                               // degrees 0..4 in FP64, 5..7 in FP32
-constexpr int kMuStride = 7;                              // row stride in doubles: 5 doubles + 3 floats + 4 bytes padding
+constexpr int kMuIntervals = kMuPerBinade * kMuBinades;   // 896 rows = 42 KB
+constexpr int kMuCoefD = 4;                               // degrees 0..3 in FP64
+constexpr int kMuCoefF = 3;                               // degrees 4..6 in FP32
+constexpr int kMuCoef = kMuCoefD + kMuCoefF;              // degree 6
+constexpr int kMuStride = 6;                              // row stride in doubles (48 bytes)
 constexpr int kMuTableDoubles = kMuIntervals * kMuStride;
 #ifndef B200MP_MU_CACHE_ROWS
 #define B200MP_MU_CACHE_ROWS 1
 #endif
 constexpr bool kMuCacheRows = B200MP_MU_CACHE_ROWS != 0;
 
+// One table row as it sits in memory (16-byte aligned, loaded as three 128-bit words).
+struct alignas(16) MuRow {
+    double c3, c2, c1, c0;
+    float c6, c5, c4, pad;
+};
+static_assert(sizeof(MuRow) == kMuStride * sizeof(double), "MuRow must be 48 bytes");
+
 struct MuTableView {
-    const double *c;   // [kMuIntervals][kMuStride]: c4 c3 c2 c1 c0 (FP64), then c7 c6 c5 (FP32); shared memory in the kernels
+    const double *c;   // [kMuIntervals] MuRow; shared memory in the kernels
     double B2;         // B^2
 };
 
-// Double-precision evaluation of one table row exactly as the device does it (host audit + hostsim).
+// Evaluation of one table row exactly as the device does it (also used by the host audit and hostsim).
+B200MP_HD double mu_row_eval(const MuRow &r, double t)
+{
+    const float tf = (float)t;
+    const float tail = fmaf(fmaf(r.c6, tf, r.c5), tf, r.c4);
+    return fma(fma(fma(fma((double)tail, t, r.c3), t, r.c2), t, r.c1), t, r.c0);
+}
+
+// 128-bit loads of one row (the compiler will not merge scalar shared-memory loads on its own)
+B200MP_HD MuRow mu_row_load(const double *table, int k)
+{
+    MuRow r;
+#if defined(__CUDA_ARCH__)
+    const double2 *p = reinterpret_cast<const double2 *>(table + k * kMuStride);
+    const double2 a = p[0], b = p[1];
+    const float4 f = *reinterpret_cast<const float4 *>(p + 2);
+    r.c3 = a.x; r.c2 = a.y; r.c1 = b.x; r.c0 = b.y;
+    r.c6 = f.x; r.c5 = f.y; r.c4 = f.z; r.pad = 0.0f;
+#else
+    r = *reinterpret_cast<const MuRow *>(table + k * kMuStride);
+#endif
+    return r;
+}
+
 B200MP_HD double mu_table_eval(const double *row, double t)
 {
-    const float *cf = reinterpret_cast<const float *>(row + kMuCoefD);
-    const float tf = (float)t;
-    const float tail = fmaf(fmaf(cf[0], tf, cf[1]), tf, cf[2]);
-    double g = (double)tail;
-#pragma unroll
-    for (int j = 0; j < kMuCoefD; ++j) g = fma(g, t, row[j]);
-    return g;
+    return mu_row_eval(*reinterpret_cast<const MuRow *>(row), t);
 }
 
 // The table row of each wheel, kept in registers across the four stages of an RK4 step: the slip of a wheel moves
-// by far less than an interval (1/32 of a binade of x) between stages, so stages 2-4 reload a row only for the lanes
-// whose interval changed -- shared-memory traffic drops ~4x, and so do the bank conflicts of a warp whose rollouts
+// by less than an interval (1/64 of a binade of x) between most stages, so stages 2-4 reload a row only for the lanes
+// whose interval changed -- shared-memory traffic drops, and so do the bank conflicts of a warp whose rollouts
 // sit in many different intervals.
 struct MuRowCache {
     int k[4];
-    double c[4][kMuCoefD];
-    float f[4][kMuCoef - kMuCoefD];
+    MuRow r[4];
 };
 
 // Host: fills table[kMuTableDoubles] for one tyre; returns the measured max relative error of the device
@@ -166,10 +195,15 @@ inline double build_mu_table(double B, double C, double D, double *table)
             scale *= half;
         }
         double *row = table + k * kMuStride;
-        for (int j = 0; j < kMuCoefD; ++j) row[j] = (double)mono[kMuCoefD - 1 - j];          // c4 .. c0
-        float *cf = reinterpret_cast<float *>(row + kMuCoefD);
-        for (int j = 0; j < n - kMuCoefD; ++j) cf[j] = (float)mono[n - 1 - j];               // c7 c6 c5
-        cf[n - kMuCoefD] = 0.0f;
+        MuRow *mr = reinterpret_cast<MuRow *>(row);
+        mr->c3 = (double)mono[3];
+        mr->c2 = (double)mono[2];
+        mr->c1 = (double)mono[1];
+        mr->c0 = (double)mono[0];
+        mr->c6 = (float)mono[6];
+        mr->c5 = (float)mono[5];
+        mr->c4 = (float)mono[4];
+        mr->pad = 0.0f;
         for (int i = 0; i <= 32; ++i) {                   // audit: the device scheme vs the long-double function
             const double x = (double)(lo + (hi - lo) * i / 32.0L * 0.999999L);
             const double g = mu_table_eval(row, x - (double)mid);
@@ -183,8 +217,16 @@ inline double build_mu_table(double B, double C, double D, double *table)
 
 // Controls of one zero-order-hold segment, with the steer trigonometry already evaluated.
 template <typename R> struct WheelCtrl {
-    R cd[4], sd[4], tq[4];
+    R cd[4], sd[4];
+    R tq[4];   // wheel torque / Jw (set_torque)
 };
+
+template <typename R>
+B200MP_HD void set_torque(WheelCtrl<R> &c, const DevParams<R> &P, const R tau[4])
+{
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c.tq[i] = tau[i] * P.inv_Jw;
+}
 
 template <typename R, bool REAR0>
 B200MP_HD void set_steer(WheelCtrl<R> &c, const R delta[4])
@@ -239,27 +281,18 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
         const int hi = M::hi_word(x);
         const int kraw = (hi - 0x3FF00000) >> (20 - kMuBits);         // exponent + leading mantissa bits
         ok &= (unsigned)kraw < (unsigned)kMuIntervals;                // NaN / Inf / beyond the table: repeat the step exactly
-        const int k = kraw < 0 ? 0 : (kraw >= kMuIntervals ? kMuIntervals - 1 : kraw);
+        const int k = (unsigned)kraw < (unsigned)kMuIntervals ? kraw : 0;   // any valid row: the step is repeated anyway
         const int keep = (int)(0xFFFFFFFFu << (20 - kMuBits));
         const double t = x - M::from_words((hi & keep) | (1 << (19 - kMuBits)), 0);   // x - interval midpoint
         double g;
         if (RC) {
             if (FIRST || k != RC->k[I]) {                 // stage 1: always; later stages: only lanes that changed interval
-                const double *row = T.c + k * kMuStride;
-                const float *cf = reinterpret_cast<const float *>(row + kMuCoefD);
-#pragma unroll
-                for (int j = 0; j < kMuCoefD; ++j) RC->c[I][j] = row[j];
-#pragma unroll
-                for (int j = 0; j < kMuCoef - kMuCoefD; ++j) RC->f[I][j] = cf[j];
+                RC->r[I] = mu_row_load(T.c, k);
                 RC->k[I] = k;
             }
-            const float tf = (float)t;
-            const float tail = fmaf(fmaf(RC->f[I][0], tf, RC->f[I][1]), tf, RC->f[I][2]);
-            g = (double)tail;
-#pragma unroll
-            for (int j = 0; j < kMuCoefD; ++j) g = fma(g, t, RC->c[I][j]);
+            g = mu_row_eval(RC->r[I], t);
         } else {
-            g = mu_table_eval(T.c + k * kMuStride, t);
+            g = mu_row_eval(mu_row_load(T.c, k), t);
         }
         s = (R)0;                        // the combined slip itself is not formed on this path (logging uses the other)
         gF = (R)g * Fz;
@@ -304,15 +337,19 @@ B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R 
     wheel_forces<R, 3, REAR0, TY1, TAB, FIRST>(P, D[TY1 ? 0 : 3], vxR, vyR, y8[6], c.cd[3], c.sd[3], Fz[3], fx[3], fy[3], fxt[3], fyt[3], s[3], T, ok, RC);
 
     const R Vwz = V * wz, Uwz = U * wz;
-    const R U_dot = P.inv_m * (fx[0] + fx[1] + fx[2] + fx[3]) + Vwz;     // :376-378
-    const R V_dot = P.inv_m * (fy[0] + fy[1] + fy[2] + fy[3]) - Uwz;
+    // pair sums shared between the force balance and the yaw moment (the reference adds left to right, :376-378;
+    // the difference is one rounding)
+    const R fyF = fy[0] + fy[1], fyR = fy[2] + fy[3];
+    const R fxL = fx[0] + fx[2], fxR = fx[1] + fx[3];
+    const R U_dot = P.inv_m * (fxL + fxR) + Vwz;                          // :376-378
+    const R V_dot = P.inv_m * (fyF + fyR) - Uwz;
     k[0] = U_dot;
     k[1] = V_dot;
-    k[2] = P.inv_Izz * (P.a * (fy[0] + fy[1]) - P.b * (fy[2] + fy[3]) + P.halfT * (fx[1] - fx[0] + fx[3] - fx[2]));
-    k[3] = (c.tq[0] - P.rw * fxt[0]) * P.inv_Jw;                          // :379-382
-    k[4] = (c.tq[1] - P.rw * fxt[1]) * P.inv_Jw;
-    k[5] = (c.tq[2] - P.rw * fx[2]) * P.inv_Jw;   // chassis-frame force on the rear axle, as the reference
-    k[6] = (c.tq[3] - P.rw * fx[3]) * P.inv_Jw;
+    k[2] = P.inv_Izz * (P.a * fyF - P.b * fyR + P.halfT * (fxR - fxL));
+    k[3] = c.tq[0] - P.rw_inv_Jw * fxt[0];                                // :379-382, (tq - rw f)/Jw
+    k[4] = c.tq[1] - P.rw_inv_Jw * fxt[1];
+    k[5] = c.tq[2] - P.rw_inv_Jw * fx[2];     // chassis-frame force on the rear axle, as the reference
+    k[6] = c.tq[3] - P.rw_inv_Jw * fx[3];
     k[7] = wz;                                                            // :383-385
     k[8] = U * cy - V * sy;
     k[9] = U * sy + V * cy;
@@ -446,8 +483,17 @@ B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> 
 {
     if (SPEC) {
         if (!rk4_step_impl<R, REAR0, AUX, TY1, true, TAB>(P, D, c, h, y, ax, ay, sdot, outs, T, RCX)) {
-            R axay[2] = {ax, ay};
-            rk4_step_checked<R, REAR0, AUX, TY1>(P, D, c, h, y, axay, sdot, outs);
+            // the out-of-line call takes addresses: hand it copies, so that the caller's y / c / D stay in
+            // registers on the hot path instead of living in local memory across the step loop
+            R axay[2] = {ax, ay}, yt[10], Dt[4];
+            WheelCtrl<R> ct = c;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) yt[i] = y[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Dt[i] = D[i];
+            rk4_step_checked<R, REAR0, AUX, TY1>(P, Dt, ct, h, yt, axay, sdot, outs);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) y[i] = yt[i];
             ax = axay[0];
             ay = axay[1];
         }

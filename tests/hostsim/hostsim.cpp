@@ -26,7 +26,7 @@ static void run(int B, int n_steps, double dt, int hold, const double *state0, c
         ax = (R)state0[(size_t)10 * B + r];
         ay = (R)state0[(size_t)11 * B + r];
         WheelCtrl<R> c;
-        static double table[kMuTableDoubles];
+        alignas(16) static double table[kMuTableDoubles];
         MuTableView T;
         T.c = table;
         const bool tab = g_use_table && !AUX && sizeof(R) == 8 && !mu;
@@ -41,7 +41,9 @@ static void run(int B, int n_steps, double dt, int hold, const double *state0, c
                 R dl[4] = {0, 0, 0, 0};
                 for (int i = 0; i < dch; ++i) dl[i] = (R)delta[(seg * dch + i) * B + r];
                 set_steer<R, REAR0>(c, dl);
-                for (int i = 0; i < 4; ++i) c.tq[i] = (R)torque[(seg * tch + (tch == 1 ? 0 : i)) * B + r];
+                R tau[4];
+                for (int i = 0; i < 4; ++i) tau[i] = (R)torque[(seg * tch + (tch == 1 ? 0 : i)) * B + r];
+                set_torque(c, P, tau);
             }
             R sdot[10], outs[18];
             if (tab)
