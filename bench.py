@@ -316,9 +316,11 @@ def run_gpu(args):
             "algorithmic_flop_per_step": ALG_FLOP_PER_STEP, "kernel_ms": kernel_ms,
             "fp64_pipe_util_ncu": prof.get("rk4_rollout_f64_fp64_pipe_pct"),
             "smem_wavefront_util_ncu": prof.get("rk4_rollout_f64_smem_wavefront_pct"),
-            "note": "friction from a host-built polynomial table in shared memory (no sqrt/atan/sin in the kernel): fewer FP64 "
-                    "instructions per step, so the FP64-pipe figure drops while throughput rises; the closed-form kernel "
-                    "(secondary.rollout_f64_closed_form) keeps the pipe 81 % busy",
+            "issue_active_ncu": prof.get("rk4_rollout_f64_issue_active_pct"),
+            "note": "friction from a host-built polynomial table in shared memory (no sqrt/atan/sin in the kernel). Measured cost "
+                    "model of this kernel on B200: cycles per warp-step = 2.17 x FP64 instructions + 1 x all other instructions "
+                    "(594 + 437 per step), i.e. the FP64 pipe can be at most 73 % busy with this instruction mix; the closed-form "
+                    "kernel (secondary.rollout_f64_closed_form) keeps the pipe 81 % busy but needs 2x the FP64 instructions",
             "hbm": {"achieved": steps_per_s_gpu * ALG_BYTES_PER_STEP * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": steps_per_s_gpu * ALG_BYTES_PER_STEP * 1e-9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},

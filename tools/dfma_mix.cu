@@ -1,54 +1,60 @@
-// Microbenchmark (development tool): does a non-FP64 instruction issue in the shadow of a DFMA (2 cycles per warp on the
-// 16-lane FP64 pipe) or does it cost its own issue cycle?  ILP-8 DFMA chains mixed with K independent FFMA / IMAD / LDS.
+// Microbenchmark (development tool): does a non-FP64 instruction issue in the shadow of a DFMA (a warp's DFMA holds the
+// 16-lane FP64 pipe of its scheduler for 2 cycles) or does it cost its own issue cycle?  Eight independent DFMA chains
+// with K independent FFMA (or IMAD) chains interleaved, straight-line, one or two warps per scheduler.
 #include <cstdio>
 #include <cuda_runtime.h>
-template <int KF, int KI, int KL> __global__ void mix(double *out, int iters, double a, double b, float fa, int ia)
+template <int K, bool INT> __global__ void mix(double *out, int iters, double a, double b, float fa, int ia)
 {
-    __shared__ float sm[1024];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = i;
-    __syncthreads();
     double x[8];
-    float f[8];
-    int n[8];
-    float l = 0;
+    float f[16];
+    int n[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { x[i] = threadIdx.x * 1e-3 + i; f[i] = threadIdx.x + i; n[i] = threadIdx.x + i; }
+    for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 1e-3 + i;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { f[i] = threadIdx.x + i; n[i] = threadIdx.x + i; }
     long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int rep = 0; rep < 4; ++rep) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                x[i] = fma(x[i], a, b);
-                if (i < KF) f[i] = fmaf(f[i], fa, 1.0f);
-                if (i >= 4 && i - 4 < KF - 8 + 4 && KF > 8) f[i] = fmaf(f[i], fa, 2.0f);
-                if (i < KI) n[i] = n[i] * ia + 7;
-                if (i < KL) l += sm[(n[0] + i * 32 + threadIdx.x) & 1023];
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x[i]) : "d"(a), "d"(b));
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = i * 2 + j;
+                    if (c < K) {
+                        if (INT) asm volatile("mad.lo.s32 %0, %0, %1, 7;" : "+r"(n[c]) : "r"(ia));
+                        else asm volatile("fma.rn.f32 %0, %0, %1, 0f3F800000;" : "+f"(f[c]) : "f"(fa));
+                    }
+                }
             }
+        }
     }
     long long t1 = clock64();
-    double s = l;
+    double s = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += x[i] + f[i] + n[i];
+    for (int i = 0; i < 8; ++i) s += x[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += f[i] + n[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (double)(t1 - t0);
 }
-template <int KF, int KI, int KL> void run(int w)
+template <int K, bool INT> void run(int w)
 {
     double *d; cudaMalloc(&d, 1 << 20);
     const int iters = 2000;
-    for (int k = 0; k < 2; ++k) mix<KF, KI, KL><<<148, 128 * w>>>(d, iters, 1.0000001, 1e-9, 1.0001f, 3);
+    for (int k = 0; k < 2; ++k) mix<K, INT><<<148, 128 * w>>>(d, iters, 1.0000001, 1e-9, 1.0001f, 3);
     double cyc; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
-    const double n = (double)iters * 32;
-    printf("per 8 DFMA: +%d FFMA +%d IMAD +%d LDS, warps/SMSP %d: %.2f cycles per DFMA per SMSP\n", KF, KI, KL, w, cyc / (n * w));
+    const double groups = (double)iters * 4 * w;   // groups of (8 DFMA + K others) issued per scheduler
+    printf("8 DFMA + %2d %s, %d warp(s)/scheduler: %6.2f cycles per group  (co-issue would give %4.1f, separate issue cycles %4.1f)\n", K,
+           INT ? "IMAD" : "FFMA", w, cyc / groups, K > 8 ? 8.0 + K : 16.0, 16.0 + K);
     cudaFree(d);
 }
 int main()
 {
-    for (int w : {1, 2}) {
-        run<0, 0, 0>(w); run<2, 0, 0>(w); run<4, 0, 0>(w); run<8, 0, 0>(w);
-        run<0, 2, 0>(w); run<0, 4, 0>(w); run<0, 8, 0>(w); run<4, 4, 0>(w); run<8, 8, 0>(w);
-        run<0, 0, 1>(w); run<0, 0, 2>(w); run<0, 0, 4>(w);
+    for (int w : {1, 2, 4}) {
+        run<0, false>(w); run<2, false>(w); run<4, false>(w); run<8, false>(w); run<16, false>(w);
+        run<4, true>(w); run<8, true>(w); run<16, true>(w);
     }
     return 0;
 }
