@@ -504,6 +504,58 @@ def secondary_metrics(eng, wl, np, torch):
     torch.cuda.synchronize()
     out["rollout_f64_endstate_only"] = {"value": B * N_STEPS / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT,
                                         "ms": ev0.elapsed_time(ev1)}
+    del s0, dl, tq
+    # config 4 (one GPU's view): 1,048,576 sampled control sequences x 100 steps from one start state, running
+    # cost, lowest-index argmin; the controls are drawn on the device (Philox keyed by the global rollout index)
+    cfg = wl.config4_mpc(B=1 << 20)
+    Bm, Nm = cfg["B"], cfg["n_steps"]
+    s0m = eng.dev(cfg["state0"]).reshape(12, 1).expand(12, Bm).contiguous()
+    cref = eng.dev(cfg["cost_ref"])
+    for k in range(4):
+        if k == 3:
+            ev0.record()
+        dm, tm = eng.mpc_sample_controls(Bm, Nm, cfg["seed"])
+        r = eng.rollout(s0m, dm, tm, DT, Nm, hold=1, cost_ref=cref, w_u=cfg["w_u"], u_ref=cfg["u_ref"])
+        mn, ix = eng.argmin(r.cost)
+    ev1.record()
+    torch.cuda.synchronize()
+    out["mpc_sample_rollout_cost_argmin"] = {"value": Bm * Nm / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT, "ms": ev0.elapsed_time(ev1),
+                                             "sequences": Bm, "horizon": Nm, "best_index": int(ix.item()), "best_cost": float(mn.item()),
+                                             "includes": "control sampling kernel + rollout with running cost + argmin kernels"}
+    del dm, tm, r, s0m
+    # config 5 (FP64 leg): 256 tyre-coefficient sets x 4,096 manoeuvres, per-rollout parameter sets (set-major), 100 steps
+    sets, st5, dl5, tq5, ps5 = wl.config5_sweep()
+    import python_motionplanning_b200 as mp
+    p5 = mp.VehicleParameters()
+    for wname in ("FL", "FR", "RL", "RR"):
+        setattr(p5, "B" + wname, sets[:, 0])
+        setattr(p5, "C" + wname, sets[:, 1])
+        setattr(p5, "D" + wname, sets[:, 2])
+    eng.set_params(p5)
+    a5, b5, c5, s5 = eng.dev(st5), eng.dev(dl5), eng.dev(tq5), eng.dev(ps5, torch.int32)
+    B5, N5 = a5.shape[1], 100
+    for mode in ("auto", "closed_form"):
+        eng.set_friction_mode(mode)
+        for k in range(4):
+            if k == 3:
+                ev0.record()
+            eng.rollout(a5, b5, c5, DT, N5, hold=N5, param_set=s5)
+        ev1.record()
+        torch.cuda.synchronize()
+        out["param_sweep_f64" + ("" if mode == "auto" else "_closed_form")] = {
+            "value": B5 * N5 / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT, "ms": ev0.elapsed_time(ev1), "sets": int(len(sets)),
+            "manoeuvres": int(B5 // len(sets)), "n_steps": N5,
+            "path": "generic kernel; blocks of 64 rollouts that share a set take the tabulated step (per-set D = 1 tables)"
+                    if mode == "auto" else "generic kernel, closed-form friction"}
+    eng.set_friction_mode("auto")
+    for k in range(4):
+        if k == 3:
+            ev0.record()
+        eng.rollout(a5, b5, c5, DT, N5, hold=N5, param_set=s5, dtype="f32")
+    ev1.record()
+    torch.cuda.synchronize()
+    out["param_sweep_f32"] = {"value": B5 * N5 / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT, "ms": ev0.elapsed_time(ev1),
+                              "drift_report": "profiles/r01_fp32_drift_cfg5.json"}
     return out
 
 

@@ -9,6 +9,9 @@
 
 #include <atomic>
 #include <mutex>
+#include <thread>
+#include <vector>
+#include <cstdint>
 
 #include "b200mp_internal.h"
 
@@ -119,6 +122,45 @@ using namespace b200mp;
     DeviceGuard guard__(device);      \
     if (guard__.status() != 0) return guard__.status()
 
+// D = 1 friction tables for every parameter set with four equal (B, C) (see DeviceState::set_tables), built on
+// host threads (23 ms of long-double trigonometry per table).
+static cudaError_t upload_set_tables(DeviceState &ds, const B200mpVehicleParams *sets, int n_sets)
+{
+    if (ds.set_tables) (void)cudaFree(ds.set_tables);
+    if (ds.set_B2) (void)cudaFree(ds.set_B2);
+    ds.set_tables = nullptr;
+    ds.set_B2 = nullptr;
+    ds.set_tables_n = 0;
+    std::vector<double> tables((size_t)n_sets * kMuTableDoubles + 2), B2(n_sets, 0.0);
+    double *base = tables.data();
+    if (reinterpret_cast<uintptr_t>(base) % 16) ++base;   // MuRow is 16-byte aligned
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (int i = next.fetch_add(1); i < n_sets; i = next.fetch_add(1)) {
+            const B200mpVehicleParams &h = sets[i];
+            bool uniform = true;
+            for (int w = 1; w < 4; ++w) uniform = uniform && h.B[w] == h.B[0] && h.C[w] == h.C[0];
+            if (!(uniform && h.B[0] > 0.0 && h.C[0] > 0.0 && h.C[0] < 4.0)) continue;
+            const double err = build_mu_table(h.B[0], h.C[0], 1.0, base + (size_t)i * kMuTableDoubles);
+            if (err < 1.0e-15) B2[i] = h.B[0] * h.B[0];
+        }
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > (unsigned)n_sets) nt = (unsigned)n_sets;
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    cudaError_t e = cudaMalloc((void **)&ds.set_tables, sizeof(double) * (size_t)n_sets * kMuTableDoubles);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ds.set_B2, sizeof(double) * n_sets);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(ds.set_tables, base, sizeof(double) * (size_t)n_sets * kMuTableDoubles, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(ds.set_B2, B2.data(), sizeof(double) * n_sets, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) ds.set_tables_n = n_sets;
+    return e;
+}
+
 extern "C" {
 
 int b200mp_version(void) { return B200MP_VERSION; }
@@ -185,6 +227,7 @@ int b200mp_set_params(int device, const B200mpVehicleParams *host_sets, int n_se
                     if (e == cudaSuccess) ds.mu_table_B2 = h.B[0] * h.B[0];
                 }
             }
+            if (e == cudaSuccess) e = upload_set_tables(ds, host_sets, n_sets);
             if (e != cudaSuccess) rc = cuda_fail(e, "set_params (friction table)");
         } else {
             rc = cuda_fail(e, "set_params");
@@ -334,13 +377,15 @@ int b200mp_shutdown(void)
     (void)cudaGetDevice(&prev);
     for (int d = 0; d < n && d < kMaxDevices; ++d) {
         DeviceState &ds = g_states[d];
-        if (!ds.table64 && !ds.table32 && !ds.scratch && !ds.sched_ring && !ds.mu_table) continue;
+        if (!ds.table64 && !ds.table32 && !ds.scratch && !ds.sched_ring && !ds.mu_table && !ds.set_tables) continue;
         if (cudaSetDevice(d) != cudaSuccess) continue;
         (void)cudaDeviceSynchronize();
         if (ds.table64) (void)cudaFree(ds.table64);
         if (ds.table32) (void)cudaFree(ds.table32);
         if (ds.scratch) (void)cudaFree(ds.scratch);
         if (ds.mu_table) (void)cudaFree(ds.mu_table);
+        if (ds.set_tables) (void)cudaFree(ds.set_tables);
+        if (ds.set_B2) (void)cudaFree(ds.set_B2);
         if (ds.sched_ring) {
             (void)cudaFree(ds.sched_ring);
             for (int i = 0; i < kSchedSlots; ++i) (void)cudaEventDestroy(ds.sched_event[i]);

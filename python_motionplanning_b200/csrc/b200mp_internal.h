@@ -33,6 +33,12 @@ struct DeviceState {
     double *mu_table = nullptr;
     double mu_table_B2 = 0.0;
     double mu_table_err = 0.0;
+    // the same tables normalised to D = 1 for EVERY parameter set whose four tyres share (B, C): [n_sets][kMuTableDoubles],
+    // and B^2 per set (0 = no table: the set is evaluated in closed form).  Used by the generic kernels when all
+    // rollouts of a CTA share one set (parameter sweeps, per-rollout mu_max).
+    double *set_tables = nullptr;
+    double *set_B2 = nullptr;
+    int set_tables_n = 0;
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     // ring of small work-queue areas for time-sliced rollout launches (one per launch in flight)

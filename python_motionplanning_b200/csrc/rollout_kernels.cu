@@ -58,6 +58,8 @@ template <typename R> struct RolloutDev {
     R w_u, u_ref;
     const double *mu_table;   // [kMuTableDoubles] friction table of set 0 (TAB kernels), B^2 beside it
     double mu_B2;
+    const double *set_tables; // [n_sets][kMuTableDoubles] D = 1 tables and [n_sets] B^2 (0 = none): GENERIC TAB kernels
+    const double *set_B2;
 };
 
 // Launch shape.  65,536 rollouts (config 2) are 2,048 warps = 13.8 per SM: with <= 144 registers per
@@ -92,15 +94,16 @@ __global__ void B200MP_ROLLOUT_BOUNDS
 rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constant__ DevParams<R> P0,
                    const __grid_constant__ SliceSched sc)
 {
-    __shared__ int s_item;
+    __shared__ int s_item, s_set, s_cur_set;
     __shared__ __align__(16) double s_mu[TAB ? kMuTableDoubles : 2];
     MuTableView T;
     T.c = s_mu;
     T.B2 = a.mu_B2;
-    if (TAB) {
+    if (TAB && !GENERIC) {   // one tyre for the whole launch: its table (D folded in) is staged once per CTA
         for (int i = threadIdx.x; i < kMuTableDoubles; i += kRolloutBlock) s_mu[i] = a.mu_table[i];
         __syncthreads();
     }
+    if (TAB && GENERIC && threadIdx.x == 0) s_cur_set = -1;   // ordered by the barriers of the first item
     const size_t B = (size_t)a.B;
     int item = blockIdx.x;
     for (;;) {
@@ -124,6 +127,29 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
             __syncthreads();
         }
         const int r = blk * kRolloutBlock + threadIdx.x;
+        // GENERIC + TAB: per-rollout parameter sets / mu_max.  When every rollout of this block uses the same set
+        // (set-major parameter sweeps; any batch with one set and per-rollout mu_max) and that set has a friction table,
+        // the table (normalised to D = 1; D scales the normal load) is staged and the block takes the tabulated step;
+        // otherwise it takes the closed-form step.  The choice is uniform over the CTA.
+        bool use_tab = TAB && !GENERIC;
+        if (TAB && GENERIC) {
+            const int myset = r < a.B ? (a.param_set ? a.param_set[r] : 0) : -1;
+            if (threadIdx.x == 0) s_set = myset;
+            __syncthreads();
+            const int set0 = s_set, cur = s_cur_set;
+            const int uniform = __syncthreads_and(myset == set0 || myset < 0);
+            const double b2 = a.set_B2[set0];
+            use_tab = uniform && b2 > 0.0;
+            if (use_tab) {
+                if (cur != set0) {
+                    const double *src = a.set_tables + (size_t)set0 * kMuTableDoubles;
+                    for (int i = threadIdx.x; i < kMuTableDoubles; i += kRolloutBlock) s_mu[i] = src[i];
+                    if (threadIdx.x == 0) s_cur_set = set0;
+                }
+                T.B2 = b2;
+            }
+            __syncthreads();
+        }
         if (r < a.B) {
             R y[10], ax, ay;
             if (!SLICED || chunk_idx == 0) {
@@ -209,8 +235,11 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
 #pragma unroll 1
                 for (; n < seg_end; ++n) {
                     R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
-                    rk4_step<R, REAR0, AUX, !GENERIC, (kRolloutSpeculative && !GENERIC && !AUX) || TAB, TAB>(P, D, c, a.dt, y, ax, ay, sdot, outs, T,
-                                                                                                              (TAB && kCacheAcrossSteps) ? &rowc : nullptr);
+                    if (TAB && GENERIC && !use_tab)
+                        rk4_step<R, REAR0, AUX, false, false, false>(P, D, c, a.dt, y, ax, ay, sdot, outs);
+                    else
+                        rk4_step<R, REAR0, AUX, !GENERIC, (kRolloutSpeculative && !GENERIC && !AUX) || TAB, TAB>(P, D, c, a.dt, y, ax, ay, sdot, outs, T,
+                                                                                                                  (TAB && kCacheAcrossSteps) ? &rowc : nullptr);
                     if (COST && a.cost) {
                         const size_t g = (size_t)(a.step0 + n);
                         const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;
@@ -382,12 +411,18 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
                      friction_mode() == B200MP_FRICTION_AUTO;
     a.mu_table = ds.mu_table;
     a.mu_B2 = ds.mu_table_B2;
+    a.set_tables = ds.set_tables;
+    a.set_B2 = ds.set_B2;
+    // per-set tables: generic FP64 launches whose blocks turn out to be set-uniform take the tabulated step
+    const bool tabg = sizeof(R) == 8 && generic && !aux && ds.set_tables && ds.set_tables_n == ds.n_sets &&
+                      friction_mode() == B200MP_FRICTION_AUTO;
 #define B200MP_START2(REAR0, GENERIC, AUX, TAB, COST) \
     start_rollout<R>(rk4_rollout_kernel<R, REAR0, GENERIC, AUX, false, TAB, COST>, rk4_rollout_kernel<R, REAR0, GENERIC, AUX, true, TAB, COST>, device, st, a, P0)
 #define B200MP_START(REAR0, GENERIC, AUX, TAB) \
     ((AUX) || g.cost ? B200MP_START2(REAR0, GENERIC, AUX, TAB, true) : B200MP_START2(REAR0, GENERIC, AUX, TAB, (AUX)))
     if (aux)   // logging mode (state_dot + outputs): one generic instantiation per steer layout
         return rear0 ? B200MP_START(true, true, true, false) : B200MP_START(false, true, true, false);
+    if (generic && tabg) return rear0 ? B200MP_START(true, true, false, (sizeof(R) == 8)) : B200MP_START(false, true, false, (sizeof(R) == 8));
     if (generic) return rear0 ? B200MP_START(true, true, false, false) : B200MP_START(false, true, false, false);
     if (tab) return rear0 ? B200MP_START(true, false, false, (sizeof(R) == 8)) : B200MP_START(false, false, false, (sizeof(R) == 8));
     return rear0 ? B200MP_START(true, false, false, false) : B200MP_START(false, false, false, false);

@@ -383,6 +383,10 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     typedef Math<R> M;
     R Fz[4];
     normal_loads(P, ax, ay, Fz);
+    if (TAB && !TY1) {   // tables of the generic path are normalised to D = 1: mu Fz = G(x) (D Fz), D per wheel
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Fz[i] *= D[i];
+    }
     R acc[10], ys[8], k[10], o[AUX ? 18 : 1], axc, ayc, sax, say;
     const R h2 = h * (R)0.5;
     // heading trigonometry: one sincos per step; the three later stage headings are yaw + e with
@@ -487,11 +491,12 @@ B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> 
             // registers on the hot path instead of living in local memory across the step loop
             R axay[2] = {ax, ay}, yt[10], Dt[4];
             WheelCtrl<R> ct = c;
+            const DevParams<R> Pt = P;
 #pragma unroll
             for (int i = 0; i < 10; ++i) yt[i] = y[i];
 #pragma unroll
             for (int i = 0; i < 4; ++i) Dt[i] = D[i];
-            rk4_step_checked<R, REAR0, AUX, TY1>(P, Dt, ct, h, yt, axay, sdot, outs);
+            rk4_step_checked<R, REAR0, AUX, TY1>(Pt, Dt, ct, h, yt, axay, sdot, outs);
 #pragma unroll
             for (int i = 0; i < 10; ++i) y[i] = yt[i];
             ax = axay[0];

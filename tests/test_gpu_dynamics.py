@@ -191,6 +191,31 @@ def test_param_sweep_cfg5_small_f64_and_f32_drift(engine):
     assert report[500] < 2e-4 and report[1] < 1e-6
 
 
+def test_generic_tabulated_step_mixed_blocks_and_mu(engine):
+    """Per-rollout parameter sets + per-wheel mu_max on the generic kernel: blocks whose 64 rollouts share one set take
+    the tabulated step (D = 1 tables, mu_max scales the normal load), a set whose tyres differ between the axles has no
+    table, and blocks that mix sets take the closed form -- all inside one launch, all against the C oracle."""
+    n_sets, B, N = 6, 64 * 12, 300
+    rng = np.random.default_rng(11)
+    sets = np.stack([rng.uniform(8.0, 25.0, n_sets), rng.uniform(1.2, 1.9, n_sets), rng.uniform(0.3, 1.2, n_sets)], 1)
+    p, op = VehicleParameters(), pn.VehicleParams()
+    for w in ("FL", "FR", "RL", "RR"):
+        for q in (p, op):
+            setattr(q, "B" + w, sets[:, 0] * (1.1 if w[0] == "R" else 1.0) ** (np.arange(n_sets) == 3))   # set 3: axles differ
+            setattr(q, "C" + w, sets[:, 1].copy())
+            setattr(q, "D" + w, sets[:, 2].copy())
+    assert engine.set_params(p) == n_sets
+    s0, d, t = wl.config2_rollouts(B=B, n_steps=N)
+    pset = np.concatenate([np.repeat(np.arange(6, dtype=np.int32), 64),            # six uniform blocks (one without table)
+                           rng.integers(0, n_sets, B - 6 * 64).astype(np.int32)])  # six mixed blocks
+    mu = rng.uniform(0.4, 1.1, (4, B))
+    for kw in (dict(param_set=pset), dict(param_set=pset, mu=mu), dict(mu=mu)):
+        got = engine.rollout(s0, d, t, DT, N, hold=wl.HOLD, store_stride=10, **kw)
+        ref = c_oracle.rollout(s0, d, t, c_oracle.make_params(op), DT, N, hold=wl.HOLD, store_stride=10, **kw)
+        e = rel_err(got.traj.cpu().numpy(), ref["traj"])
+        assert e.max() < REL_TOL_F64, (sorted(kw), e.max())
+
+
 def test_mpc_controls_cost_argmin(engine):
     """Config 4 (reduced): Philox control sampling, running cost and device argmin vs restatements."""
     cfg = wl.config4_mpc(B=8192, n_steps=100)
