@@ -89,7 +89,10 @@ constexpr bool kCacheAcrossSteps = B200MP_MU_CACHE_STEPS != 0;
 // SLICED = false: one CTA = one rollout block for the whole launch (no queue code in the kernel at all).
 // COST = false compiles the running-cost code out (it is otherwise carried as predicated-off instructions
 // through every step of a plain rollout).
-template <typename R, bool REAR0, bool GENERIC, bool AUX, bool SLICED, bool TAB, bool COST>
+// H1 = true (front-steer fast path with hold = 1, i.e. new controls every step: sampling MPC, config 4): the controls of
+// step n + 1 are turned into steer sin/cos inside the straight-line block of step n (branch-free form, checked after the
+// step) and those of step n + 2 are requested, instead of a load -> sincos dependency chain in front of every step.
+template <typename R, bool REAR0, bool GENERIC, bool AUX, bool SLICED, bool TAB, bool COST, bool H1 = false>
 __global__ void B200MP_ROLLOUT_BOUNDS
 rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constant__ DevParams<R> P0,
                    const __grid_constant__ SliceSched sc)
@@ -195,7 +198,62 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
             MuRowCache rowc;
             rowc.k[0] = rowc.k[1] = rowc.k[2] = rowc.k[3] = -1;
             int n = n_begin;
-            while (n < n_end) {
+            auto step_body = [&](int nn) {   // one RK4 step + running cost + trajectory / log store
+                    R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
+                    if (TAB && GENERIC && !use_tab)
+                        rk4_step<R, REAR0, AUX, false, false, false>(P, D, c, a.dt, y, ax, ay, sdot, outs);
+                    else
+                        rk4_step<R, REAR0, AUX, !GENERIC, (kRolloutSpeculative && !GENERIC && !AUX) || TAB, TAB>(P, D, c, a.dt, y, ax, ay, sdot, outs, T,
+                                                                                                                  (TAB && kCacheAcrossSteps) ? &rowc : nullptr);
+                    if (COST && a.cost) {
+                        const size_t g = (size_t)(a.step0 + nn);
+                        const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;
+                        J = J + (ex * ex + ey * ey + a.w_u * (eu * eu));
+                    }
+                    if (a.store_stride > 0 && --until_store == 0) {
+                        until_store = a.store_stride;
+                        if (tp) {
+#pragma unroll
+                            for (int cidx = 0; cidx < 10; ++cidx) tp[cidx * B] = y[cidx];
+                            tp += 10 * B;
+                        }
+                        if (AUX && xp) {
+#pragma unroll
+                            for (int cidx = 0; cidx < 10; ++cidx) xp[cidx * B] = sdot[cidx];
+#pragma unroll
+                            for (int cidx = 0; cidx < 18; ++cidx) xp[(10 + cidx) * B] = outs[cidx];
+                            xp += 28 * B;
+                        }
+                    }
+            };
+            static_assert(!H1 || (REAR0 && !GENERIC && !AUX), "H1 is a variant of the front-steer fast path");
+            if (H1) {
+                const size_t g0 = (size_t)(a.step0 + n_begin), glast = (size_t)(a.step0 + n_end - 1);
+                R dl_now = a.delta[g0 * cB + rc], tq_now = a.torque[g0 * cB + rc];
+                set_steer<R, true>(c, &dl_now);
+                c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = tq_now * P.inv_Jw;
+                const size_t g1 = g0 + 1 < glast ? g0 + 1 : glast;
+                R dl_next = a.delta[g1 * cB + rc], tq_next = a.torque[g1 * cB + rc];
+#pragma unroll 1
+                for (; n < n_end; ++n) {
+                    WheelCtrl<R> cn;
+                    R sn, cs;
+                    const R dl_used = dl_next;
+                    const bool steer_ok = Math<R>::sincos_core(dl_used, &sn, &cs);
+                    cn.sd[0] = cn.sd[1] = sn;
+                    cn.cd[0] = cn.cd[1] = cs;
+                    cn.sd[2] = cn.sd[3] = (R)0;
+                    cn.cd[2] = cn.cd[3] = (R)1;
+                    cn.tq[0] = cn.tq[1] = cn.tq[2] = cn.tq[3] = tq_next * P.inv_Jw;
+                    const size_t g2 = (size_t)(a.step0 + n) + 2 < glast ? (size_t)(a.step0 + n) + 2 : glast;
+                    dl_next = a.delta[g2 * cB + rc];
+                    tq_next = a.torque[g2 * cB + rc];
+                    step_body(n);
+                    if (!steer_ok) set_steer<R, true>(cn, &dl_used);   // |delta| > 1e5 or NaN: the library path
+                    c = cn;
+                }
+            }
+            while (!H1 && n < n_end) {
                 const int seg = (a.step0 + n) / a.hold;
                 int seg_end = (seg + 1) * a.hold - a.step0;
                 if (seg_end > n_end) seg_end = n_end;
@@ -234,32 +292,7 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
                 }
 #pragma unroll 1
                 for (; n < seg_end; ++n) {
-                    R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
-                    if (TAB && GENERIC && !use_tab)
-                        rk4_step<R, REAR0, AUX, false, false, false>(P, D, c, a.dt, y, ax, ay, sdot, outs);
-                    else
-                        rk4_step<R, REAR0, AUX, !GENERIC, (kRolloutSpeculative && !GENERIC && !AUX) || TAB, TAB>(P, D, c, a.dt, y, ax, ay, sdot, outs, T,
-                                                                                                                  (TAB && kCacheAcrossSteps) ? &rowc : nullptr);
-                    if (COST && a.cost) {
-                        const size_t g = (size_t)(a.step0 + n);
-                        const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;
-                        J = J + (ex * ex + ey * ey + a.w_u * (eu * eu));
-                    }
-                    if (a.store_stride > 0 && --until_store == 0) {
-                        until_store = a.store_stride;
-                        if (tp) {
-#pragma unroll
-                            for (int cidx = 0; cidx < 10; ++cidx) tp[cidx * B] = y[cidx];
-                            tp += 10 * B;
-                        }
-                        if (AUX && xp) {
-#pragma unroll
-                            for (int cidx = 0; cidx < 10; ++cidx) xp[cidx * B] = sdot[cidx];
-#pragma unroll
-                            for (int cidx = 0; cidx < 18; ++cidx) xp[(10 + cidx) * B] = outs[cidx];
-                            xp += 28 * B;
-                        }
-                    }
+                    step_body(n);
                 }
             }
 #pragma unroll
@@ -418,16 +451,24 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
                       friction_mode() == B200MP_FRICTION_AUTO;
 #define B200MP_START2(REAR0, GENERIC, AUX, TAB, COST) \
     start_rollout<R>(rk4_rollout_kernel<R, REAR0, GENERIC, AUX, false, TAB, COST>, rk4_rollout_kernel<R, REAR0, GENERIC, AUX, true, TAB, COST>, device, st, a, P0)
+#define B200MP_START_H1(TAB, COST) \
+    start_rollout<R>(rk4_rollout_kernel<R, true, false, false, false, TAB, COST, true>, rk4_rollout_kernel<R, true, false, false, true, TAB, COST, true>, device, st, a, P0)
 #define B200MP_START(REAR0, GENERIC, AUX, TAB) \
     ((AUX) || g.cost ? B200MP_START2(REAR0, GENERIC, AUX, TAB, true) : B200MP_START2(REAR0, GENERIC, AUX, TAB, (AUX)))
     if (aux)   // logging mode (state_dot + outputs): one generic instantiation per steer layout
         return rear0 ? B200MP_START(true, true, true, false) : B200MP_START(false, true, true, false);
     if (generic && tabg) return rear0 ? B200MP_START(true, true, false, (sizeof(R) == 8)) : B200MP_START(false, true, false, (sizeof(R) == 8));
     if (generic) return rear0 ? B200MP_START(true, true, false, false) : B200MP_START(false, true, false, false);
+    // per-step controls on the front-steer fast path (sampling MPC): software-pipelined control preparation
+    if (rear0 && !generic && !aux && g.hold == 1 && g.torque_ch == 1 && sizeof(R) == 8) {
+        if (tab) return g.cost ? B200MP_START_H1((sizeof(R) == 8), true) : B200MP_START_H1((sizeof(R) == 8), false);
+        return g.cost ? B200MP_START_H1(false, true) : B200MP_START_H1(false, false);
+    }
     if (tab) return rear0 ? B200MP_START(true, false, false, (sizeof(R) == 8)) : B200MP_START(false, false, false, (sizeof(R) == 8));
     return rear0 ? B200MP_START(true, false, false, false) : B200MP_START(false, false, false, false);
 #undef B200MP_START
 #undef B200MP_START2
+#undef B200MP_START_H1
 }
 
 int launch_rollout_f64(int device, cudaStream_t st, const B200mpRolloutArgs &a) { return launch_rollout<double>(device, st, a); }

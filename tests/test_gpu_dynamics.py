@@ -302,3 +302,26 @@ def test_rollout_out_of_range_headings_take_checked_step(engine):
     # reference's own arithmetic, so the bound on those rows is looser by that factor
     assert e[:, :, mixed].max() < 1e-8, e[:, :, mixed].max()
     assert e[:, :8, mixed].max() < REL_TOL_F64          # body-frame states do not depend on the heading
+
+
+def test_per_step_controls_pipeline_vs_c_oracle(engine):
+    """hold = 1 on the front-steer fast path (the sampling-MPC shape): the kernel prepares the controls of step n + 1
+    inside step n.  Same trajectories as the oracle, including a steer angle beyond the branch-free sincos range
+    (library path), single-step and two-step launches (pipeline prologue / clamped look-ahead) and a resumed launch."""
+    B, N = 640, 60
+    rng = np.random.default_rng(3)
+    s0, _, _ = wl.config2_rollouts(B=B, n_steps=N)
+    d = rng.uniform(-0.1, 0.1, (N, 1, B))
+    t = rng.uniform(-300.0, 300.0, (N, 1, B))
+    d[7, 0, 5] = 2.0e5 + 0.3          # |delta| > 1e5: outside the fast range reduction
+    d[N - 1, 0, 9] = -3.0e5 - 0.2     # ... in the last step, where the look-ahead index is clamped
+    engine.set_params(_params())
+    ref = c_oracle.rollout(s0, d, t, _c_params(), DT, N, hold=1, store_stride=1)
+    got = engine.rollout(s0, d, t, DT, N, hold=1, store_stride=1)
+    e = rel_err(got.traj.cpu().numpy(), ref["traj"])
+    assert e.max() < REL_TOL_F64, e.max()
+    for n1 in (1, 2, 31):             # split launches reproduce the single launch bit for bit
+        a = engine.rollout(s0, d, t, DT, n1, hold=1, store_stride=1)
+        b = engine.rollout(a.state_end, d, t, DT, N - n1, hold=1, store_stride=1, step0=n1)
+        assert torch.equal(torch.cat([a.traj, b.traj]), got.traj)
+        assert torch.equal(b.state_end, got.state_end)
