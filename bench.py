@@ -288,6 +288,32 @@ def run_gpu(args):
     h2d = int(hs.numel() + hd.numel() + ht.numel()) * 8
     d2h = int(traj_host.numel()) * 8
 
+    # ---- config 4 as BASELINE.json states it: 1,048,576 control sequences x 100 steps SHARDED over the ranks (strong
+    # scaling), each plan = sample -> rollout with cost -> local argmin -> all-gather of (cost, index) -> broadcast of
+    # the winner's controls from its owner (NCCL); device-timed, max over ranks
+    mpc_sharded = None
+    if world > 1:
+        from python_motionplanning_b200 import distributed as D
+        cfg4 = wl.config4_mpc(B=1 << 20)
+        for _ in range(3):
+            plan = D.mpc_plan(eng, cfg4)
+        barrier()
+        n_plans = 10
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(n_plans):
+            plan = D.mpc_plan(eng, cfg4)
+        m1.record()
+        barrier()
+        t_m = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_m, op=dist.ReduceOp.MAX)
+        ms_plan = float(t_m.item()) / n_plans
+        mpc_sharded = {"value": cfg4["B"] * cfg4["n_steps"] / (ms_plan * 1e-3), "unit": UNIT, "ms_per_plan": ms_plan,
+                       "sequences_total": cfg4["B"], "horizon": cfg4["n_steps"], "scaling": "strong", "n_gpus": world,
+                       "best_index": int(plan["index"]), "best_cost": float(plan["cost"]), "owner_rank": int(plan["owner"]),
+                       "includes": "sampling + rollout with cost + argmin kernels, NCCL all-gather of (cost, index), broadcast of the "
+                                   "winning control sequence, and the host read of the winner"}
+
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel (rk4_rollout_kernel<double,...>), measured live on this GPU
@@ -347,6 +373,8 @@ def run_gpu(args):
         }
         if extras:
             line["secondary"] = extras
+        if mpc_sharded:
+            line["secondary"] = {"mpc_plan_sharded": mpc_sharded}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
