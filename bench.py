@@ -289,8 +289,8 @@ def run_gpu(args):
     d2h = int(traj_host.numel()) * 8
 
     # ---- config 4 as BASELINE.json states it: 1,048,576 control sequences x 100 steps SHARDED over the ranks (strong
-    # scaling), each plan = sample -> rollout with cost -> local argmin -> all-gather of (cost, index) -> broadcast of
-    # the winner's controls from its owner (NCCL); device-timed, max over ranks
+    # scaling), each plan = sample -> rollout with cost -> local argmin -> one all-gather of per-rank
+    # winner records (cost, index, control sequence; NCCL); device-timed, max over ranks
     mpc_sharded = None
     if world > 1:
         from python_motionplanning_b200 import distributed as D
@@ -311,8 +311,8 @@ def run_gpu(args):
         mpc_sharded = {"value": cfg4["B"] * cfg4["n_steps"] / (ms_plan * 1e-3), "unit": UNIT, "ms_per_plan": ms_plan,
                        "sequences_total": cfg4["B"], "horizon": cfg4["n_steps"], "scaling": "strong", "n_gpus": world,
                        "best_index": int(plan["index"]), "best_cost": float(plan["cost"]), "owner_rank": int(plan["owner"]),
-                       "includes": "sampling + rollout with cost + argmin kernels, NCCL all-gather of (cost, index), broadcast of the "
-                                   "winning control sequence, and the host read of the winner"}
+                       "includes": "sampling + rollout with cost + argmin kernels, ONE NCCL all-gather of per-rank winner records "
+                                   "(cost, index, control sequence) and the host read of the winner"}
 
     line = None
     if rank == 0:

@@ -43,6 +43,15 @@ def _worker(rank, ws, port, cost, flags, q):
         # broadcast of the winner's "control sequence" from its owner
         seq = torch.full((5,), float(rank + 1) * 100 + best_idx) if owner == rank else torch.zeros(5)
         D.broadcast_from(seq, owner)
+        # the MPC exchange proper: one all-gather of per-rank winner records (cost, index, control sequence)
+        n_seg = 5
+        gcol = torch.arange(lo, hi, dtype=torch.float64)
+        dl = torch.arange(n_seg, dtype=torch.float64).reshape(n_seg, 1) * 1000 + gcol            # value = 1000 seg + global index
+        gw = D.gather_winner(mn.to(torch.float64), ix, dl, -dl, lo)
+        assert gw[:3] == (best_cost, best_idx, owner)
+        if best_idx >= 0:
+            want = torch.arange(n_seg, dtype=torch.float64) * 1000 + best_idx
+            assert torch.equal(gw[3], want) and torch.equal(gw[4], -want)
         fl = D.gather_flags(torch.from_numpy(flags[slice(*D.shard_range(len(flags), rank, ws))].copy()), len(flags))
         q.put((rank, best_cost, best_idx, owner, seq.tolist(), fl.numpy().tolist()))
     finally:
