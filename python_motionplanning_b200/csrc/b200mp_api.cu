@@ -218,7 +218,16 @@ int b200mp_set_params(int device, const B200mpVehicleParams *host_sets, int n_se
             bool uniform = true;
             for (int i = 1; i < 4; ++i) uniform = uniform && h.B[i] == h.B[0] && h.C[i] == h.C[0] && h.D[i] == h.D[0];
             ds.mu_table_B2 = 0.0;
+            ds.mu_table_f32_ok = false;
             if (uniform && h.B[0] > 0.0 && h.C[0] > 0.0 && h.C[0] < 4.0 && h.D[0] == h.D[0]) {
+                alignas(16) static float host_table_f32[kMuTableFloats];
+                if (build_mu_table_f32(h.B[0], h.C[0], h.D[0], host_table_f32) < 1.0e-6) {
+                    if (!ds.mu_table_f32) e = cudaMalloc((void **)&ds.mu_table_f32, sizeof(host_table_f32));
+                    if (e == cudaSuccess) e = cudaMemcpy(ds.mu_table_f32, host_table_f32, sizeof(host_table_f32), cudaMemcpyHostToDevice);
+                    ds.mu_table_f32_ok = e == cudaSuccess;
+                }
+            }
+            if (e == cudaSuccess && uniform && h.B[0] > 0.0 && h.C[0] > 0.0 && h.C[0] < 4.0 && h.D[0] == h.D[0]) {
                 alignas(16) static double host_table[kMuTableDoubles];
                 ds.mu_table_err = build_mu_table(h.B[0], h.C[0], h.D[0], host_table);
                 if (ds.mu_table_err < 1.0e-15) {
@@ -384,6 +393,7 @@ int b200mp_shutdown(void)
         if (ds.table32) (void)cudaFree(ds.table32);
         if (ds.scratch) (void)cudaFree(ds.scratch);
         if (ds.mu_table) (void)cudaFree(ds.mu_table);
+        if (ds.mu_table_f32) (void)cudaFree(ds.mu_table_f32);
         if (ds.set_tables) (void)cudaFree(ds.set_tables);
         if (ds.set_B2) (void)cudaFree(ds.set_B2);
         if (ds.sched_ring) {

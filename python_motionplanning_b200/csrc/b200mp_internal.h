@@ -33,6 +33,8 @@ struct DeviceState {
     double *mu_table = nullptr;
     double mu_table_B2 = 0.0;
     double mu_table_err = 0.0;
+    float *mu_table_f32 = nullptr;   // FP32 twin (cubic per interval, vehicle_rhs.cuh: build_mu_table_f32); valid iff mu_table_f32_ok
+    bool mu_table_f32_ok = false;
     // the same tables normalised to D = 1 for EVERY parameter set whose four tyres share (B, C): [n_sets][kMuTableDoubles],
     // and B^2 per set (0 = no table: the set is evaluated in closed form).  Used by the generic kernels when all
     // rollouts of a CTA share one set (parameter sweeps, per-rollout mu_max).

@@ -311,8 +311,6 @@ template <> struct Math<float> {
 #endif
     }
     static B200MP_HD float abs(float x) { return ::fabsf(x); }
-    static B200MP_HD int hi_word(double) { return 0; }             // the tabulated path is FP64 only
-    static B200MP_HD double from_words(int, int) { return 0.0; }
     static B200MP_HD int bits(float x)
     {
 #if defined(__CUDA_ARCH__)

@@ -56,7 +56,7 @@ template <typename R> struct RolloutDev {
     R *traj, *aux, *state_end, *cost;
     const R *cost_in, *cost_ref;
     R w_u, u_ref;
-    const double *mu_table;   // [kMuTableDoubles] friction table of set 0 (TAB kernels), B^2 beside it
+    const void *mu_table;     // friction table of set 0 in the precision of R (TAB kernels), B^2 beside it
     double mu_B2;
     const double *set_tables; // [n_sets][kMuTableDoubles] D = 1 tables and [n_sets] B^2 (0 = none): GENERIC TAB kernels
     const double *set_B2;
@@ -98,12 +98,14 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
                    const __grid_constant__ SliceSched sc)
 {
     __shared__ int s_item, s_set, s_cur_set;
-    __shared__ __align__(16) double s_mu[TAB ? kMuTableDoubles : 2];
+    constexpr int kTabWords = MuTab<R>::kBytes / 8;
+    __shared__ __align__(16) double s_mu[TAB ? kTabWords : 2];
     MuTableView T;
     T.c = s_mu;
     T.B2 = a.mu_B2;
     if (TAB && !GENERIC) {   // one tyre for the whole launch: its table (D folded in) is staged once per CTA
-        for (int i = threadIdx.x; i < kMuTableDoubles; i += kRolloutBlock) s_mu[i] = a.mu_table[i];
+        const double *src = static_cast<const double *>(a.mu_table);
+        for (int i = threadIdx.x; i < kTabWords; i += kRolloutBlock) s_mu[i] = src[i];
         __syncthreads();
     }
     if (TAB && GENERIC && threadIdx.x == 0) s_cur_set = -1;   // ordered by the barriers of the first item
@@ -195,7 +197,7 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
             int until_store = a.store_stride;
 
             WheelCtrl<R> c;
-            MuRowCache rowc;
+            MuRowCacheT<typename MuTab<R>::Row> rowc;
             rowc.k[0] = rowc.k[1] = rowc.k[2] = rowc.k[3] = -1;
             int n = n_begin;
             auto step_body = [&](int nn) {   // one RK4 step + running cost + trajectory / log store
@@ -440,9 +442,9 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
     const bool generic = g.mu != nullptr || g.param_set != nullptr || !uniform_tyres;
     const bool aux = g.aux != nullptr;
     // tabulated friction: FP64 fast path only, when set_params could build the table of set 0
-    const bool tab = sizeof(R) == 8 && !generic && !aux && ds.mu_table && ds.mu_table_B2 > 0.0 &&
-                     friction_mode() == B200MP_FRICTION_AUTO;
-    a.mu_table = ds.mu_table;
+    const bool have_table = sizeof(R) == 8 ? (ds.mu_table && ds.mu_table_B2 > 0.0) : ds.mu_table_f32_ok;
+    const bool tab = !generic && !aux && have_table && friction_mode() == B200MP_FRICTION_AUTO;
+    a.mu_table = sizeof(R) == 8 ? (const void *)ds.mu_table : (const void *)ds.mu_table_f32;
     a.mu_B2 = ds.mu_table_B2;
     a.set_tables = ds.set_tables;
     a.set_B2 = ds.set_B2;
@@ -460,11 +462,11 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
     if (generic && tabg) return rear0 ? B200MP_START(true, true, false, (sizeof(R) == 8)) : B200MP_START(false, true, false, (sizeof(R) == 8));
     if (generic) return rear0 ? B200MP_START(true, true, false, false) : B200MP_START(false, true, false, false);
     // per-step controls on the front-steer fast path (sampling MPC): software-pipelined control preparation
-    if (rear0 && !generic && !aux && g.hold == 1 && g.torque_ch == 1 && sizeof(R) == 8) {
-        if (tab) return g.cost ? B200MP_START_H1((sizeof(R) == 8), true) : B200MP_START_H1((sizeof(R) == 8), false);
+    if (rear0 && !generic && !aux && g.hold == 1 && g.torque_ch == 1) {
+        if (tab) return g.cost ? B200MP_START_H1(true, true) : B200MP_START_H1(true, false);
         return g.cost ? B200MP_START_H1(false, true) : B200MP_START_H1(false, false);
     }
-    if (tab) return rear0 ? B200MP_START(true, false, false, (sizeof(R) == 8)) : B200MP_START(false, false, false, (sizeof(R) == 8));
+    if (tab) return rear0 ? B200MP_START(true, false, false, true) : B200MP_START(false, false, false, true);
     return rear0 ? B200MP_START(true, false, false, false) : B200MP_START(false, false, false, false);
 #undef B200MP_START
 #undef B200MP_START2

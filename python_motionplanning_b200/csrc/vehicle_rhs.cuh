@@ -107,7 +107,7 @@ struct alignas(16) MuRow {
 static_assert(sizeof(MuRow) == kMuStride * sizeof(double), "MuRow must be 48 bytes");
 
 struct MuTableView {
-    const double *c;   // [kMuIntervals] MuRow; shared memory in the kernels
+    const void *c;     // the table (MuRow[kMuIntervals] for FP64, MuRowF[kMuIntervalsF] for FP32); shared memory in the kernels
     double B2;         // B^2
 };
 
@@ -144,9 +144,57 @@ B200MP_HD double mu_table_eval(const double *row, double t)
 // by less than an interval (1/64 of a binade of x) between most stages, so stages 2-4 reload a row only for the lanes
 // whose interval changed -- shared-memory traffic drops, and so do the bank conflicts of a warp whose rollouts
 // sit in many different intervals.
-struct MuRowCache {
+template <typename Row> struct MuRowCacheT {
     int k[4];
-    MuRow r[4];
+    Row r[4];
+};
+typedef MuRowCacheT<MuRow> MuRowCache;
+
+// Host: monomial coefficients (in x - mid) of the degree n-1 Chebyshev interpolant of G on [lo, hi], in long double.
+template <typename F> inline void mu_fit_interval(F G, long double lo, long double hi, int n, long double *mono, long double *mid_out)
+{
+    typedef long double L;
+    const L pi = 3.14159265358979323846264338327950288L;
+    const L mid = 0.5L * (lo + hi), half = 0.5L * (hi - lo);
+    L f[16], c[16], T0[16] = {0}, T1[16] = {0};
+    for (int i = 0; i < n; ++i) f[i] = G(mid + half * cosl(pi * (2 * i + 1) / (2 * n)));
+    for (int j = 0; j < n; ++j) {
+        L acc = 0;
+        for (int i = 0; i < n; ++i) acc += f[i] * cosl(pi * j * (2 * i + 1) / (2 * n));
+        c[j] = acc * 2 / n;
+    }
+    c[0] /= 2;
+    // Chebyshev series in tau = (x - mid)/half -> monomials in tau -> monomials in (x - mid)
+    T0[0] = 1;
+    T1[1] = 1;
+    for (int j = 0; j < n; ++j) mono[j] = c[0] * T0[j] + c[1] * T1[j];
+    for (int d = 2; d < n; ++d) {
+        L T2[16];
+        for (int j = 0; j < n; ++j) T2[j] = (j > 0 ? 2 * T1[j - 1] : 0) - T0[j];
+        for (int j = 0; j < n; ++j) {
+            mono[j] += c[d] * T2[j];
+            T0[j] = T1[j];
+            T1[j] = T2[j];
+        }
+    }
+    L scale = 1;
+    for (int j = 0; j < n; ++j) {
+        mono[j] /= scale;
+        scale *= half;
+    }
+    *mid_out = mid;
+}
+
+struct MuFunction {   // G(x) = D B sin(C atan(sqrt(x-1))) / sqrt(x-1) in long double
+    double B, C, D;
+    long double operator()(long double x) const
+    {
+        typedef long double L;
+        const L u = x - 1.0L;
+        if (u <= 0.0L) return (L)D * (L)B * (L)C;
+        const L r = sqrtl(u);
+        return (L)D * (L)B * sinl((L)C * atanl(r)) / r;
+    }
 };
 
 // Host: fills table[kMuTableDoubles] for one tyre; returns the measured max relative error of the device
@@ -154,46 +202,13 @@ struct MuRowCache {
 inline double build_mu_table(double B, double C, double D, double *table)
 {
     typedef long double L;
-    const L pi = 3.14159265358979323846264338327950288L;
-    auto G = [&](L x) -> L {
-        const L u = x - 1.0L;
-        if (u <= 0.0L) return (L)D * (L)B * (L)C;
-        const L r = sqrtl(u);
-        return (L)D * (L)B * sinl((L)C * atanl(r)) / r;
-    };
-    const int n = kMuCoef;
+    const MuFunction G{B, C, D};
     double worst = 0.0;
     for (int k = 0; k < kMuIntervals; ++k) {
         const int e = k / kMuPerBinade, m = k % kMuPerBinade;
         const L lo = ldexpl(1.0L + (L)m / kMuPerBinade, e), hi = ldexpl(1.0L + (L)(m + 1) / kMuPerBinade, e);
-        const L mid = 0.5L * (lo + hi), half = 0.5L * (hi - lo);
-        L f[kMuCoef], c[kMuCoef];
-        for (int i = 0; i < n; ++i) f[i] = G(mid + half * cosl(pi * (2 * i + 1) / (2 * n)));
-        for (int j = 0; j < n; ++j) {
-            L acc = 0;
-            for (int i = 0; i < n; ++i) acc += f[i] * cosl(pi * j * (2 * i + 1) / (2 * n));
-            c[j] = acc * 2 / n;
-        }
-        c[0] /= 2;
-        // Chebyshev series in tau = (x - mid)/half -> monomials in tau -> monomials in (x - mid)
-        L T0[kMuCoef] = {0}, T1[kMuCoef] = {0}, mono[kMuCoef] = {0};
-        T0[0] = 1;
-        T1[1] = 1;
-        for (int j = 0; j < n; ++j) mono[j] = c[0] * T0[j] + c[1] * T1[j];
-        for (int d = 2; d < n; ++d) {
-            L T2[kMuCoef];
-            for (int j = 0; j < n; ++j) T2[j] = (j > 0 ? 2 * T1[j - 1] : 0) - T0[j];
-            for (int j = 0; j < n; ++j) {
-                mono[j] += c[d] * T2[j];
-                T0[j] = T1[j];
-                T1[j] = T2[j];
-            }
-        }
-        L scale = 1;
-        for (int j = 0; j < n; ++j) {
-            mono[j] /= scale;
-            scale *= half;
-        }
+        L mono[16], mid;
+        mu_fit_interval(G, lo, hi, kMuCoef, mono, &mid);
         double *row = table + k * kMuStride;
         MuRow *mr = reinterpret_cast<MuRow *>(row);
         mr->c3 = (double)mono[3];
@@ -214,6 +229,88 @@ inline double build_mu_table(double B, double C, double D, double *table)
     }
     return worst;
 }
+
+// ---- FP32 twin of the table (K1f): the same function of x = 1 + (B s)^2 evaluated in single precision, 32 intervals
+// per binade (five leading mantissa bits of the float), one cubic per interval = 4 floats = ONE 128-bit load; 448 rows
+// = 7 KB.  Cubic truncation is ~1e-8 of G, below the FP32 rounding of the evaluation itself (audited <= 4e-7 against
+// the long-double function, i.e. a few FP32 ulps, like the closed-form FP32 routines it replaces).
+constexpr int kMuBitsF = 5;
+constexpr int kMuPerBinadeF = 1 << kMuBitsF;
+constexpr int kMuIntervalsF = kMuPerBinadeF * kMuBinades;   // 448
+constexpr int kMuTableFloats = kMuIntervalsF * 4;
+struct alignas(16) MuRowF {
+    float c3, c2, c1, c0;
+};
+B200MP_HD float mu_row_eval(const MuRowF &r, float t) { return fmaf(fmaf(fmaf(r.c3, t, r.c2), t, r.c1), t, r.c0); }
+B200MP_HD MuRowF mu_row_load(const float *table, int k)
+{
+    MuRowF r;
+#if defined(__CUDA_ARCH__)
+    const float4 v = reinterpret_cast<const float4 *>(table)[k];
+    r.c3 = v.x; r.c2 = v.y; r.c1 = v.z; r.c0 = v.w;
+#else
+    r = reinterpret_cast<const MuRowF *>(table)[k];
+#endif
+    return r;
+}
+inline double build_mu_table_f32(double B, double C, double D, float *table)
+{
+    typedef long double L;
+    const MuFunction G{B, C, D};
+    double worst = 0.0;
+    for (int k = 0; k < kMuIntervalsF; ++k) {
+        const int e = k / kMuPerBinadeF, m = k % kMuPerBinadeF;
+        const L lo = ldexpl(1.0L + (L)m / kMuPerBinadeF, e), hi = ldexpl(1.0L + (L)(m + 1) / kMuPerBinadeF, e);
+        L mono[16], mid;
+        mu_fit_interval(G, lo, hi, 4, mono, &mid);
+        MuRowF *mr = reinterpret_cast<MuRowF *>(table) + k;
+        mr->c3 = (float)mono[3];
+        mr->c2 = (float)mono[2];
+        mr->c1 = (float)mono[1];
+        mr->c0 = (float)mono[0];
+        for (int i = 0; i <= 32; ++i) {
+            const float x = (float)(lo + (hi - lo) * i / 32.0L * 0.999999L);
+            if ((L)x < lo || (L)x >= hi) continue;
+            const float g = mu_row_eval(*mr, x - (float)mid);
+            const L ref = G((L)x);
+            const double err = (double)fabsl(((L)g - ref) / ref);
+            if (err > worst) worst = err;
+        }
+    }
+    return worst;
+}
+
+// Per-precision view of the table machinery used by wheel_forces<.., TAB = true>.
+template <typename R> struct MuTab;
+template <> struct MuTab<double> {
+    typedef MuRow Row;
+    static constexpr int kIntervals = kMuIntervals;
+    static constexpr int kBytes = kMuTableDoubles * 8;
+    // interval index (unclamped) and t = x - midpoint from the bit pattern of x = 1 + B^2 q
+    static B200MP_HD int locate(double q, double B2, double *t)
+    {
+        const double x = fma(q, B2, 1.0);
+        const int hi = Math<double>::hi_word(x);
+        const int keep = (int)(0xFFFFFFFFu << (20 - kMuBits));
+        *t = x - Math<double>::from_words((hi & keep) | (1 << (19 - kMuBits)), 0);
+        return (hi - 0x3FF00000) >> (20 - kMuBits);              // exponent + leading mantissa bits
+    }
+    static B200MP_HD Row load(const void *table, int k) { return mu_row_load(static_cast<const double *>(table), k); }
+};
+template <> struct MuTab<float> {
+    typedef MuRowF Row;
+    static constexpr int kIntervals = kMuIntervalsF;
+    static constexpr int kBytes = kMuTableFloats * 4;
+    static B200MP_HD int locate(float q, float B2, float *t)
+    {
+        const float x = fmaf(q, B2, 1.0f);
+        const int b = Math<float>::bits(x);
+        const int keep = (int)(0xFFFFFFFFu << (23 - kMuBitsF));
+        *t = x - Math<float>::from_bits((b & keep) | (1 << (22 - kMuBitsF)));
+        return (b - 0x3F800000) >> (23 - kMuBitsF);
+    }
+    static B200MP_HD Row load(const void *table, int k) { return mu_row_load(static_cast<const float *>(table), k); }
+};
 
 // Controls of one zero-order-hold segment, with the steer trigonometry already evaluated.
 template <typename R> struct WheelCtrl {
@@ -256,7 +353,7 @@ B200MP_HD void normal_loads(const DevParams<R> &P, R ax_prev, R ay_prev, R Fz[4]
 // TY1: all four tyres share one (B, C) pair -- read entry 0 so the kernel carries 2 constants, not 8.
 template <typename R, int I, bool REAR0, bool TY1, bool TAB, bool FIRST = true>
 B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd, R sd, R Fz,
-                            R &fx, R &fy, R &fxt, R &fyt, R &s, const MuTableView &T, bool &ok, MuRowCache *RC = nullptr)
+                            R &fx, R &fy, R &fxt, R &fyt, R &s, const MuTableView &T, bool &ok, MuRowCacheT<typename MuTab<R>::Row> *RC = nullptr)
 {
     constexpr int J = TY1 ? 0 : I;
     typedef Math<R> M;
@@ -277,25 +374,23 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
     R gF;
     if (TAB) {
         // tabulated G(x) = D B sin(C atan(B s)) / (B s), x = 1 + (B s)^2: no sqrt, no reciprocal, no atan, no sin
-        const double x = fma((double)q, T.B2, 1.0);
-        const int hi = M::hi_word(x);
-        const int kraw = (hi - 0x3FF00000) >> (20 - kMuBits);         // exponent + leading mantissa bits
-        ok &= (unsigned)kraw < (unsigned)kMuIntervals;                // NaN / Inf / beyond the table: repeat the step exactly
-        const int k = (unsigned)kraw < (unsigned)kMuIntervals ? kraw : 0;   // any valid row: the step is repeated anyway
-        const int keep = (int)(0xFFFFFFFFu << (20 - kMuBits));
-        const double t = x - M::from_words((hi & keep) | (1 << (19 - kMuBits)), 0);   // x - interval midpoint
-        double g;
+        typedef MuTab<R> MT;
+        R t;
+        const int kraw = MT::locate(q, (R)T.B2, &t);
+        ok &= (unsigned)kraw < (unsigned)MT::kIntervals;                   // NaN / Inf / beyond the table: repeat the step exactly
+        const int k = (unsigned)kraw < (unsigned)MT::kIntervals ? kraw : 0;   // any valid row: the step is repeated anyway
+        R g;
         if (RC) {
             if (FIRST || k != RC->k[I]) {                 // stage 1: always; later stages: only lanes that changed interval
-                RC->r[I] = mu_row_load(T.c, k);
+                RC->r[I] = MT::load(T.c, k);
                 RC->k[I] = k;
             }
             g = mu_row_eval(RC->r[I], t);
         } else {
-            g = mu_row_eval(mu_row_load(T.c, k), t);
+            g = mu_row_eval(MT::load(T.c, k), t);
         }
         s = (R)0;                        // the combined slip itself is not formed on this path (logging uses the other)
-        gF = (R)g * Fz;
+        gF = g * Fz;
     } else {
         (void)J;
         const bool slipping = q != (R)0;
@@ -323,7 +418,7 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
 template <typename R, bool REAR0, bool AUX, bool TY1, bool TAB = false, bool FIRST = true>
 B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R sy, R cy, const WheelCtrl<R> &c,
                           const R Fz[4], R k[10], R &axc, R &ayc, R *out, const MuTableView &T = MuTableView(),
-                          bool *okp = nullptr, MuRowCache *RC = nullptr)
+                          bool *okp = nullptr, MuRowCacheT<typename MuTab<R>::Row> *RC = nullptr)
 {
     bool ok = true;
     const R U = y8[0], V = y8[1], wz = y8[2];
@@ -377,7 +472,7 @@ B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R 
 // repeats the step with SPEC = false, which branches to the library where needed).
 template <typename R, bool REAR0, bool AUX, bool TY1, bool SPEC, bool TAB = false>
 B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtrl<R> &c, R h, R y[10], R &ax, R &ay,
-                             R *sdot, R *outs, const MuTableView &T = MuTableView(), MuRowCache *RCX = nullptr)
+                             R *sdot, R *outs, const MuTableView &T = MuTableView(), MuRowCacheT<typename MuTab<R>::Row> *RCX = nullptr)
 {
     static_assert(!TAB || (SPEC && !AUX), "the tabulated friction path is speculative and does not log the slip");
     typedef Math<R> M;
@@ -399,8 +494,8 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
         M::sincos(y[7], &s0, &c0);
 
     // rows cached across the stages (and, when the caller keeps the cache, across steps: RCX->k starts at -1)
-    MuRowCache rc_store;
-    MuRowCache *RC = (TAB && kMuCacheRows) ? (RCX ? RCX : &rc_store) : nullptr;
+    MuRowCacheT<typename MuTab<R>::Row> rc_store;
+    MuRowCacheT<typename MuTab<R>::Row> *RC = (TAB && kMuCacheRows) ? (RCX ? RCX : &rc_store) : nullptr;
     if (RCX)
         planar_rhs<R, REAR0, AUX, TY1, TAB, false>(P, D, y, s0, c0, c, Fz, k, axc, ayc, o, T, &ok, RC);
     else
@@ -483,7 +578,7 @@ void rk4_step_checked(const DevParams<R> &P, const R *D, const WheelCtrl<R> &c, 
 // generic / logging instantiations are already at the register ceiling and keep the branching form).
 template <typename R, bool REAR0, bool AUX, bool TY1, bool SPEC, bool TAB = false>
 B200MP_HD void rk4_step(const DevParams<R> &P, const R D[4], const WheelCtrl<R> &c, R h, R y[10], R &ax, R &ay,
-                        R *sdot, R *outs, const MuTableView &T = MuTableView(), MuRowCache *RCX = nullptr)
+                        R *sdot, R *outs, const MuTableView &T = MuTableView(), MuRowCacheT<typename MuTab<R>::Row> *RCX = nullptr)
 {
     if (SPEC) {
         if (!rk4_step_impl<R, REAR0, AUX, TY1, true, TAB>(P, D, c, h, y, ax, ay, sdot, outs, T, RCX)) {
