@@ -12,6 +12,7 @@
 //   * controls are zero-order-hold segments: the steer sincos is evaluated once per segment;
 //   * bound: the FP64 (or FP32) CUDA-core pipe; no tensor cores (nothing is a contraction), HBM only
 //     for the 80 B/step trajectory writeback.
+#pragma once
 #include "b200mp_internal.h"
 
 namespace b200mp {
@@ -473,9 +474,16 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
 #undef B200MP_START_H1
 }
 
+// One translation unit per precision (rollout_kernels_f64.cu / rollout_kernels_f32.cu define the macro): the two sets
+// of ~40 kernel instantiations compile in parallel.
+#if defined(B200MP_ROLLOUT_F64)
 int launch_rollout_f64(int device, cudaStream_t st, const B200mpRolloutArgs &a) { return launch_rollout<double>(device, st, a); }
+#endif
+#if defined(B200MP_ROLLOUT_F32)
 int launch_rollout_f32(int device, cudaStream_t st, const B200mpRolloutArgs &a) { return launch_rollout<float>(device, st, a); }
+#endif
 
+#if defined(B200MP_ROLLOUT_F64)
 // ---------------------------------------------------------------------------------------------------
 // Batched single RHS evaluation: VehicleModel.planar_model (vehicle_model.py:220-425), full return list.
 __global__ void __launch_bounds__(128)
@@ -535,5 +543,7 @@ int launch_planar_model_f64(int device, cudaStream_t st, int B, const double *st
     B200MP_CUDA(cudaGetLastError());
     return 0;
 }
+
+#endif   // B200MP_ROLLOUT_F64
 
 }  // namespace b200mp
