@@ -386,7 +386,12 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
 #pragma unroll 1
         for (; n < n_end; ++n) {
             double sdot[LOG ? 10 : 1], outs[LOG ? 18 : 1];
-            rk4_step<double, true, LOG, true, !LOG, TAB>(P0, P0.Dc, c, a.dt, y, ax, ay, sdot, outs, T);
+            // the DataLog needs state_dot and the 18 outputs (combined slips included) only for the steps it stores:
+            // those take the closed-form logging step, every other step of a logging launch the tabulated one
+            if (LOG && !(TAB && !(a.store_stride > 0 && until_store == 1)))
+                rk4_step<double, true, true, true, false, false>(P0, P0.Dc, c, a.dt, y, ax, ay, sdot, outs);
+            else
+                rk4_step<double, true, false, true, true, TAB>(P0, P0.Dc, c, a.dt, y, ax, ay, sdot, outs, T);
             if (a.store_stride > 0 && --until_store == 0) {
                 until_store = a.store_stride;
                 if (tp) {
@@ -522,7 +527,9 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     a.mu_table = ds.mu_table;
     a.mu_B2 = ds.mu_table_B2;
     const bool tab = ds.mu_table && ds.mu_table_B2 > 0.0 && friction_mode() == B200MP_FRICTION_AUTO;
-    if (g.log)
+    if (g.log && tab && g.store_stride > 1)   // logging launch that stores a subset of the steps
+        track_kernel<true, true><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
+    else if (g.log)
         track_kernel<true, false><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
     else if (tab)
         track_kernel<false, true><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
