@@ -72,7 +72,11 @@ collision_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, 
             cy[k] = __dadd_rn(y, __dmul_rn(cs.off[k], s));
         }
     }
-    double clr = INFINITY;
+    // CLEAR: min over obstacle points of fl(sqrt_rn(q) - r) equals fl(sqrt_rn(min q) - r) bit for bit (both roundings
+    // are monotone), so the running minimum is kept on q and ONE square root per circle is taken at the end
+    double qmin[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) qmin[k] = INFINITY;
     for (int m0 = 0; m0 < M; m0 += kObsTile) {
         const int m1 = min(kObsTile, M - m0);
         __syncthreads();
@@ -89,18 +93,24 @@ collision_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, 
                 const double dx = __dsub_rn(ob.x, cx[k]);
                 const double dy = __dsub_rn(ob.y, cy[k]);
                 const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                if (CLEAR) {
-                    const double d = __dsub_rn(__dsqrt_rn(q), cs.rad[k]);   // collision_checker.py:101-105
-                    hit |= d < 0.0;
-                    clr = fmin(clr, d);
-                } else {
+                if (CLEAR)
+                    qmin[k] = fmin(qmin[k], q);                             // NaN is skipped, as fmin(clr, d) did
+                else
                     hit |= q < cs.thr[k];
-                }
             }
+        }
+        if (CLEAR) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) hit |= qmin[k] < cs.thr[k];        // sqrt_rn(q) - r < 0  <=>  q < thr
         }
         if (hit) free_out[p] = 0;
     }
-    if (CLEAR && t < n_items) clear_pts[t] = clr;
+    if (CLEAR && t < n_items) {
+        double clr = INFINITY;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) clr = fmin(clr, __dsub_rn(__dsqrt_rn(qmin[k]), cs.rad[k]));   // collision_checker.py:101-105
+        clear_pts[t] = clr;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
