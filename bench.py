@@ -587,7 +587,7 @@ def secondary_metrics(eng, wl, np, torch):
     ev1.record()
     torch.cuda.synchronize()
     out["param_sweep_f32"] = {"value": B5 * N5 / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT, "ms": ev0.elapsed_time(ev1),
-                              "drift_report": "profiles/r01_fp32_drift_cfg5.json"}
+                              "drift_report": "profiles/r01_fp32_drift_cfg5.json", "path": "generic kernel; set-uniform blocks take the tabulated FP32 step"}
     return out
 
 

@@ -131,9 +131,14 @@ static cudaError_t upload_set_tables(DeviceState &ds, const B200mpVehicleParams 
     ds.set_tables = nullptr;
     ds.set_B2 = nullptr;
     ds.set_tables_n = 0;
+    if (ds.set_tables_f32) (void)cudaFree(ds.set_tables_f32);
+    ds.set_tables_f32 = nullptr;
     std::vector<double> tables((size_t)n_sets * kMuTableDoubles + 2), B2(n_sets, 0.0);
+    std::vector<float> tables32((size_t)n_sets * kMuTableFloats + 4);
     double *base = tables.data();
     if (reinterpret_cast<uintptr_t>(base) % 16) ++base;   // MuRow is 16-byte aligned
+    float *base32 = tables32.data();
+    while (reinterpret_cast<uintptr_t>(base32) % 16) ++base32;
     std::atomic<int> next(0);
     auto work = [&]() {
         for (int i = next.fetch_add(1); i < n_sets; i = next.fetch_add(1)) {
@@ -142,7 +147,8 @@ static cudaError_t upload_set_tables(DeviceState &ds, const B200mpVehicleParams 
             for (int w = 1; w < 4; ++w) uniform = uniform && h.B[w] == h.B[0] && h.C[w] == h.C[0];
             if (!(uniform && h.B[0] > 0.0 && h.C[0] > 0.0 && h.C[0] < 4.0)) continue;
             const double err = build_mu_table(h.B[0], h.C[0], 1.0, base + (size_t)i * kMuTableDoubles);
-            if (err < 1.0e-15) B2[i] = h.B[0] * h.B[0];
+            const double err32 = build_mu_table_f32(h.B[0], h.C[0], 1.0, base32 + (size_t)i * kMuTableFloats);
+            if (err < 1.0e-15 && err32 < 1.0e-6) B2[i] = h.B[0] * h.B[0];
         }
     };
     unsigned nt = std::thread::hardware_concurrency();
@@ -157,6 +163,9 @@ static cudaError_t upload_set_tables(DeviceState &ds, const B200mpVehicleParams 
     if (e == cudaSuccess)
         e = cudaMemcpy(ds.set_tables, base, sizeof(double) * (size_t)n_sets * kMuTableDoubles, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(ds.set_B2, B2.data(), sizeof(double) * n_sets, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ds.set_tables_f32, sizeof(float) * (size_t)n_sets * kMuTableFloats);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(ds.set_tables_f32, base32, sizeof(float) * (size_t)n_sets * kMuTableFloats, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) ds.set_tables_n = n_sets;
     return e;
 }
@@ -396,6 +405,7 @@ int b200mp_shutdown(void)
         if (ds.mu_table_f32) (void)cudaFree(ds.mu_table_f32);
         if (ds.set_tables) (void)cudaFree(ds.set_tables);
         if (ds.set_B2) (void)cudaFree(ds.set_B2);
+        if (ds.set_tables_f32) (void)cudaFree(ds.set_tables_f32);
         if (ds.sched_ring) {
             (void)cudaFree(ds.sched_ring);
             for (int i = 0; i < kSchedSlots; ++i) (void)cudaEventDestroy(ds.sched_event[i]);

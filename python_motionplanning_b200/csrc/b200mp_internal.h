@@ -39,6 +39,7 @@ struct DeviceState {
     // and B^2 per set (0 = no table: the set is evaluated in closed form).  Used by the generic kernels when all
     // rollouts of a CTA share one set (parameter sweeps, per-rollout mu_max).
     double *set_tables = nullptr;
+    float *set_tables_f32 = nullptr;   // FP32 twins [n_sets][kMuTableFloats]; a set has one iff set_B2 > 0 (both are built or neither)
     double *set_B2 = nullptr;
     int set_tables_n = 0;
     void *scratch = nullptr;

@@ -59,7 +59,7 @@ template <typename R> struct RolloutDev {
     R w_u, u_ref;
     const void *mu_table;     // friction table of set 0 in the precision of R (TAB kernels), B^2 beside it
     double mu_B2;
-    const double *set_tables; // [n_sets][kMuTableDoubles] D = 1 tables and [n_sets] B^2 (0 = none): GENERIC TAB kernels
+    const void *set_tables;   // [n_sets] D = 1 tables in the precision of R and [n_sets] B^2 (0 = none): GENERIC TAB kernels
     const double *set_B2;
 };
 
@@ -148,8 +148,8 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
             use_tab = uniform && b2 > 0.0;
             if (use_tab) {
                 if (cur != set0) {
-                    const double *src = a.set_tables + (size_t)set0 * kMuTableDoubles;
-                    for (int i = threadIdx.x; i < kMuTableDoubles; i += kRolloutBlock) s_mu[i] = src[i];
+                    const double *src = static_cast<const double *>(a.set_tables) + (size_t)set0 * kTabWords;
+                    for (int i = threadIdx.x; i < kTabWords; i += kRolloutBlock) s_mu[i] = src[i];
                     if (threadIdx.x == 0) s_cur_set = set0;
                 }
                 T.B2 = b2;
@@ -447,10 +447,10 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
     const bool tab = !generic && !aux && have_table && friction_mode() == B200MP_FRICTION_AUTO;
     a.mu_table = sizeof(R) == 8 ? (const void *)ds.mu_table : (const void *)ds.mu_table_f32;
     a.mu_B2 = ds.mu_table_B2;
-    a.set_tables = ds.set_tables;
+    a.set_tables = sizeof(R) == 8 ? (const void *)ds.set_tables : (const void *)ds.set_tables_f32;
     a.set_B2 = ds.set_B2;
     // per-set tables: generic FP64 launches whose blocks turn out to be set-uniform take the tabulated step
-    const bool tabg = sizeof(R) == 8 && generic && !aux && ds.set_tables && ds.set_tables_n == ds.n_sets &&
+    const bool tabg = generic && !aux && ds.set_tables && ds.set_tables_f32 && ds.set_tables_n == ds.n_sets &&
                       friction_mode() == B200MP_FRICTION_AUTO;
 #define B200MP_START2(REAR0, GENERIC, AUX, TAB, COST) \
     start_rollout<R>(rk4_rollout_kernel<R, REAR0, GENERIC, AUX, false, TAB, COST>, rk4_rollout_kernel<R, REAR0, GENERIC, AUX, true, TAB, COST>, device, st, a, P0)
@@ -460,7 +460,7 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
     ((AUX) || g.cost ? B200MP_START2(REAR0, GENERIC, AUX, TAB, true) : B200MP_START2(REAR0, GENERIC, AUX, TAB, (AUX)))
     if (aux)   // logging mode (state_dot + outputs): one generic instantiation per steer layout
         return rear0 ? B200MP_START(true, true, true, false) : B200MP_START(false, true, true, false);
-    if (generic && tabg) return rear0 ? B200MP_START(true, true, false, (sizeof(R) == 8)) : B200MP_START(false, true, false, (sizeof(R) == 8));
+    if (generic && tabg) return rear0 ? B200MP_START(true, true, false, true) : B200MP_START(false, true, false, true);
     if (generic) return rear0 ? B200MP_START(true, true, false, false) : B200MP_START(false, true, false, false);
     // per-step controls on the front-steer fast path (sampling MPC): software-pipelined control preparation
     if (rear0 && !generic && !aux && g.hold == 1 && g.torque_ch == 1) {
