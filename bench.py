@@ -537,6 +537,24 @@ def secondary_metrics(eng, wl, np, torch):
     out["rollout_f64_endstate_only"] = {"value": B * N_STEPS / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT,
                                         "ms": ev0.elapsed_time(ev1)}
     del s0, dl, tq
+    # config 1's inner call: the scalar drop-in VehicleModel.planar_model_RK4 (one vehicle, one step per call, host lists
+    # in and out, as drive.py:141-143 calls it) -- launch- and copy-latency bound by construction
+    import python_motionplanning_b200 as mp
+    vm = mp.VehicleModel(dt=DT, engine=eng)
+    pv = mp.VehicleParameters()
+    st1 = [20.0, 0.0, 0.0, 20.0 / pv.rw, 20.0 / pv.rw, 20.0 / pv.rw, 20.0 / pv.rw, 0.0, 0.0, 0.0]
+    axp = ayp = 0.0
+    for k in range(230):
+        if k == 30:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        r1 = vm.planar_model_RK4(st1, [50.0] * 4, [1.0] * 4, [0.01, 0.01, 0.0, 0.0], pv, axp, ayp)
+        st1, axp, ayp = list(r1[0]), r1[7], r1[8]
+    out["scalar_drop_in_planar_model_RK4"] = {"us_per_call": (time.perf_counter() - t0) / 200 * 1e6, "calls": 200,
+                                              "note": "one vehicle, one RK4 step per call through the reference's own method signature "
+                                                      "(H2D of 24 doubles, one launch, D2H of 40 doubles, stream sync); the literal "
+                                                      "Python reference needs ~1 ms per call (tests/golden/rollout_cfg2_sub.npz)"}
+    eng.set_params(pv)                     # D = mu_max = 1 on the four wheels, the set the headline runs with
     # config 4 (one GPU's view): 1,048,576 sampled control sequences x 100 steps from one start state, running
     # cost, lowest-index argmin; the controls are drawn on the device (Philox keyed by the global rollout index)
     cfg = wl.config4_mpc(B=1 << 20)
@@ -557,7 +575,6 @@ def secondary_metrics(eng, wl, np, torch):
     del dm, tm, r, s0m
     # config 5 (FP64 leg): 256 tyre-coefficient sets x 4,096 manoeuvres, per-rollout parameter sets (set-major), 100 steps
     sets, st5, dl5, tq5, ps5 = wl.config5_sweep()
-    import python_motionplanning_b200 as mp
     p5 = mp.VehicleParameters()
     for wname in ("FL", "FR", "RL", "RR"):
         setattr(p5, "B" + wname, sets[:, 0])
