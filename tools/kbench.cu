@@ -11,7 +11,7 @@ static double lcg(unsigned long long &s) { s = s * 6364136223846793005ULL + 1442
 
 int main(int argc, char **argv)
 {
-    const int B = argc > 1 ? atoi(argv[1]) : 65536, N = argc > 2 ? atoi(argv[2]) : 500, hold = 10;
+    const int B = argc > 1 ? atoi(argv[1]) : 65536, N = argc > 2 ? atoi(argv[2]) : 500, hold = getenv("KB_HOLD") ? atoi(getenv("KB_HOLD")) : 10;
     const int stride = argc > 3 ? atoi(argv[3]) : 1;
     if (argc > 5) b200mp_set_friction_mode(atoi(argv[5]));   // 1 = closed form
     B200mpVehicleParams p{};
