@@ -202,32 +202,32 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
             rowc.k[0] = rowc.k[1] = rowc.k[2] = rowc.k[3] = -1;
             int n = n_begin;
             auto step_body = [&](int nn) {   // one RK4 step + running cost + trajectory / log store
-                    R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
-                    if (TAB && GENERIC && !use_tab)
-                        rk4_step<R, REAR0, AUX, false, false, false>(P, D, c, a.dt, y, ax, ay, sdot, outs);
-                    else
-                        rk4_step<R, REAR0, AUX, !GENERIC, (kRolloutSpeculative && !GENERIC && !AUX) || TAB, TAB>(P, D, c, a.dt, y, ax, ay, sdot, outs, T,
-                                                                                                                  (TAB && kCacheAcrossSteps) ? &rowc : nullptr);
-                    if (COST && a.cost) {
-                        const size_t g = (size_t)(a.step0 + nn);
-                        const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;
-                        J = J + (ex * ex + ey * ey + a.w_u * (eu * eu));
+                R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
+                if (TAB && GENERIC && !use_tab)
+                    rk4_step<R, REAR0, AUX, false, false, false>(P, D, c, a.dt, y, ax, ay, sdot, outs);
+                else
+                    rk4_step<R, REAR0, AUX, !GENERIC, (kRolloutSpeculative && !GENERIC && !AUX) || TAB, TAB>(P, D, c, a.dt, y, ax, ay, sdot, outs, T,
+                                                                                                              (TAB && kCacheAcrossSteps) ? &rowc : nullptr);
+                if (COST && a.cost) {
+                    const size_t g = (size_t)(a.step0 + nn);
+                    const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;
+                    J = J + (ex * ex + ey * ey + a.w_u * (eu * eu));
+                }
+                if (a.store_stride > 0 && --until_store == 0) {
+                    until_store = a.store_stride;
+                    if (tp) {
+#pragma unroll
+                        for (int cidx = 0; cidx < 10; ++cidx) tp[cidx * B] = y[cidx];
+                        tp += 10 * B;
                     }
-                    if (a.store_stride > 0 && --until_store == 0) {
-                        until_store = a.store_stride;
-                        if (tp) {
+                    if (AUX && xp) {
 #pragma unroll
-                            for (int cidx = 0; cidx < 10; ++cidx) tp[cidx * B] = y[cidx];
-                            tp += 10 * B;
-                        }
-                        if (AUX && xp) {
+                        for (int cidx = 0; cidx < 10; ++cidx) xp[cidx * B] = sdot[cidx];
 #pragma unroll
-                            for (int cidx = 0; cidx < 10; ++cidx) xp[cidx * B] = sdot[cidx];
-#pragma unroll
-                            for (int cidx = 0; cidx < 18; ++cidx) xp[(10 + cidx) * B] = outs[cidx];
-                            xp += 28 * B;
-                        }
+                        for (int cidx = 0; cidx < 18; ++cidx) xp[(10 + cidx) * B] = outs[cidx];
+                        xp += 28 * B;
                     }
+                }
             };
             static_assert(!H1 || (REAR0 && !GENERIC && !AUX), "H1 is a variant of the front-steer fast path");
             if (H1) {
