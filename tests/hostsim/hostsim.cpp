@@ -9,8 +9,8 @@
 
 using namespace b200mp;
 
-static int g_use_table = 0;          // hostsim_set_table(1): FP64 no-log runs take the tabulated friction path
-static double g_table_err = 0.0;
+static int g_use_table = 0;          // hostsim_set_table(1): no-log runs take the tabulated friction path (FP64 and FP32)
+static double g_table_err = 0.0, g_table_err32 = 0.0;
 
 template <typename R, bool REAR0, bool AUX>
 static void run(int B, int n_steps, double dt, int hold, const double *state0, const double *delta, const double *torque,
@@ -26,13 +26,22 @@ static void run(int B, int n_steps, double dt, int hold, const double *state0, c
         ax = (R)state0[(size_t)10 * B + r];
         ay = (R)state0[(size_t)11 * B + r];
         WheelCtrl<R> c;
+        // tabulated friction as the generic device path uses it: the table of the rollout's tyre normalised to D = 1 (in the
+        // precision of R), the per-wheel D (parameter set or mu_max) scaling the normal load inside rk4_step
         alignas(16) static double table[kMuTableDoubles];
+        alignas(16) static float table32[kMuTableFloats];
+        static double key_B = -1.0, key_C = -1.0;
         MuTableView T;
-        T.c = table;
-        const bool tab = g_use_table && !AUX && sizeof(R) == 8 && !mu;
+        T.c = sizeof(R) == 8 ? (const void *)table : (const void *)table32;
+        const bool tab = g_use_table && !AUX;
         if (tab) {
             const HostParams &hp = params[param_set ? param_set[r] : 0];
-            g_table_err = build_mu_table(hp.B[0], hp.C[0], hp.D[0], table);
+            if (hp.B[0] != key_B || hp.C[0] != key_C) {
+                g_table_err = build_mu_table(hp.B[0], hp.C[0], 1.0, table);
+                g_table_err32 = build_mu_table_f32(hp.B[0], hp.C[0], 1.0, table32);
+                key_B = hp.B[0];
+                key_C = hp.C[0];
+            }
             T.B2 = hp.B[0] * hp.B[0];
         }
         for (int n = 0; n < n_steps; ++n) {
@@ -47,7 +56,7 @@ static void run(int B, int n_steps, double dt, int hold, const double *state0, c
             }
             R sdot[10], outs[18];
             if (tab)
-                rk4_step<R, REAR0, false, false, true, (sizeof(R) == 8)>(P, D, c, (R)dt, y, ax, ay, sdot, outs, T);
+                rk4_step<R, REAR0, false, false, true, true>(P, D, c, (R)dt, y, ax, ay, sdot, outs, T);
             else
                 rk4_step<R, REAR0, AUX, false, !AUX>(P, D, c, (R)dt, y, ax, ay, sdot, outs);   // !AUX: speculative form + checked fallback
             if (store_stride > 0 && (n + 1) % store_stride == 0) {
@@ -70,6 +79,8 @@ extern "C" double hostsim_set_table(int on)
     g_use_table = on;
     return g_table_err;
 }
+
+extern "C" double hostsim_table_err_f32(void) { return g_table_err32; }
 
 extern "C" void hostsim_rollout(int use_f32, int B, int n_steps, double dt, int hold, const double *state0,
                                 const double *delta, int dch, const double *torque, int tch, const double *mu,

@@ -99,5 +99,16 @@ def test_tabulated_friction_path_matches_oracle(hostsim):
         z[0], z[3:7] = 25.0, 25.0 / 0.308309813617345
         zt, _, zend = _run(hostsim, 0, z, np.zeros((1, 1, 1)), np.zeros((1, 1, 1)), par, 10, 10, 10)
         assert zend[0, 0] == 25.0 and np.all(zend[1:3, 0] == 0.0) and np.all(zend[3:7, 0] == z[3, 0]) and zend[9, 0] == 0.0
+        # per-wheel D (mu_max) and a parameter sweep with D != 1: the tables are normalised to D = 1, D scales the normal load
+        mu = np.random.default_rng(2).uniform(0.4, 1.1, (4, B))
+        refm = c_oracle.rollout(s0, d, t, par, 1e-4, N, hold=10, mu=mu, store_stride=50)
+        trajm, _, endm = _run(hostsim, 0, s0, d, t, par, N, 10, 50, mu=mu)
+        assert rel_err(trajm, refm["traj"]).max() < 1e-12
+        # the FP32 twin of the table: audited to a few FP32 ulps, trajectories inside the FP32 drift bound
+        sub = [np.ascontiguousarray(a[..., 16:]) for a in (s0, d, t)]        # without the rollouts sent beyond the table
+        traj32, _, end32 = _run(hostsim, 1, sub[0], sub[1], sub[2], par, N, 10, 50)
+        hostsim.hostsim_table_err_f32.restype = C.c_double
+        assert 0.0 < hostsim.hostsim_table_err_f32() < 1e-6
+        assert rel_err(end32[:10], ref["state_end"][:10, 16:]).max() < 2e-4
     finally:
         hostsim.hostsim_set_table(0)
