@@ -102,7 +102,8 @@ const char *b200mp_last_error(void);
 int b200mp_device_count(void);
 
 /* Upload n_sets parameter sets for `device` (synchronous; must not race with rollouts in flight on
- * that device).  Replaces constructing VehicleParameters (vehicle_model.py:17-61, drive.py:37). */
+ * that device) and build their friction tables (see b200mp_set_friction_mode; ~25 ms of host work per set, spread
+ * over the host threads).  Replaces constructing VehicleParameters (vehicle_model.py:17-61, drive.py:37). */
 int b200mp_set_params(int device, const B200mpVehicleParams *host_sets, int n_sets);
 
 /* Batched RK4 rollouts, one thread per rollout.  vehicle_model.py:427-445 looped as drive.py:141-143. */
@@ -147,12 +148,16 @@ int b200mp_collision_check_f64(int device, void *stream, int P, int n_pts, int n
                                const double *psin, const double *pyaw, int yaw_stride, int M, const double *obs,
                                unsigned char *free_out, double *min_clear);
 
-/* How the fast-path rollout / tracking kernels (FP64, one tyre triple, no logging, no per-rollout mu_max) evaluate the
- * combined-slip friction D sin(C atan(B s)) / s (vehicle_model.py:296-348).  AUTO (default): from a table of
- * degree-12 polynomials in 1 + (B s)^2 built on the host by b200mp_set_params (long double, audited to <= 3e-16
- * relative), no square root / reciprocal / atan / sin in the kernel; slips beyond the table and non-finite values
- * repeat the step on the closed form.  CLOSED_FORM: always the sqrt / atan / sin sequence (A/B checks).  Both are
- * within the 1e-9 parity contract with ~1e-13 to spare.  Process-wide; returns the previous mode, or B200MP_E_ARG. */
+/* How the rollout / tracking kernels evaluate the combined-slip friction D sin(C atan(B s)) / s
+ * (vehicle_model.py:296-348).  AUTO (default): from tables of piecewise polynomials in 1 + (B s)^2 built on the host by
+ * b200mp_set_params (long double fits, audited: FP64 <= 4e-16 relative with degree 6 on 64 intervals per binade, FP32 a
+ * few ulps with cubics on 32), no square root / reciprocal / atan / sin in the kernel; slips beyond the table and
+ * non-finite values repeat the step on the closed form.  Set 0 has a table with D folded in (launches without param_set
+ * and mu); every set whose four tyres share (B, C) has a D = 1 table that the generic kernels use for blocks of 64
+ * rollouts sharing one set, with D (or mu_max) scaling the normal load; a set that fails the audit (e.g. C > 2, where
+ * the function changes sign) and logging steps are evaluated in closed form.  CLOSED_FORM: always the sqrt / atan / sin
+ * sequence (A/B checks).  Both are within the 1e-9 parity contract with ~1e-13 to spare.  Process-wide; returns the
+ * previous mode, or B200MP_E_ARG. */
 #define B200MP_FRICTION_AUTO 0
 #define B200MP_FRICTION_CLOSED_FORM 1
 int b200mp_set_friction_mode(int mode);
