@@ -287,6 +287,20 @@ def run_gpu(args):
     e2e_value = world * units_per_step * e2e_steps / float(t_e.item())
     h2d = int(hs.numel() + hd.numel() + ht.numel()) * 8
     d2h = int(traj_host.numel()) * 8
+    # supplementary: the same host-buffer call when only the final states are read back (no trajectory D2H); the
+    # controls are uploaded chunk by chunk behind the kernels
+    end_host = torch.empty(12, B, dtype=torch.float64).pin_memory()
+    for _ in range(2):
+        eng.rollout_endstate_to_host(hs, hd, ht, DT, N_STEPS, HOLD, end_host, chunk_steps=100)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.rollout_endstate_to_host(hs, hd, ht, DT, N_STEPS, HOLD, end_host, chunk_steps=100)
+    barrier()
+    t_e2 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2, op=dist.ReduceOp.MAX)
+    e2e_end_value = world * units_per_step * e2e_steps / float(t_e2.item())
 
     # ---- config 4 as BASELINE.json states it: 1,048,576 control sequences x 100 steps SHARDED over the ranks (strong
     # scaling), each plan = sample -> rollout with cost -> local argmin -> one all-gather of per-rank
@@ -364,7 +378,11 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "n_steps": N_STEPS, "parallelism": f"dp{world} (independent rollouts, no data-path collective)",
                        "l2": "256 MiB buffer written between timed iterations (untimed); each step also streams 2.62 GB of output through the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "Engine.rollout_to_host: pinned host inputs -> H2D, 10 time-chunks of 50 steps, D2H of the full trajectory overlapped on a copy stream"},
+                    "api": "Engine.rollout_to_host: pinned host inputs -> H2D, 10 time-chunks of 50 steps, D2H of the full trajectory overlapped on a copy stream",
+                    "bound": "PCIe: 2.62 GB of trajectory per step at ~55 GB/s",
+                    "endstate_only": {"value": e2e_end_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12 * B * 8,
+                                      "api": "Engine.rollout_endstate_to_host: same host inputs, controls uploaded in 5 time-chunks behind "
+                                             "the kernels, only the [12, B] end states read back"}},
             "gpu_launches": args.steps * world,
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"], "how": clocks.get("how"), "power_w_max": clocks.get("power_w_max"),

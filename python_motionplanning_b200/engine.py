@@ -247,6 +247,45 @@ class Engine:
         compute.synchronize()
         return s
 
+    def rollout_endstate_to_host(self, state0_host: torch.Tensor, delta_host: torch.Tensor, torque_host: torch.Tensor,
+                                 dt: float, n_steps: int, hold: int, state_end_host: torch.Tensor, chunk_steps: int = 100,
+                                 dtype: str = "f64"):
+        """End-to-end rollout with HOST buffers when only the final states are wanted (no trajectory readback):
+        the controls are uploaded in time-chunks on the copy stream while the previous chunk computes, so the H2D of
+        the inputs (the only sizeable transfer left) hides behind the kernels.  ``*_host`` are pinned CPU tensors;
+        ``state_end_host`` is ``[12, B]``.  Returns after the end states have landed in ``state_end_host``."""
+        if chunk_steps % hold != 0 and n_steps > chunk_steps:
+            raise ValueError("chunk_steps must be a multiple of hold")
+        compute = torch.cuda.current_stream(self.tdev)
+        copy = self._copy_stream()
+        seg_per_chunk = max(chunk_steps // hold, 1)
+        s = state0_host.to(self.tdev, non_blocking=True)
+        n_seg = delta_host.shape[0]
+        dl = torch.empty(delta_host.shape, dtype=delta_host.dtype, device=self.tdev)
+        tq = torch.empty(torque_host.shape, dtype=torque_host.dtype, device=self.tdev)
+        start = torch.cuda.Event()
+        start.record(compute)
+        copy.wait_event(start)
+        ready = []
+        with torch.cuda.stream(copy):
+            for s0 in range(0, n_seg, seg_per_chunk):
+                s1 = min(n_seg, s0 + seg_per_chunk)
+                dl[s0:s1].copy_(delta_host[s0:s1], non_blocking=True)
+                tq[s0:s1].copy_(torque_host[s0:s1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                ready.append(ev)
+        n0, k = 0, 0
+        while n0 < n_steps:
+            nc = min(chunk_steps, n_steps - n0)
+            compute.wait_event(ready[min(k, len(ready) - 1)])
+            s = self.rollout(s, dl, tq, dt, nc, hold=hold, store_stride=0, dtype=dtype, step0=n0).state_end
+            n0 += nc
+            k += 1
+        state_end_host.copy_(s, non_blocking=True)
+        compute.synchronize()
+        return s
+
     def _copy_stream(self):
         if not hasattr(self, "_cstream"):
             self._cstream = torch.cuda.Stream(self.tdev)

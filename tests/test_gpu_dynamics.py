@@ -260,6 +260,12 @@ def test_rollout_to_host_pipeline(engine):
     out = torch.empty(N, 10, B, dtype=torch.float64).pin_memory()
     end = engine.rollout_to_host(hs, hd, ht, DT, N, wl.HOLD, out, chunk_steps=50)
     assert torch.equal(out, dev.traj.cpu()) and torch.equal(end, dev.state_end)
+    # end states only: controls uploaded chunk by chunk behind the kernels, no trajectory readback
+    end_host = torch.empty(12, B, dtype=torch.float64).pin_memory()
+    for chunk in (50, 80, 200):
+        end_host.zero_()
+        engine.rollout_endstate_to_host(hs, hd, ht, DT, N, wl.HOLD, end_host, chunk_steps=chunk)
+        assert torch.equal(end_host, dev.state_end.cpu())
 
 
 def test_abi_error_behaviour(engine):
