@@ -149,7 +149,8 @@ class Engine:
     def rollout(self, state0, delta, torque, dt: float, n_steps: int, hold: int = 1, mu=None, param_set=None,
                 store_stride: int = 0, want_aux: bool = False, dtype: str = "f64", ctrl_broadcast: bool = False,
                 cost_ref=None, cost_in=None, w_u: float = 0.1, u_ref: float = 25.0, step0: int = 0,
-                traj_out: Optional[torch.Tensor] = None, state_out: Optional[torch.Tensor] = None) -> RolloutResult:
+                traj_out: Optional[torch.Tensor] = None, state_out: Optional[torch.Tensor] = None,
+                aux_out: Optional[torch.Tensor] = None) -> RolloutResult:
         """Batched open-loop RK4 rollouts (``b200mp_rk4_rollout_f64/_f32``), asynchronous on the current stream.
 
         state0 ``[12,B]`` (or ``[10,B]``: ax_prev = ay_prev = 0, drive.py:60-61); delta ``[n_seg,1|4,B]``;
@@ -174,11 +175,14 @@ class Engine:
         n_out = n_steps // store_stride if store_stride else 0
         traj = aux = None
         if n_out:
-            traj = traj_out if traj_out is not None else self.empty(n_out, 10, B, dtype=td)
-            if traj.shape != (n_out, 10, B) or traj.dtype != td or not traj.is_contiguous():
-                raise ValueError("traj_out has the wrong shape/dtype")
+            if traj_out is not None or not (want_aux and aux_out is not None):
+                traj = traj_out if traj_out is not None else self.empty(n_out, 10, B, dtype=td)
+                if traj.shape != (n_out, 10, B) or traj.dtype != td or not traj.is_contiguous():
+                    raise ValueError("traj_out has the wrong shape/dtype")
             if want_aux:
-                aux = self.empty(n_out, 28, B, dtype=td)
+                aux = aux_out if aux_out is not None else self.empty(n_out, 28, B, dtype=td)
+                if aux.shape != (n_out, 28, B) or aux.dtype != td or not aux.is_contiguous():
+                    raise ValueError("aux_out has the wrong shape/dtype")
         end = state_out if state_out is not None else self.empty(12, B, dtype=td)
         mu_t = None if mu is None else self.dev(mu, td)
         ps_t = None if param_set is None else self.dev(param_set, torch.int32)
@@ -298,15 +302,18 @@ class Engine:
             self._slab_key = key
         return self._slab
 
-    def planar_model_batch(self, state, torque, mu, delta, ax_prev, ay_prev, param_set=None):
-        """Batched ``VehicleModel.planar_model``: returns ``(state_dot[10,B], misc[6,B], outputs[18,B])``."""
+    def planar_model_batch(self, state, torque, mu, delta, ax_prev, ay_prev, param_set=None, axay=None, out=None):
+        """Batched ``VehicleModel.planar_model``: returns ``(state_dot[10,B], misc[6,B], outputs[18,B])``.
+        ``axay`` (a ready ``[2,B]`` device tensor, instead of ``ax_prev, ay_prev``) and ``out`` (three preallocated
+        device tensors) let a caller in a latency-bound loop skip the staging work."""
         st = self.dev(state)
         B = st.shape[1]
         tq, dl = self.dev(torque), self.dev(delta)
         mu_t = None if mu is None else self.dev(mu)
-        axay = torch.stack([self.dev(ax_prev).reshape(B), self.dev(ay_prev).reshape(B)]).contiguous()
+        if axay is None:
+            axay = torch.stack([self.dev(ax_prev).reshape(B), self.dev(ay_prev).reshape(B)]).contiguous()
         ps = None if param_set is None else self.dev(param_set, torch.int32)
-        sd, misc, out = self.empty(10, B), self.empty(6, B), self.empty(18, B)
+        sd, misc, out = out if out is not None else (self.empty(10, B), self.empty(6, B), self.empty(18, B))
         check(self.lib.b200mp_planar_model_f64(self.device, self._stream(), B, self._ptr(st), self._ptr(tq),
                                                self._ptr(mu_t), self._ptr(dl), self._ptr(axay), self._ptr(ps),
                                                self._ptr(sd), self._ptr(misc), self._ptr(out)), "b200mp_planar_model_f64")

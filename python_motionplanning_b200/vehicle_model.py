@@ -112,11 +112,10 @@ class VehicleModel:
         """One right-hand-side evaluation -> ``[state_dot, vx, vy, ax, ay, outputs, axc, ayc]`` (:425)."""
         eng = self._load_inputs(state, tire_torques, mu_max, delta, p, ax_prev, ay_prev)
         d = self._d_in
-        sd, misc, out = eng.planar_model_batch(d[0:10].view(10, 1), d[12:16].view(4, 1), d[16:20].view(4, 1),
-                                               d[20:24].view(4, 1), d[10:11], d[11:12])
-        self._d_out[0:10].copy_(sd.view(-1))
-        self._d_out[10:16].copy_(misc.view(-1))
-        self._d_out[16:34].copy_(out.view(-1))
+        # the three results land directly in the staging buffer ([ax_prev, ay_prev] sit side by side in the input one)
+        o = self._d_out
+        eng.planar_model_batch(d[0:10].view(10, 1), d[12:16].view(4, 1), d[16:20].view(4, 1), d[20:24].view(4, 1), None, None,
+                               axay=d[10:12].view(2, 1), out=(o[0:10].view(10, 1), o[10:16].view(6, 1), o[16:34].view(18, 1)))
         self._h_out.copy_(self._d_out, non_blocking=True)
         torch.cuda.current_stream(eng.tdev).synchronize()
         o = self._np_out
@@ -128,9 +127,10 @@ class VehicleModel:
         ``[state_update, x, y, yaw, U, state_dot, outputs, axc, ayc]`` (:445)."""
         eng = self._load_inputs(state, tire_torques, mu_max, delta, p, ax_prev, ay_prev)
         d = self._d_in
-        res = eng.rollout(d[0:12].view(12, 1), d[20:24].view(1, 4, 1), d[12:16].view(1, 4, 1), self.dt, 1, hold=1,
-                          mu=d[16:20].view(4, 1), store_stride=1, want_aux=True, state_out=self._d_out[0:12].view(12, 1))
-        self._d_out[12:40].copy_(res.aux.view(-1))
+        # state_end and the 28 logged outputs land directly in the staging buffer: one launch, no device-side copies
+        eng.rollout(d[0:12].view(12, 1), d[20:24].view(1, 4, 1), d[12:16].view(1, 4, 1), self.dt, 1, hold=1,
+                    mu=d[16:20].view(4, 1), store_stride=1, want_aux=True, state_out=self._d_out[0:12].view(12, 1),
+                    aux_out=self._d_out[12:40].view(1, 28, 1))
         self._h_out.copy_(self._d_out, non_blocking=True)
         torch.cuda.current_stream(eng.tdev).synchronize()
         o = self._np_out
