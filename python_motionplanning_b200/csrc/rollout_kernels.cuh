@@ -203,11 +203,18 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
             int n = n_begin;
             auto step_body = [&](int nn) {   // one RK4 step + running cost + trajectory / log store
                 R sdot[AUX ? 10 : 1], outs[AUX ? 18 : 1];
-                if (TAB && GENERIC && !use_tab)
-                    rk4_step<R, REAR0, AUX, false, false, false>(P, D, c, a.dt, y, ax, ay, sdot, outs);
-                else
+                if constexpr (TAB && GENERIC) {
+                    // a logging launch needs state_dot and the 18 outputs (combined slips included) only on the steps it
+                    // stores: those take the closed-form logging step, every other step the tabulated one
+                    const bool log_step = AUX && a.store_stride > 0 && until_store == 1;
+                    if (use_tab && !log_step)
+                        rk4_step<R, REAR0, false, false, true, true>(P, D, c, a.dt, y, ax, ay, sdot, outs, T);
+                    else
+                        rk4_step<R, REAR0, AUX, false, false, false>(P, D, c, a.dt, y, ax, ay, sdot, outs);
+                } else {
                     rk4_step<R, REAR0, AUX, !GENERIC, (kRolloutSpeculative && !GENERIC && !AUX) || TAB, TAB>(P, D, c, a.dt, y, ax, ay, sdot, outs, T,
                                                                                                               (TAB && kCacheAcrossSteps) ? &rowc : nullptr);
+                }
                 if (COST && a.cost) {
                     const size_t g = (size_t)(a.step0 + nn);
                     const R ex = y[8] - a.cost_ref[2 * g], ey = y[9] - a.cost_ref[2 * g + 1], eu = y[0] - a.u_ref;
@@ -450,14 +457,18 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
     a.set_tables = sizeof(R) == 8 ? (const void *)ds.set_tables : (const void *)ds.set_tables_f32;
     a.set_B2 = ds.set_B2;
     // per-set tables: generic FP64 launches whose blocks turn out to be set-uniform take the tabulated step
-    const bool tabg = generic && !aux && ds.set_tables && ds.set_tables_f32 && ds.set_tables_n == ds.n_sets &&
-                      friction_mode() == B200MP_FRICTION_AUTO;
+    const bool set_tables_ok = ds.set_tables && ds.set_tables_f32 && ds.set_tables_n == ds.n_sets &&
+                               friction_mode() == B200MP_FRICTION_AUTO;
+    const bool tabg = generic && !aux && set_tables_ok;
+    // FP64 logging launches that store a subset of the steps: tabulated step between the stored ones
+    const bool tab_aux = aux && sizeof(R) == 8 && set_tables_ok && g.store_stride > 1;
 #define B200MP_START2(REAR0, GENERIC, AUX, TAB, COST) \
     start_rollout<R>(rk4_rollout_kernel<R, REAR0, GENERIC, AUX, false, TAB, COST>, rk4_rollout_kernel<R, REAR0, GENERIC, AUX, true, TAB, COST>, device, st, a, P0)
 #define B200MP_START_H1(TAB, COST) \
     start_rollout<R>(rk4_rollout_kernel<R, true, false, false, false, TAB, COST, true>, rk4_rollout_kernel<R, true, false, false, true, TAB, COST, true>, device, st, a, P0)
 #define B200MP_START(REAR0, GENERIC, AUX, TAB) \
     ((AUX) || g.cost ? B200MP_START2(REAR0, GENERIC, AUX, TAB, true) : B200MP_START2(REAR0, GENERIC, AUX, TAB, (AUX)))
+    if (aux && tab_aux) return rear0 ? B200MP_START(true, true, true, (sizeof(R) == 8)) : B200MP_START(false, true, true, (sizeof(R) == 8));
     if (aux)   // logging mode (state_dot + outputs): one generic instantiation per steer layout
         return rear0 ? B200MP_START(true, true, true, false) : B200MP_START(false, true, true, false);
     if (generic && tabg) return rear0 ? B200MP_START(true, true, false, true) : B200MP_START(false, true, false, true);

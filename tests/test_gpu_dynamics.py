@@ -337,3 +337,21 @@ def test_per_step_controls_pipeline_vs_c_oracle(engine):
         b = engine.rollout(a.state_end, d, t, DT, N - n1, hold=1, store_stride=1, step0=n1)
         assert torch.equal(torch.cat([a.traj, b.traj]), got.traj)
         assert torch.equal(b.state_end, got.state_end)
+
+
+def test_logging_rollout_with_stride_vs_c_oracle(engine):
+    """want_aux with store_stride > 1 (the open-loop DataLog): the kernel takes the tabulated step between the stored
+    steps and the closed-form logging step on them; trajectory, state_dot and the 18 outputs against the C oracle,
+    front-steer and 4-channel layouts, and the assembled 45-column rows."""
+    B, N, stride = 1000, 120, 10
+    s0, d, t = wl.config2_rollouts(B=B, n_steps=N)
+    engine.set_params(_params())
+    ref = c_oracle.rollout(s0, d, t, _c_params(), DT, N, hold=wl.HOLD, store_stride=stride, want_aux=True)
+    got = engine.rollout(s0, d, t, DT, N, hold=wl.HOLD, store_stride=stride, want_aux=True)
+    assert rel_err(got.traj.cpu().numpy(), ref["traj"]).max() < REL_TOL_F64
+    assert rel_err(got.aux.cpu().numpy(), ref["aux"]).max() < REL_TOL_F64
+    assert rel_err(got.state_end.cpu().numpy(), ref["state_end"]).max() < REL_TOL_F64
+    z = np.zeros_like(d)
+    d4, t4 = np.concatenate([d, d, z, z], axis=1), np.repeat(t, 4, axis=1)
+    got4 = engine.rollout(s0, d4, t4, DT, N, hold=wl.HOLD, store_stride=stride, want_aux=True)
+    assert rel_err(got4.aux.cpu().numpy(), ref["aux"]).max() < REL_TOL_F64
