@@ -319,6 +319,160 @@ collision_filter_kernel(int n_items, int n_pts, const __grid_constant__ CircleSp
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Exact minimum clearance with an FP32 screen (CLEAR mode of K2 in the AUTO / SCREEN arithmetic).  The result is
+// min over obstacle points of fl(sqrt_rn(q64) - r) = fl(sqrt_rn(min q64) - r) per circle, so only the exact minimum of
+// q64 is needed.  Pass A sweeps all obstacle tiles in packed FP32 and keeps min q32 per circle; with the error model of
+// the screen above, |d64 - sqrt(q32)(1 +- 4u)| <= E0 for every point, the exact minimiser o* satisfies
+//     sqrt(q32(o*)) <= (d64(o*) + E0)/(1 - 4u) <= (d64(o_A) + E0)/(1 - 4u) <= (sqrt(min q32)(1 + 4u) + 2 E0)/(1 - 4u) =: sqrt(T),
+// so pass B repeats the FP32 sweep and evaluates q64 exactly only for the points with q32 <= T (the minimiser, its ties
+// and a few neighbours within ~1e-5 m): two FP32 sweeps instead of one FP64 sweep.  Where the screen is not sharp
+// (non-finite or huge coordinates) T = +inf and every point is evaluated exactly, as in collision_kernel<NC, true>;
+// NaN points are skipped by fmin in both, so the doubles returned are identical for every input.
+template <int NC>
+__global__ void __launch_bounds__(kColBlock)
+clearance_screen_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, const double *__restrict__ px,
+                        const double *__restrict__ py, const double *__restrict__ pcos, const double *__restrict__ psin,
+                        const double *__restrict__ pyaw, int yaw_stride, int M, const double2 *__restrict__ obs,
+                        unsigned char *free_out, double *__restrict__ clear_pts)
+{
+    __shared__ __align__(16) float2 tile[kFTile];
+    __shared__ int s_amax;
+    const int t = blockIdx.x * kColBlock + threadIdx.x;
+    const bool active = t < n_items;
+    const int p = active ? t / n_pts : 0;
+    const double2 org = obs[0];
+    if (threadIdx.x == 0) s_amax = 0;
+
+    double cx[NC], cy[NC], ac = 0.0;
+    unsigned long long ncx[NC], ncy[NC];
+    bool bad = false;
+    {
+        double x = 0.0, y = 0.0, c = 1.0, s = 0.0;
+        if (active) {
+            x = px[t];
+            y = py[t];
+            if (pcos) {
+                c = pcos[t];
+                s = psin[t];
+            } else {
+                sincos(pyaw[(size_t)p * yaw_stride + (t - p * n_pts)], &s, &c);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            cx[k] = __dadd_rn(x, __dmul_rn(cs.off[k], c));
+            cy[k] = __dadd_rn(y, __dmul_rn(cs.off[k], s));
+            const double rx = cx[k] - org.x, ry = cy[k] - org.y;
+            const float fx = (float)rx, fy = (float)ry;
+            ncx[k] = pack2(-fx, -fx);
+            ncy[k] = pack2(-fy, -fy);
+            bad |= !(fabs(rx) <= 1.0e30) | !(fabs(ry) <= 1.0e30);   // NaN / Inf / beyond FP32 range
+            ac = fmax(ac, fmax(fabs(rx), fabs(ry)));
+        }
+    }
+    const float4 *tile4 = reinterpret_cast<const float4 *>(tile);
+    float amax = 0.0f;
+    // stages obstacle tile m0 as FP32 pairs (xa, xb, ya, yb) relative to the origin; padding points are at infinity
+    auto stage = [&](int m0, int m1, int m1pad) {
+        __syncthreads();
+        float *tf = reinterpret_cast<float *>(tile);
+        for (int i = threadIdx.x; i < m1pad; i += kColBlock) {
+            float2 v = make_float2(INFINITY, INFINITY);
+            if (i < m1) {
+                const double2 o = obs[m0 + i];
+                v.x = (float)(o.x - org.x);
+                v.y = (float)(o.y - org.y);
+                amax = fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y)));
+            }
+            tf[(i >> 1) * 4 + (i & 1)] = v.x;
+            tf[(i >> 1) * 4 + 2 + (i & 1)] = v.y;
+        }
+        __syncthreads();
+    };
+
+    // ---- pass A: min q32 per circle over all obstacle points
+    float mn[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) mn[k] = INFINITY;
+    for (int m0 = 0; m0 < M; m0 += kFTile) {
+        const int m1 = min(kFTile, M - m0), m1pad = (m1 + 7) & ~7;
+        stage(m0, m1, m1pad);
+        if (!active) continue;
+#pragma unroll 2
+        for (int o = 0; o < m1pad / 2; ++o) {
+            const float4 ob = tile4[o];
+            const unsigned long long X = pack2(ob.x, ob.y), Y = pack2(ob.z, ob.w);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                const unsigned long long dx = add2(X, ncx[k]), dy = add2(Y, ncy[k]);
+                const unsigned long long q = fma2(dy, dy, mul2(dx, dx));
+                mn[k] = fminf(mn[k], fminf(lo2(q), hi2(q)));
+            }
+        }
+    }
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, w));
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_amax, __float_as_int(amax));   // non-negative floats order as ints
+    __syncthreads();
+
+    // ---- candidate thresholds
+    float T[NC];
+    {
+        const double u = 5.9604644775390625e-08;   // 2^-24
+        const double e0 = 2.0 * u * ((double)__int_as_float(s_amax) + ac) * 1.000001 + 1.0e-18;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const double b = (sqrt((double)mn[k]) * (1.0 + 4.0 * u) + 2.0 * e0) / (1.0 - 4.0 * u);
+            const bool sharp = !bad && e0 < 1.0e30 && mn[k] < INFINITY;
+            T[k] = sharp ? __double2float_ru(b * b * 1.000001) : INFINITY;
+        }
+    }
+
+    // ---- pass B: exact q64 for the candidates only
+    double qmin[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) qmin[k] = INFINITY;
+    for (int m0 = 0; m0 < M; m0 += kFTile) {
+        const int m1 = min(kFTile, M - m0), m1pad = (m1 + 7) & ~7;
+        stage(m0, m1, m1pad);
+        if (!active) continue;
+#pragma unroll 2
+        for (int o = 0; o < m1pad / 2; ++o) {
+            const float4 ob = tile4[o];
+            const unsigned long long X = pack2(ob.x, ob.y), Y = pack2(ob.z, ob.w);
+            bool cand = false;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                const unsigned long long dx = add2(X, ncx[k]), dy = add2(Y, ncy[k]);
+                const unsigned long long q = fma2(dy, dy, mul2(dx, dx));
+                cand |= !(fminf(lo2(q), hi2(q)) > T[k]);   // NaN counts as a candidate (it drops out in fmin below)
+            }
+            if (cand) {
+                for (int i = 2 * o; i < 2 * o + 2 && i < m1; ++i) {
+                    const double2 e = obs[m0 + i];
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        const double dx = __dsub_rn(e.x, cx[k]);
+                        const double dy = __dsub_rn(e.y, cy[k]);
+                        qmin[k] = fmin(qmin[k], __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                    }
+                }
+            }
+        }
+    }
+    if (!active) return;
+    bool hit = false;
+    double clr = INFINITY;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        hit |= qmin[k] < cs.thr[k];                                              // sqrt_rn(q) - r < 0  <=>  q < thr
+        clr = fmin(clr, __dsub_rn(__dsqrt_rn(qmin[k]), cs.rad[k]));             // collision_checker.py:101-105
+    }
+    if (hit) free_out[p] = 0;
+    clear_pts[t] = clr;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K2 broad phase: the obstacle set of a planner is a handful of outlines (the reference samples boxes every
 // 0.2 m, env.py:93-127), i.e. consecutive obstacle points are spatially coherent.  A prepare kernel shifts the
 // points to the common origin in FP32 once per launch (instead of once per CTA and tile) and records the bounding
@@ -528,8 +682,12 @@ static int launch_collision_nc(int device, cudaStream_t st, int P, int n_pts, co
         void *scratch = nullptr;
         int rc = ensure_scratch(device, sizeof(double) * (size_t)items, &scratch);
         if (rc) return rc;
-        collision_kernel<NC, true><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
-                                                              M, (const double2 *)obs, free_out, (double *)scratch);
+        if (collision_mode() == B200MP_COLLISION_FP64_ONLY)
+            collision_kernel<NC, true><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
+                                                                  M, (const double2 *)obs, free_out, (double *)scratch);
+        else
+            clearance_screen_kernel<NC><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
+                                                                   M, (const double2 *)obs, free_out, (double *)scratch);
         B200MP_CUDA(cudaGetLastError());
         clearance_reduce_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, n_pts, (const double *)scratch, min_clear);
     } else if (collision_mode() == B200MP_COLLISION_FP64_ONLY) {

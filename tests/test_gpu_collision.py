@@ -193,6 +193,10 @@ def test_collision_filter_adversarial_bands(engine, scale_shift):
     got = _np(engine.collision_check_batch(px, py, pyaw, obs, off, rad)).astype(bool)
     assert np.array_equal(got, ref)
     assert 0 < ref.sum() < P                       # the case exercises both verdicts
+    # exact minimum clearance (FP32 screen for the candidate set + exact FP64 on the candidates): the same doubles
+    ref2, clr_ref, _ = c_oracle.collision_check(px, py, pyaw, obs, off, rad, want_clearance=True)
+    free2, clr = engine.collision_check_batch(px, py, pyaw, obs, off, rad, want_clearance=True)
+    assert np.array_equal(_np(free2).astype(bool), ref2) and np.array_equal(_np(clr), clr_ref)
     # one path at a time as well (different tile / origin per call)
     for p in range(0, 32):
         ref1, _, _ = c_oracle.collision_check(px[p:p + 1], py[p:p + 1], pyaw[p:p + 1], obs, off, rad)
@@ -211,6 +215,12 @@ def test_collision_filter_exceptional_values(engine):
         ref, _, _ = c_oracle.collision_check(px, py, pyaw, obs, off, rad)
         got = _np(engine.collision_check_batch(px, py, pyaw, obs, off, rad)).astype(bool)
         assert np.array_equal(got, ref), f"{what}: {int((got != ref).sum())} flags differ"
+        # min-clearance: the screened kernel returns the doubles of the all-FP64 kernel, bit for bit, whatever the input
+        f1, c1 = engine.collision_check_batch(px, py, pyaw, obs, off, rad, want_clearance=True)
+        prev = engine.set_collision_mode("fp64")
+        f0, c0 = engine.collision_check_batch(px, py, pyaw, obs, off, rad, want_clearance=True)
+        engine.set_collision_mode(prev)
+        assert torch.equal(f1, f0) and torch.equal(c1.view(torch.int64), c0.view(torch.int64)), f"{what}: clearance differs"
         return ref
 
     base = both(px, py, obs)
