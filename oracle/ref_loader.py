@@ -1,7 +1,8 @@
 """Import the UNMODIFIED reference (earasteh/Python-Motionplanning) for oracle pinning.
 
-TEST INFRASTRUCTURE.  Works only where ``/root/reference`` exists (the build container);
-the GPU box has no reference, so nothing that runs there may call :func:`load`.
+TEST INFRASTRUCTURE.  ``/root/reference`` exists only in the build container; on the GPU box the loader
+falls back to the verbatim copy that ``baseline/stage_reference.py`` staged under ``baseline/_ref/``
+(git-ignored, shipped with the snapshot).  Nothing at run time reads ``/root/reference`` on the box.
 
 The reference does not import as-is in this image:
   * ``libs/vehicle_model/vehicle_model.py:7`` and ``libs/utils/env.py:8`` import
@@ -19,11 +20,28 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("B200MP_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _has_reference(root: str) -> bool:
+    return os.path.isfile(os.path.join(root, "libs", "vehicle_model", "vehicle_model.py"))
+
+
+def _pick_root() -> str:
+    env = os.environ.get("B200MP_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if _has_reference(cand):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "libs", "vehicle_model", "vehicle_model.py"))
+    return _has_reference(REFERENCE_ROOT)
 
 
 def _install_shims() -> None:
@@ -53,7 +71,7 @@ class Reference(types.SimpleNamespace):
 def load(quiet_terminal: bool = True) -> Reference:
     if not available():
         raise RuntimeError(
-            f"reference not found under {REFERENCE_ROOT}; it exists only in the build container")
+            f"reference not found under {REFERENCE_ROOT} (nor staged under baseline/_ref: run baseline/stage_reference.py)")
     _install_shims()
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)

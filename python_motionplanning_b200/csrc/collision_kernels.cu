@@ -45,6 +45,57 @@ static double sqrt_threshold(double r)
     return q;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Exact verdicts from yaws (no host trigonometry on the bulk of the data).  The reference evaluates cos / sin of
+// every path yaw with numpy (collision_checker.py:88-89); an obstacle point is inside a circle iff
+// sqrt_rn(q64) < r with q64 computed from centres that carry numpy's roundings.  The kernels below evaluate the yaws
+// with the CUDA library sincos instead and PROVE each verdict against any host trigonometry within kTrigTau of the
+// exact value (numpy measures <= 0.52 ulp here, CUDA documents <= 2 ulp; tau = 2^-44 is ~500 ulp):
+//   |c_host - c_dev| <= tau  =>  host and device centres differ by at most
+//       ec = 2 |off| (tau + 2^-50) + 2^-51 (|cx| + |cy|)            (two products, two sums, both roundings each)
+//   and with d = true distance, sqrt_rn(q64) = d (1 +- 2^-51) on either side, so
+//       q64_dev <  LO64 = ((r (1 - 2^-50) - ec) / (1 + 2^-51))^2 (rounded down)  =>  the host's test collides
+//       q64_dev >= HI64 = ((r (1 + 2^-50) + ec) / (1 - 2^-51))^2 (rounded up)    =>  the host's test is free.
+// The FP32 screen's band (1e-5 m wide) is widened by ec (1e-13 m); a pair that lands in [LO64, HI64) -- an obstacle
+// point within ~1e-13 m of a circle -- is NOT decided on the device: the path point's index is appended to a list
+// the caller resolves with host-evaluated cos / sin (collision_resolve_kernel; a handful of points per batch at most).
+constexpr double kTrigTau = 5.6843418860808015e-14;   // 2^-44
+
+struct YawFix {
+    int *list;      // list[0] = number of appended items (may exceed capacity), list[1..capacity] = item = p * n_pts + j
+    int capacity;   // list == nullptr: legacy device-trig mode (pairs inside the band are decided with the device's values)
+};
+
+__device__ __forceinline__ void yaw_fix_append(const YawFix &yf, int item)
+{
+    const int i = atomicAdd(yf.list, 1);
+    if (i < yf.capacity) yf.list[1 + i] = item;
+}
+
+// per-thread centre uncertainty and the certain-hit / certain-free thresholds on q64
+template <int NC>
+__device__ __forceinline__ double yaw_bounds(const CircleSpec &cs, const double *cx, const double *cy, double *lo64, double *hi64)
+{
+    double ec = 0.0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const double e = 2.0 * fabs(cs.off[k]) * (kTrigTau + 8.881784197001252e-16) + 4.440892098500626e-16 * (fabs(cx[k]) + fabs(cy[k]));
+        ec = fmax(ec, e);
+        if (!(e == e)) ec = INFINITY;    // fmax drops NaN: a NaN centre never hits in either arithmetic, inf keeps it undecidable
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const double r = cs.rad[k];
+        const double a = (r * (1.0 - 8.881784197001252e-16) - ec) / (1.0 + 4.440892098500626e-16);
+        const double b = (r * (1.0 + 8.881784197001252e-16) + ec) / (1.0 - 4.440892098500626e-16);
+        const bool ok = r > 1.0e-100 && r < 1.0e150 && ec < INFINITY;
+        lo64[k] = (ok && a > 0.0) ? a * a * (1.0 - 2.0e-15) : 0.0;
+        hi64[k] = ok ? b * b * (1.0 + 2.0e-15) : INFINITY;
+        if (!(r > 0.0)) lo64[k] = hi64[k] = 0.0;   // r <= 0 or NaN: d >= 0 is never < r
+    }
+    return ec;
+}
+
 template <int NC, bool CLEAR>
 __global__ void __launch_bounds__(kColBlock)
 collision_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, const double *__restrict__ px,
