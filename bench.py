@@ -12,8 +12,11 @@ independent, so N GPUs run N such batches with no data-path collective (weak sca
 One JSON line is printed by rank 0.  ``value`` is timed with CUDA events around each step with the inputs
 resident in HBM; ``e2e`` goes through the public host-buffer API (H2D of the inputs, time-chunked kernels,
 D2H of the whole trajectory, overlapped) and is the number to hold against the CPU reference arm.
-``--impl reference`` times the CPU port of the reference's path (the plain-C oracle, all host threads) on a
-bounded sample of the same workload.  The reference itself is pure Python and cannot travel to the GPU box.
+``--impl reference`` times the reference's own CPU path on the box's host cores on a bounded sample of the same
+workload: the UNMODIFIED Python (``planar_model_RK4`` under ``multiprocessing.Pool(os.cpu_count())``) from the verbatim
+copy staged under ``baseline/_ref`` (``baseline/stage_reference.py``), with the plain-C/OpenMP port (``oracle/csrc``)
+timed beside it; the port alone when no copy is staged.  The lattice half of the metric (collision checks/s, config 3)
+is reported in the same line: ``collision``, ``roofline_collision``, ``cpu_baseline_collision``.
 """
 from __future__ import annotations
 
@@ -39,6 +42,25 @@ ALG_FLOP_PER_STEP = 854          # 806 add/mul/di
 ALG_BYTES_PER_STEP = 80          # 10 states x 8 B written per rollout-step
 ALG_FLOP_PER_TEST = 8            # one circle-vs-point test
 WORKLOAD = f"config2: {B} rollouts x {N_STEPS} steps, FP64, dt=1e-4, ZOH-{HOLD} controls, full trajectory stored"
+
+
+def bench_config(n_gpus: int) -> dict:
+    """The `config` object of BOTH arms (the reference arm times a bounded sample of this workload; what the sample
+    was is stated in its `cpu_baseline.sample`)."""
+    return {"workload": WORKLOAD, "per_gpu_batch": B, "n_steps": N_STEPS,
+            "parallelism": f"dp{n_gpus} (independent rollouts, no data-path collective)",
+            "l2": "256 MiB buffer written between timed iterations (untimed); each step also streams 2.62 GB of output through the 126 MB L2"}
+
+
+def kernel_source_sha16() -> str:
+    """Hash of the CUDA sources the ncu-derived numbers in profiles/roofline_inputs.json were captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "python_motionplanning_b200", "csrc")
+    for name in sorted(os.listdir(csrc)):
+        with open(os.path.join(csrc, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
 
 
 def _host_threads() -> int:
@@ -70,25 +92,54 @@ def cpu_port_run(threads: int, rollouts_per_thread: int = 2048, repeats: int = 1
     return nb * N_STEPS, times, sample
 
 
+def literal_run(rollouts_per_proc: int = 16, paths_per_proc: int = 0, repeats: int = 1, timeout: int = 900):
+    """The UNMODIFIED reference timed in a subprocess (no CUDA context is forked): oracle/literal_baseline.py.
+    Returns its JSON object, or {"unavailable": why}."""
+    cmd = [sys.executable, "-m", "oracle.literal_baseline", "--rollouts-per-proc", str(rollouts_per_proc),
+           "--paths-per-proc", str(paths_per_proc), "--repeats", str(repeats)]
+    try:
+        res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+        for ln in reversed(res.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": f"literal baseline printed no JSON (rc={res.returncode}): {res.stderr[-200:]}"}
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = _host_threads()
-    for _ in range(args.warmup):
-        cpu_port_run(threads, rollouts_per_thread=256)
-    units, times, sample = cpu_port_run(threads, repeats=args.steps)
-    total = sum(times)
-    value = units * args.steps / total
+    # the C port, all host threads (a far stronger CPU implementation than the reference's own Python)
+    cpu_port_run(threads, rollouts_per_thread=256)
+    p_units, p_times, p_sample = cpu_port_run(threads, repeats=max(1, min(args.steps, 3)))
+    port = {"value": p_units * len(p_times) / sum(p_times), "unit": UNIT, "cores": threads, "kind": "port", "sample": p_sample,
+            "note": "plain-C/OpenMP restatement of vehicle_model.py:220-445 (oracle/csrc/oracle.c)"}
+    # the unmodified reference: every step = procs x R rollouts x 500 steps, R sized so that warmup + steps end in ~2 min
+    total_steps = args.steps + args.warmup
+    R = max(1, min(16, 360 // max(total_steps, 1)))
+    lit = literal_run(rollouts_per_proc=R, repeats=total_steps)
+    times, units, procs, sample = [], 0, None, None
+    if "rollout" in lit:
+        times = lit["rollout"]["seconds_each"][args.warmup:]
+        units = lit["rollout"]["rollouts"] * lit["rollout"]["n_steps"] * len(times)
+        procs, sample = lit["procs"], lit["rollout"]["sample"]
+    if times:
+        value, ms = units / sum(times), 1e3 * sum(times) / len(times)
+        cpu = {"value": value, "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample + f"; one such sample per step ({len(times)} timed)",
+               "reference_root": os.path.relpath(lit.get("reference_root", ""), ROOT) if lit.get("reference_root", "").startswith(ROOT) else lit.get("reference_root"),
+               "port": port}
+    else:
+        value, ms = port["value"], 1e3 * sum(p_times) / len(p_times)
+        cpu = dict(port, literal_unavailable=lit.get("unavailable"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "step": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "note": "plain-C restatement of vehicle_model.py:220-445 (oracle/csrc/oracle.c); the reference "
-                                 "is pure Python (~2e3 steps/s/core, tests/golden/rollout_cfg2_sub.npz) and cannot "
-                                 "travel to the GPU box"},
+        "config": bench_config(args.gpus),
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -343,11 +394,16 @@ def run_gpu(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
         prof = {}
+        src_sha = kernel_source_sha16()
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_inputs.json")))
-            traffic = prof.get("rk4_rollout_f64_dram_bytes_per_launch")
         except Exception:
             pass
+        # ncu-derived numbers are carried only while the CUDA sources are the ones that were profiled
+        prof_fresh = prof.get("csrc_sha16") == src_sha
+        if not prof_fresh:
+            prof = {"stale": True}
+        traffic = prof.get("rk4_rollout_f64_dram_bytes_per_launch")
         roofline = {
             "bound": "fp64", "kernel": "rk4_rollout_kernel<double,front-steer>", "achieved": achieved_tf, "peak": peak64,
             "unit": "TFLOP/s", "frac": achieved_tf / peak64 if peak64 else None, "traffic": traffic,
@@ -357,26 +413,34 @@ def run_gpu(args):
             "fp64_pipe_util_ncu": prof.get("rk4_rollout_f64_fp64_pipe_pct"),
             "smem_wavefront_util_ncu": prof.get("rk4_rollout_f64_smem_wavefront_pct"),
             "issue_active_ncu": prof.get("rk4_rollout_f64_issue_active_pct"),
-            "note": "friction from a host-built polynomial table in shared memory (no sqrt/atan/sin in the kernel). Measured cost "
-                    "model of this kernel on B200: cycles per warp-step = 2.17 x FP64 instructions + 1 x all other instructions "
-                    "(594 + 437 per step), i.e. the FP64 pipe can be at most 73 % busy with this instruction mix; the closed-form "
-                    "kernel (secondary.rollout_f64_closed_form) keeps the pipe 81 % busy but needs 2x the FP64 instructions",
+            "ncu_source": prof.get("rk4_rollout_f64_source_file"), "csrc_sha16": src_sha,
+            "ncu_numbers_match_this_source": prof_fresh,
+            "note": "friction from a host-built polynomial table in shared memory (no sqrt/atan/sin in the kernel); traffic and the "
+                    "*_ncu fields come from profiles/roofline_inputs.json and are dropped (null) when its csrc_sha16 differs from "
+                    "the sources this run was built from",
             "hbm": {"achieved": steps_per_s_gpu * ALG_BYTES_PER_STEP * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": steps_per_s_gpu * ALG_BYTES_PER_STEP * 1e-9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
         }
         cpu_baseline = None
+        col = {}
         if world == 1:
             threads = _host_threads()
             units, times, sample = cpu_port_run(threads)
             cpu_baseline = {"value": units / times[0], "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+            lit = literal_run(rollouts_per_proc=16, paths_per_proc=2)
+            if "rollout" in lit:
+                cpu_baseline["literal"] = {"value": lit["rollout"]["value"], "unit": UNIT, "cores": lit["procs"], "kind": "reference",
+                                           "sample": lit["rollout"]["sample"], "seconds": lit["rollout"]["seconds"]}
+            else:
+                cpu_baseline["literal"] = {"unavailable": lit.get("unavailable", "no rollout leg")}
+            col = collision_metrics(eng, wl, np, torch, lit)
         extras = secondary_metrics(eng, wl, np, torch) if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "n_steps": N_STEPS, "parallelism": f"dp{world} (independent rollouts, no data-path collective)",
-                       "l2": "256 MiB buffer written between timed iterations (untimed); each step also streams 2.62 GB of output through the 126 MB L2"},
+            "config": bench_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "Engine.rollout_to_host: pinned host inputs -> H2D, 10 time-chunks of 50 steps, D2H of the full trajectory overlapped on a copy stream",
                     "bound": "PCIe: 2.62 GB of trajectory per step at ~55 GB/s",
@@ -389,6 +453,7 @@ def run_gpu(args):
                        "remeasured": remeasured},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_s_timed_region": wall,
         }
+        line.update(col)          # collision, roofline_collision, cpu_baseline_collision (N = 1)
         if extras:
             line["secondary"] = extras
         if mpc_sharded:
@@ -401,8 +466,129 @@ def run_gpu(args):
     return 0
 
 
+def collision_metrics(eng, wl, np, torch, lit):
+    """The metric's second half -- lattice collision checks/s on BASELINE config 3 (4,096 paths x 49 points x 3 circles vs
+    10,000 obstacle points) -- as top-level objects: `collision` (kernel-resident value, the public-API number with host
+    buffers, the variants), `roofline_collision` (the SHIPPED broad-phase kernel on executed and on nominal tests) and
+    `cpu_baseline_collision` (C port on all host threads + the unmodified collision_check on a subsample)."""
+    w = wl.config3_lattice()
+    P, n = w["px"].shape
+    M = len(w["obstacles"])
+    nc = len(w["offsets"])
+    tests = P * n * nc * M
+    unit = "circle-point tests/s (nominal P*49*3*M)"
+    px, py, yaw = eng.dev(w["px"]), eng.dev(w["py"]), eng.dev(w["pyaw"])
+    obs = eng.dev(w["obstacles"])
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def dev_ms(fn, reps=10, warm=3):
+        evs = [(ev(), ev()) for _ in range(reps + warm)]
+        for e0, e1 in evs:
+            e0.record()
+            r = fn()
+            e1.record()
+        torch.cuda.synchronize()
+        return statistics.median(e0.elapsed_time(e1) for e0, e1 in evs[warm:]), r
+
+    def wall_ms(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        return statistics.median(ts) * 1e3, r
+
+    out = {}
+    # ---- shipped path, inputs resident: yaws on the device, proven verdicts, host-resolved leftovers (count read back)
+    ms_res, free = wall_ms(lambda: eng.collision_check_batch(px, py, yaw, obs, w["offsets"], w["radii"]))
+    undecided = eng.last_collision_undecided
+    st2 = (C.c_ulonglong * 2)()
+    eng.lib.b200mp_collision_stats(eng.device, eng._stream(), M, st2)
+    n_warps = -(-P * n // 32)
+    executed = int(st2[0]) * 32 * 32 * nc
+    # ---- public API with HOST buffers (numpy in, numpy out): H2D of px, py, pyaw, obstacles; D2H of the flags
+    hx, hy, hyaw, hobs = w["px"], w["py"], w["pyaw"], w["obstacles"]
+    ms_e2e, _ = wall_ms(lambda: eng.collision_check_batch(hx, hy, hyaw, hobs, w["offsets"], w["radii"]).cpu())
+    h2d = int(hx.nbytes + hy.nbytes + hyaw.nbytes + hobs.nbytes)
+    # ---- the former default (numpy cos / sin of all 200k yaws on the host) for comparison
+    ms_host_trig, _ = wall_ms(lambda: eng.collision_check_batch(px, py, w["pyaw"], obs, w["offsets"], w["radii"], host_trig=True), reps=5)
+    # ---- kernels only, CUDA events, caller-supplied trig (no host work in the call), all three arithmetic modes; the
+    # shipped scene and the same scene with the obstacles out of reach (nothing collides: no early exit, nothing culled by verdict)
+    trig = eng.path_trig(w["pyaw"], n)
+    far = eng.dev(w["obstacles"] + np.array([400.0, 0.0]))
+    peak32 = eng.fma_peak(32, reps=3)
+    peak64 = eng.fma_peak(64, reps=3)
+    variants = {}
+    for name, ob in (("shipped_scene", obs), ("no_early_exit", far)):
+        for mode in ("auto", "screen", "fp64"):
+            ms, fr = dev_ms(lambda: eng.collision_check_batch(px, py, None, ob, w["offsets"], w["radii"], trig=trig, mode=mode))
+            variants[f"{name}_{mode}"] = {"ms": ms, "value": tests / (ms * 1e-3), "free_fraction": float(fr.float().mean().item())}
+    ms_k = variants["shipped_scene_auto"]["ms"]
+    ms_clear, _ = dev_ms(lambda: eng.collision_check_batch(px, py, None, obs, w["offsets"], w["radii"], trig=trig, want_clearance=True))
+    ms_clear_api, _ = wall_ms(lambda: eng.collision_check_batch(px, py, w["pyaw"], obs, w["offsets"], w["radii"], want_clearance=True), reps=5)
+    out["collision"] = {
+        "metric": "lattice collision checks/sec", "unit": unit, "workload": f"config3: {P} paths x {n} points x {nc} circles vs {M} obstacle points, bit-exact flags",
+        "value": tests / (ms_k * 1e-3), "ms": ms_k, "paths_per_s": P / (ms_k * 1e-3),
+        "value_note": "memset + obstacle_prepare_kernel + collision_cull_kernel<3>, CUDA events, paths / trig / obstacles resident",
+        "free_fraction": float(free.float().mean().item()),
+        "e2e": {"value": tests / (ms_e2e * 1e-3), "unit": unit, "ms": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": P + 4,
+                "api": "Engine.collision_check_batch(numpy px, py, pyaw, obstacles) -> flags on the host: yaws evaluated on the device with "
+                       "proven verdicts, undecided path points resolved with host numpy cos/sin (b200mp_collision_check_yaw_f64 + _resolve_)",
+                "path_points_resolved_on_host": undecided},
+        "api_inputs_resident": {"ms": ms_res, "value": tests / (ms_res * 1e-3),
+                                "includes": "kernels + the 4-byte undecided count read back + stream sync"},
+        "api_host_trig_all_yaws": {"ms": ms_host_trig, "note": "the former default: numpy cos/sin of 200k yaws on the host + their H2D"},
+        "min_clearance": {"kernel_ms": ms_clear, "value": tests / (ms_clear * 1e-3), "api_ms_host_trig": ms_clear_api},
+        "variants": variants,
+    }
+    # ---- roofline of the shipped kernel: 4 FP32 lane-operations per executed test (2 subtractions, 1 multiply, 1 FMA = 5 flop)
+    k_far = variants["no_early_exit_screen"]
+    out["roofline_collision"] = {
+        "kernel": "collision_cull_kernel<3> (+ obstacle_prepare_kernel)", "bound": "fp32",
+        "achieved": executed * 5 / (ms_k * 1e-3) * 1e-12, "peak": peak32, "unit": "TFLOP/s",
+        "frac": executed * 5 / (ms_k * 1e-3) * 1e-12 / peak32,
+        "basis": "EXECUTED tests (b200mp_collision_stats: warp-chunks that survive the bounding-box broad phase x 32 path points x 32 "
+                 "obstacle points x 3 circles) x 5 FP32 flop, over the whole launch",
+        "tests_executed": executed, "tests_nominal": tests, "executed_fraction": executed / tests,
+        "warp_chunks_screened": int(st2[0]), "warp_chunks_total": n_warps * (-(-M // 32)), "thread_chunks_rechecked_fp64": int(st2[1]),
+        "nominal": {"achieved": tests * ALG_FLOP_PER_TEST / (ms_k * 1e-3) * 1e-12, "peak": peak64, "unit": "TFLOP/s",
+                    "frac": tests * ALG_FLOP_PER_TEST / (ms_k * 1e-3) * 1e-12 / peak64,
+                    "basis": "NOMINAL tests x 8 FP64 flop (SURVEY.md 8d) against the measured FP64 peak: above 1 because culled and "
+                             "FP32-screened pairs never reach the FP64 pipe (flags proven bit-exact)"},
+        "screen_every_pair": {"ms": k_far["ms"], "achieved": k_far["value"] * 5 * 1e-12, "peak": peak32, "frac": k_far["value"] * 5 * 1e-12 / peak32,
+                              "frac_of_fp32_lane_issue": k_far["value"] * 4 / (peak32 * 1e12 / 2),
+                              "basis": "collision_filter_kernel<3>, obstacles out of reach: every nominal test executed in packed FP32"},
+        "peak_source": "measured live: register-resident FFMA / DFMA chains (b200mp_fma_peak)", "traffic": None,
+        "traffic_note": "inputs 4.9 MB, outputs 4 KB per launch: not memory-bound (profiles/r02_collision_cull.md)",
+    }
+    # ---- CPU: the C port on all host threads (full config 3, early exit like the reference) + the literal reference
+    from oracle import c_oracle
+    threads = _host_threads()
+    c_oracle.collision_check(w["px"][:64], w["py"][:64], w["pyaw"][:64], w["obstacles"], w["offsets"], w["radii"], nthreads=threads)
+    t0 = time.perf_counter()
+    ref_free, _, c_tests = c_oracle.collision_check(w["px"], w["py"], w["pyaw"], w["obstacles"], w["offsets"], w["radii"], nthreads=threads)
+    c_s = time.perf_counter() - t0
+    same = bool(np.array_equal(ref_free, free.cpu().numpy().astype(bool)))
+    cb = {"value": tests / c_s, "unit": unit, "cores": threads, "kind": "port", "seconds": c_s, "paths_per_s": P / c_s,
+          "tests_executed": int(c_tests), "flags_equal_gpu": same,
+          "sample": f"all {P} config-3 paths, plain-C restatement of collision_checker.py:32-117 with the reference's early exit, {threads} OpenMP threads"}
+    if "collision" in lit:
+        lc = lit["collision"]
+        cb["literal"] = {"value": lc["value"], "unit": unit, "cores": lit["procs"], "kind": "reference", "paths_per_s": lc["paths_per_s"],
+                         "seconds": lc["seconds"], "sample": lc["sample"],
+                         "flags_equal_gpu": bool(np.array_equal(np.array(lc["free"], bool), free.cpu().numpy().astype(bool)[:lc["paths"]]))}
+    else:
+        cb["literal"] = {"unavailable": lit.get("unavailable", "no collision leg")}
+    out["cpu_baseline_collision"] = cb
+    return out
+
+
 def secondary_metrics(eng, wl, np, torch):
-    """The metric's second half (lattice collision checks/s, config 3) and the other configs, N = 1 only."""
+    """The other configs and kernels, N = 1 only (the collision half of the metric is `collision_metrics`)."""
     out = {}
     w = wl.config3_lattice()
     P, n = w["px"].shape
@@ -410,62 +596,8 @@ def secondary_metrics(eng, wl, np, torch):
     tests = P * n * 3 * M
     px, py = eng.dev(w["px"]), eng.dev(w["py"])
     obs = eng.dev(w["obstacles"])
-
-    def run(clear):
-        return eng.collision_check_batch(px, py, w["pyaw"], obs, w["offsets"], w["radii"], want_clearance=clear)
-
-    for name, clear in (("collision_flags", False), ("collision_min_clearance", True)):
-        for _ in range(3):
-            run(clear)
-        torch.cuda.synchronize()
-        ts = []
-        for _ in range(10):
-            t0 = time.perf_counter()
-            r = run(clear)
-            torch.cuda.synchronize()
-            ts.append(time.perf_counter() - t0)
-        free = r[0] if clear else r
-        sec = statistics.median(ts)
-        out[name] = {"metric": "lattice collision checks/sec", "value": tests / sec, "unit": "circle-point tests/s (nominal P*49*3*M)",
-                     "ms": sec * 1e3, "paths_per_s": P / sec, "free_fraction": float(free.float().mean().item()),
-                     "includes": "host numpy cos/sin of 200k yaws + H2D of them + kernel(s) + sync",
-                     "algorithmic_tflops": tests * ALG_FLOP_PER_TEST / sec * 1e-12}
-    # kernel-only (paths, host-evaluated cos/sin and obstacles resident; CUDA events), the shipped scene and the same
-    # scene with the obstacles moved out of reach (nothing collides -> no early exit, every nominal test is executed)
-    trig = eng.path_trig(w["pyaw"], n)
-    far = eng.dev(w["obstacles"] + np.array([400.0, 0.0]))
+    free = eng.collision_check_batch(px, py, w["pyaw"], obs, w["offsets"], w["radii"])
     peak32 = eng.fma_peak(32, reps=3)
-    for name, ob in (("collision_kernel", obs), ("collision_kernel_no_early_exit", far)):
-        for mode in ("auto", "screen", "fp64"):
-            eng.set_collision_mode(mode)
-            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(13)]
-            for e0, e1 in evs:
-                e0.record()
-                fr = eng.collision_check_batch(px, py, None, ob, w["offsets"], w["radii"], trig=trig)
-                e1.record()
-            torch.cuda.synchronize()
-            ms = statistics.median(e0.elapsed_time(e1) for e0, e1 in evs[3:])
-            key = name + {"auto": "", "screen": "_screen_only", "fp64": "_fp64_only"}[mode]
-            out[key] = {"ms": ms, "value": tests / (ms * 1e-3), "unit": "circle-point tests/s (nominal)",
-                        "free_fraction": float(fr.float().mean().item()),
-                        "arithmetic": {"auto": "bounding-box broad phase over 32-point obstacle chunks + FP32 screen (packed f32x2) + "
-                                               "exact FP64 recheck of undecided pairs",
-                                       "screen": "FP32 screen (packed f32x2) + exact FP64 recheck of undecided pairs, every pair",
-                                       "fp64": "all FP64, every pair"}[mode]}
-            if mode == "auto":
-                st2 = (C.c_ulonglong * 2)()
-                eng.lib.b200mp_collision_stats(eng.device, eng._stream(), M, st2)
-                n_warps = -(-P * n // 32)
-                out[key]["broad_phase"] = {"warp_chunks_screened": int(st2[0]), "warp_chunks_total": n_warps * (-(-M // 32)),
-                                           "thread_chunks_rechecked_fp64": int(st2[1]),
-                                           "tests_executed": int(st2[0]) * 32 * 32 * 3}
-        eng.set_collision_mode("auto")
-    k = out["collision_kernel_no_early_exit_screen_only"]
-    # 4 FP32 lane-operations per test (2 subtractions, 1 multiply, 1 FMA = 5 flop) against the measured FP32 FMA peak
-    k["roofline"] = {"bound": "fp32", "achieved": k["value"] * 5 * 1e-12, "peak": peak32, "unit": "TFLOP/s",
-                     "frac": k["value"] * 5 * 1e-12 / peak32, "frac_of_fp32_lane_issue": k["value"] * 4 / (peak32 * 1e12 / 2),
-                     "flop_per_test_executed": 5, "flop_per_test_algorithmic": ALG_FLOP_PER_TEST,
-                     "peak_source": "measured live: register-resident FFMA chains (b200mp_fma_peak 32)"}
     ex_d, ey_d = px[:, -1].contiguous(), py[:, -1].contiguous()
     eng.select_best_path_index_batch(ex_d, ey_d, free, w["goal"], w["weight"])   # first call probes the host's norm closed form
     torch.cuda.synchronize()
@@ -500,8 +632,8 @@ def secondary_metrics(eng, wl, np, torch):
             a1, a2, a3 = o["p"][0], o["p"][1], o["p"][2]
         else:
             a1, a2, a3 = k1d, k2d, sfd
-        lt = eng.sample_lattice(a1, a2, a3, ego=egod)
-        fr = eng.collision_check_batch(lt["px"], lt["py"], None, obs, w["offsets"], w["radii"], trig=(lt["pcos"], lt["psin"]))
+        lt = eng.sample_lattice(a1, a2, a3, ego=egod, want_trig=False)
+        fr = eng.collision_check_batch(lt["px"], lt["py"], lt["pyaw"], obs, w["offsets"], w["radii"])
         return eng.select_best_path_index_batch(lt["end_xy"][0], lt["end_xy"][1], fr, w["goal"], w["weight"]), fr
     for name, optimise in (("lattice_pipeline_sample_check_select", False), ("lattice_pipeline_optimise_sample_check_select", True)):
         for _ in range(3):
@@ -515,7 +647,7 @@ def secondary_metrics(eng, wl, np, torch):
         sec = statistics.median(ts)
         out[name] = {"ms": sec * 1e3, "paths_per_s": P / sec, "value": tests / sec, "unit": "circle-point tests/s (nominal)",
                      "best_index": bi, "free_fraction": float(fr.float().mean().item()),
-                     "includes": "all kernels + the device->host read of the chosen index; no host trig, no path upload"}
+                     "includes": "all kernels + the undecided count and the chosen index read back; no host trig on the bulk, no path upload"}
     # closed-loop tracking: 65,536 vehicles on 16 waypoint lists of 3,000 points, 500 sub-steps =
     # 50 Stanley/PID updates each; same RK4 work per step as the headline metric plus the controllers
     st0, wps = wl.tracking_fleet(V=B, n_sets=16)
@@ -541,8 +673,7 @@ def secondary_metrics(eng, wl, np, torch):
     ev1.record()
     torch.cuda.synchronize()
     eng.set_friction_mode("auto")
-    out["rollout_f64_closed_form"] = {"value": B * N_STEPS / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT, "ms": ev0.elapsed_time(ev1),
-                                      "fp64_pipe_util_ncu": 80.6}
+    out["rollout_f64_closed_form"] = {"value": B * N_STEPS / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT, "ms": ev0.elapsed_time(ev1)}
     del trj
     # end-state-only FP64 (no trajectory writeback): separates compute from writeback
     s0, dl, tq = eng.dev(s0_h), eng.dev(d_h), eng.dev(t_h)

@@ -137,8 +137,10 @@ int b200mp_argmin_f64(int device, void *stream, long long n, const double *cost,
  *   off, rad   HOST arrays [n_circ] (n_circ <= 8)
  *   px, py     dev [P][n_pts]
  *   pcos, psin dev [P][n_pts] cos / sin of path[2][j] computed by the caller on the host (numpy), which is
- *              what makes the booleans bit-exact; or NULL with pyaw dev [P][yaw_stride] (first n_pts of
- *              each row used) to evaluate sincos on the device (<= 1-2 ulp from libm)
+ *              what makes the booleans and min_clear bit-exact; or NULL with pyaw dev [P][yaw_stride] (first
+ *              n_pts of each row used) to evaluate sincos on the device (<= 2 ulp: a verdict can then differ from the
+ *              reference's only for an obstacle point within ~1e-13 m of a circle -- use b200mp_collision_check_yaw_f64
+ *              for proven verdicts)
  *   obs        dev [M][2]
  *   free_out   dev [P] bytes, 1 = collision-free (the reference's polarity)
  *   min_clear  dev [P] min over all tests of (distance - radius), or NULL
@@ -147,6 +149,33 @@ int b200mp_collision_check_f64(int device, void *stream, int P, int n_pts, int n
                                const double *rad, const double *px, const double *py, const double *pcos,
                                const double *psin, const double *pyaw, int yaw_stride, int M, const double *obs,
                                unsigned char *free_out, double *min_clear);
+
+/* The same test from path YAWS, bit-exact without host trigonometry on the bulk of the data (collision_checker.py:88-89
+ * evaluates np.cos / np.sin of every yaw; here the device does).  Every verdict the device writes is PROVEN to equal the
+ * verdict of the reference's arithmetic for any host cos / sin within 2^-44 of the exact values (numpy: <= 0.52 ulp;
+ * CUDA sincos: <= 2 ulp): the host's and the device's circle centres then differ by at most
+ *   ec = 2 |off| (2^-44 + 2^-50) + 2^-51 (|cx| + |cy|)   (~1e-13 m),
+ * the FP32 screen's band is widened by ec, and the exact FP64 recheck declares a collision only for
+ * q64 < ((r (1 - 2^-50) - ec) / (1 + 2^-51))^2 and "free" only for q64 >= ((r (1 + 2^-50) + ec) / (1 - 2^-51))^2.
+ * A path point with an obstacle point inside that band is NOT decided on the device: its item index p * n_pts + j is
+ * appended to `undecided` (dev int [1 + capacity]: [0] = number of appended items, which may exceed capacity and may
+ * contain duplicates; [1..] = items) and free_out[p] is left as the other points of the path decide it.  The caller reads
+ * the count, evaluates cos / sin of the listed yaws on the HOST (numpy) and calls b200mp_collision_resolve_f64; if the
+ * count exceeds capacity it falls back to b200mp_collision_check_f64 with host pcos / psin.  On BASELINE config 3 the
+ * list is empty; a list entry needs an obstacle point within ~1e-13 m of a circle.
+ *   pyaw  dev [P][yaw_stride], the first n_pts of each row are used (the reference's 49/50 quirk)
+ *   mode  B200MP_COLLISION_* for THIS call, or -1 for the process-wide default */
+int b200mp_collision_check_yaw_f64(int device, void *stream, int P, int n_pts, int n_circ, const double *off,
+                                   const double *rad, const double *px, const double *py, const double *pyaw,
+                                   int yaw_stride, int M, const double *obs, unsigned char *free_out, int *undecided,
+                                   int undecided_capacity, int mode);
+
+/* Decides the listed path points exactly: items dev [n_list] (as written by b200mp_collision_check_yaw_f64), cos_sin dev
+ * [2][n_list] = the caller's host-evaluated cos and sin of the items' yaws; every obstacle point is tested against the
+ * items' circles with the FP64 sequence of b200mp_collision_check_f64 and free_out[p] is cleared on a collision. */
+int b200mp_collision_resolve_f64(int device, void *stream, int n_list, const int *items, const double *cos_sin, int P,
+                                 int n_pts, int n_circ, const double *off, const double *rad, const double *px,
+                                 const double *py, int M, const double *obs, unsigned char *free_out);
 
 /* How the rollout / tracking kernels evaluate the combined-slip friction D sin(C atan(B s)) / s
  * (vehicle_model.py:296-348).  AUTO (default): from tables of piecewise polynomials in 1 + (B s)^2 built on the host by
@@ -181,6 +210,10 @@ int b200mp_collision_stats(int device, void *stream, int M, unsigned long long *
 /* select_best_path_index on the path end points (collision_checker.py:134-203):
  *   score_i = norm([ex_i-gx, ey_i-gy]) + sum over colliding j (ascending) of weight*norm([ex_i-ex_j, ey_i-ey_j])
  * colliding i -> +inf; first strict minimum wins; best_out[0] = -1 for the reference's None.
+ * free_in dev [P] bytes: 1 = collision-free (a candidate), 0 = colliding (a penalty term for the others), any other value
+ * = excluded -- neither candidate nor penalty, which is how a path the planner dropped before the selection
+ * (local_planner.py:317-323: spiral end point farther than 0.1 from its goal) is passed without compacting the arrays;
+ * the relative order of the remaining paths, and with it the tie-break, is the filtered list's.
  * norm_mode picks the closed form of np.linalg.norm the host follows (B200MP_NORM2_*).
  * scores_out dev [P] or NULL. */
 int b200mp_select_best_f64(int device, void *stream, int P, const double *ex, const double *ey,

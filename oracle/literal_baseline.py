@@ -66,7 +66,7 @@ def _collision_task(args):
     return bool(cc.collision_check(path, obstacles))
 
 
-def run(rollouts_per_proc: int = 16, paths_per_proc: int = 2, procs: int | None = None, n_steps: int = 500):
+def run(rollouts_per_proc: int = 16, paths_per_proc: int = 2, procs: int | None = None, n_steps: int = 500, repeats: int = 1):
     procs = procs or os.cpu_count() or 1
     out = {"procs": procs, "reference_root": ref_loader.REFERENCE_ROOT}
     nb = procs * rollouts_per_proc
@@ -76,10 +76,13 @@ def run(rollouts_per_proc: int = 16, paths_per_proc: int = 2, procs: int | None 
                   t[:, :, k::procs][:, :, :rollouts_per_proc].copy(), n_steps, wl.HOLD) for k in range(procs)]
         with mp.Pool(procs, initializer=_init_worker) as pool:
             pool.map(abs, range(procs))                 # workers forked and warm before the clock starts
-            t0 = time.perf_counter()
-            res = pool.map(_rollout_task, tasks, chunksize=1)
-            el = time.perf_counter() - t0
-        out["rollout"] = {"value": nb * n_steps / el, "unit": "rollout-steps/s", "seconds": el, "rollouts": nb, "n_steps": n_steps,
+            secs = []
+            for _ in range(max(1, repeats)):
+                t0 = time.perf_counter()
+                res = pool.map(_rollout_task, tasks, chunksize=1)
+                secs.append(time.perf_counter() - t0)
+            el = sum(secs) / len(secs)
+        out["rollout"] = {"value": nb * n_steps / el, "unit": "rollout-steps/s", "seconds": el, "seconds_each": secs, "rollouts": nb, "n_steps": n_steps,
                           "sample": f"config 2 rollouts k, k+{procs}, ... ({rollouts_per_proc} per process) x {n_steps} steps, "
                                     f"unmodified planar_model_RK4 under multiprocessing.Pool({procs})",
                           "end_state_checksum": float(np.sum([r[0] for r in res]))}
@@ -107,8 +110,9 @@ if __name__ == "__main__":
     ap.add_argument("--paths-per-proc", type=int, default=2)
     ap.add_argument("--procs", type=int, default=None)
     ap.add_argument("--n-steps", type=int, default=500)
+    ap.add_argument("--repeats", type=int, default=1, help="timed repetitions of the rollout sample (one pool)")
     a = ap.parse_args()
     if not ref_loader.available():
         print(json.dumps({"unavailable": f"no reference under {ref_loader.REFERENCE_ROOT} or baseline/_ref"}))
         sys.exit(0)
-    print(json.dumps(run(a.rollouts_per_proc, a.paths_per_proc, a.procs, a.n_steps)))
+    print(json.dumps(run(a.rollouts_per_proc, a.paths_per_proc, a.procs, a.n_steps, a.repeats)))

@@ -2,7 +2,7 @@
 
 Run in the build container (the only place ``/root/reference`` exists):
 
-    python -m oracle.make_golden [--only planar|rollout|collision|closedloop] [--frames 400]
+    python -m oracle.make_golden [--only planar|rollout|collision|closedloop|spiral_opt|lattice|tracking|plan_invalid] [--frames 400]
 
 The reference has no tests or golden vectors of its own, so these files -- outputs of
 the literal reference code on seeded inputs -- are what pins the oracle (``tests/test_oracle_pinned.py``)
@@ -426,6 +426,55 @@ def gen_spiral_opt(n_eval=256, n_goals=192):
     print(f"spiral_opt.npz: {n_eval} objective/gradient evaluations, {n_goals} optimisations in {el:.1f}s, valid {valid.mean():.2f}")
 
 
+# ------------------------------------------------- planner core with dropped paths (plan_lattice)
+def gen_plan_invalid():
+    """Literal ``plan_paths`` (local_planner.py:277-325: a spiral whose end point misses its goal by more than 0.1 is
+    DROPPED from the list) -> ``transform_paths`` (:424-470) -> literal ``collision_check`` per path ->
+    ``select_best_path_index`` (collision_checker.py:134-203) on goal sets that contain unreachable goals at the head,
+    in the middle, at the tail and at the would-be winner.  The chosen index refers to the FILTERED list."""
+    ref = ref_loader.load()
+    lp = ref.local_planner.LocalPlanner(30, 7, 2, list(wl.CIRCLE_OFFSETS), list(wl.CIRCLE_RADII), wl.PATH_SELECT_WEIGHT,
+                                        1.0, 1.5, 2.0, 3.5)
+    cc = lp._collision_checker
+    rng = np.random.default_rng(wl.SEED + 21)
+    unreachable = [(5.0, 3.0, 2.0), (4.0, 4.0, 0.0), (5.0, 3.0, 2.1), (4.0, 4.2, 0.0)]      # end-point error ~0.26 >> 0.1
+    cases = []
+    for c in range(8):
+        n_goals = [7, 7, 9, 12, 7, 16, 7, 10][c]
+        gt = rng.uniform(-0.3, 0.3)
+        gx, gy = rng.uniform(24.0, 36.0), rng.uniform(-2.0, 2.0)
+        goals = [[gx + (k - n_goals // 2) * 2.0 * np.cos(gt + np.pi / 2), gy + (k - n_goals // 2) * 2.0 * np.sin(gt + np.pi / 2),
+                  gt, 25.0] for k in range(n_goals)]
+        bad_at = [[0], [6], [3], [0, 5, 11], [2, 3, 4], [1, 8, 15], list(range(7)), []][c]
+        for i, k in enumerate(bad_at):
+            u = unreachable[(c + i) % len(unreachable)]
+            goals[k] = [u[0], u[1], u[2], 25.0]
+        ego = [rng.uniform(-20, 20), rng.uniform(-20, 20), rng.uniform(-np.pi, np.pi), 25.0]
+        paths, validity = lp.plan_paths(goals)
+        paths = ref.local_planner.transform_paths(paths, ego)
+        # obstacles: a box outline on the centre path's far half and a few scattered points, in the global frame
+        obstacles = []
+        if paths:
+            mid = paths[(len(paths) // 2 + c) % len(paths)]
+            cxo, cyo = mid[0][35], mid[1][35]
+            X, Y = wl.box_outline(np.array([cxo + rng.uniform(-0.5, 0.5), cyo + rng.uniform(-0.5, 0.5)]), 1.0, 1.0, 0.21)
+            obstacles = np.stack([X, Y], 1).tolist()
+        flags = [bool(cc.collision_check(pth, obstacles)) for pth in paths]
+        goal_state = [ego[0] + gx * np.cos(ego[2]) - gy * np.sin(ego[2]), ego[1] + gx * np.sin(ego[2]) + gy * np.cos(ego[2]), 25.0]
+        best = cc.select_best_path_index(paths, flags, goal_state)
+        cases.append(dict(goals=np.array(goals), ego=np.array(ego), obstacles=np.array(obstacles, float).reshape(-1, 2),
+                          validity=np.array(validity, bool), flags=np.array(flags, bool), goal_state=np.array(goal_state),
+                          best=-1 if best is None else int(best),
+                          ends=np.array([[pth[0][-1], pth[1][-1]] for pth in paths], float).reshape(-1, 2)))
+        print(f"case {c}: {n_goals} goals, valid {np.array(validity, int)}, free {np.array(flags, int)}, best(filtered) {best}")
+    out = {"n_cases": len(cases), "weight": wl.PATH_SELECT_WEIGHT}
+    for c, d in enumerate(cases):
+        for k, v in d.items():
+            out[f"c{c}_{k}"] = v
+    np.savez_compressed(os.path.join(GOLDEN, "plan_invalid.npz"), **out, **_host_facts())
+    print("plan_invalid.npz written")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -448,6 +497,8 @@ def main():
         gen_lattice()
     if a.only in (None, "tracking"):
         gen_tracking(min(a.frames, 200))
+    if a.only in (None, "plan_invalid"):
+        gen_plan_invalid()
 
 
 if __name__ == "__main__":

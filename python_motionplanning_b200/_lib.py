@@ -61,6 +61,8 @@ PROTOTYPES = {
     "b200mp_mpc_sample_controls_f64": (_i, [_i, _vp, _i, _i, _ull, _ll, _d, _d, _d, _d, _d, _vp, _vp]),
     "b200mp_argmin_f64": (_i, [_i, _vp, _ll, _vp, _ll, _vp, _vp]),
     "b200mp_collision_check_f64": (_i, [_i, _vp, _i, _i, _i, _dp, _dp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "b200mp_collision_check_yaw_f64": (_i, [_i, _vp, _i, _i, _i, _dp, _dp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i]),
+    "b200mp_collision_resolve_f64": (_i, [_i, _vp, _i, _vp, _vp, _i, _i, _i, _dp, _dp, _vp, _vp, _i, _vp, _vp]),
     "b200mp_set_friction_mode": (_i, [_i]),
     "b200mp_set_collision_mode": (_i, [_i]),
     "b200mp_collision_stats": (_i, [_i, _vp, _i, C.POINTER(C.c_ulonglong)]),

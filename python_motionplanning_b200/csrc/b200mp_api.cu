@@ -48,6 +48,7 @@ int ensure_scratch(int device, size_t bytes, void **out)
     std::lock_guard<std::mutex> lock(g_mutex);
     DeviceState &ds = dev_state(device);
     if (bytes < 4096) bytes = 4096;
+    ds.cull_stats_valid = false;   // whoever asks is about to overwrite the area (the broad-phase launcher re-arms it)
     if (ds.scratch_bytes < bytes) {
         if (ds.scratch) {
             // a larger area is needed: wait for work that may still use the old one
@@ -308,7 +309,34 @@ int b200mp_collision_check_f64(int device, void *stream, int P, int n_pts, int n
 {
     B200MP_ENTER(device);
     return launch_collision_f64(device, (cudaStream_t)stream, P, n_pts, n_circ, off, rad, px, py, pcos, psin, pyaw,
-                                yaw_stride, M, obs, free_out, min_clear);
+                                yaw_stride, M, obs, free_out, min_clear, nullptr, 0, -1);
+}
+
+int b200mp_collision_check_yaw_f64(int device, void *stream, int P, int n_pts, int n_circ, const double *off,
+                                   const double *rad, const double *px, const double *py, const double *pyaw,
+                                   int yaw_stride, int M, const double *obs, unsigned char *free_out, int *undecided,
+                                   int undecided_capacity, int mode)
+{
+    B200MP_ENTER(device);
+    if (!undecided) {
+        set_error("collision_check_yaw: undecided must be a device array of 1 + capacity ints");
+        return B200MP_E_ARG;
+    }
+    if (mode != -1 && mode != B200MP_COLLISION_AUTO && mode != B200MP_COLLISION_FP64_ONLY && mode != B200MP_COLLISION_SCREEN_ONLY) {
+        set_error("collision_check_yaw: unknown mode %d", mode);
+        return B200MP_E_ARG;
+    }
+    return launch_collision_f64(device, (cudaStream_t)stream, P, n_pts, n_circ, off, rad, px, py, nullptr, nullptr, pyaw,
+                                yaw_stride, M, obs, free_out, nullptr, undecided, undecided_capacity, mode);
+}
+
+int b200mp_collision_resolve_f64(int device, void *stream, int n_list, const int *items, const double *cos_sin, int P,
+                                 int n_pts, int n_circ, const double *off, const double *rad, const double *px,
+                                 const double *py, int M, const double *obs, unsigned char *free_out)
+{
+    B200MP_ENTER(device);
+    return launch_collision_resolve_f64(device, (cudaStream_t)stream, n_list, items, cos_sin, P, n_pts, n_circ, off, rad,
+                                        px, py, M, obs, free_out);
 }
 
 int b200mp_set_friction_mode(int mode)

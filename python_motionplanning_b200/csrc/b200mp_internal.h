@@ -44,6 +44,9 @@ struct DeviceState {
     int set_tables_n = 0;
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    // where the broad-phase statistics of the last collision launch sit in `scratch`; cleared by every other scratch user
+    size_t cull_stats_offset = 0;
+    bool cull_stats_valid = false;
     // ring of small work-queue areas for time-sliced rollout launches (one per launch in flight)
     void *sched_ring = nullptr;
     cudaEvent_t sched_event[kSchedSlots] = {};
@@ -82,7 +85,10 @@ int launch_planar_model_f64(int device, cudaStream_t st, int B, const double *st
 int launch_collision_f64(int device, cudaStream_t st, int P, int n_pts, int n_circ, const double *off,
                          const double *rad, const double *px, const double *py, const double *pcos,
                          const double *psin, const double *pyaw, int yaw_stride, int M, const double *obs,
-                         unsigned char *free_out, double *min_clear);
+                         unsigned char *free_out, double *min_clear, int *undecided, int undecided_capacity, int mode);
+int launch_collision_resolve_f64(int device, cudaStream_t st, int n_list, const int *items, const double *cos_sin, int P,
+                                 int n_pts, int n_circ, const double *off, const double *rad, const double *px,
+                                 const double *py, int M, const double *obs, unsigned char *free_out);
 int collision_stats(int device, cudaStream_t st, int M, unsigned long long out[2]);
 int launch_select_best_f64(int device, cudaStream_t st, int P, const double *ex, const double *ey,
                            const unsigned char *free_in, double gx, double gy, double weight, int norm_mode,

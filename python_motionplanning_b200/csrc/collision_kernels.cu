@@ -96,12 +96,12 @@ __device__ __forceinline__ double yaw_bounds(const CircleSpec &cs, const double 
     return ec;
 }
 
-template <int NC, bool CLEAR>
+template <int NC, bool CLEAR, bool YAWFIX = false>
 __global__ void __launch_bounds__(kColBlock)
 collision_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, const double *__restrict__ px,
                  const double *__restrict__ py, const double *__restrict__ pcos, const double *__restrict__ psin,
                  const double *__restrict__ pyaw, int yaw_stride, int M, const double2 *__restrict__ obs,
-                 unsigned char *free_out, double *__restrict__ clear_pts)
+                 unsigned char *free_out, double *__restrict__ clear_pts, YawFix yf = YawFix{nullptr, 0})
 {
     __shared__ double2 tile[kObsTile];
     const int t = blockIdx.x * kColBlock + threadIdx.x;
@@ -128,6 +128,10 @@ collision_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, 
     double qmin[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) qmin[k] = INFINITY;
+    // YAWFIX: verdicts proven against host trigonometry (see yaw_bounds); a pair inside the band is left to the caller
+    double lo64[YAWFIX ? NC : 1], hi64[YAWFIX ? NC : 1];
+    bool appended = false;
+    if (YAWFIX && active) yaw_bounds<NC>(cs, cx, cy, lo64, hi64);
     for (int m0 = 0; m0 < M; m0 += kObsTile) {
         const int m1 = min(kObsTile, M - m0);
         __syncthreads();
@@ -135,7 +139,7 @@ collision_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, 
         if (!CLEAR && active && ((volatile unsigned char *)free_out)[p] == 0) active = false;   // path already known to collide
         if (!__syncthreads_or(active)) break;
         if (!active) continue;
-        bool hit = false;
+        bool hit = false, maybe = false;
 #pragma unroll 4
         for (int o = 0; o < m1; ++o) {
             const double2 ob = tile[o];
@@ -144,17 +148,26 @@ collision_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, 
                 const double dx = __dsub_rn(ob.x, cx[k]);
                 const double dy = __dsub_rn(ob.y, cy[k]);
                 const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                if (CLEAR)
+                if (CLEAR) {
                     qmin[k] = fmin(qmin[k], q);                             // NaN is skipped, as fmin(clr, d) did
-                else
+                } else if (YAWFIX) {
+                    hit |= q < lo64[k];
+                    maybe |= q < hi64[k];
+                } else {
                     hit |= q < cs.thr[k];
+                }
             }
         }
         if (CLEAR) {
 #pragma unroll
             for (int k = 0; k < NC; ++k) hit |= qmin[k] < cs.thr[k];        // sqrt_rn(q) - r < 0  <=>  q < thr
         }
-        if (hit) free_out[p] = 0;
+        if (hit) {
+            free_out[p] = 0;
+        } else if (YAWFIX && maybe && !appended) {
+            yaw_fix_append(yf, t);
+            appended = true;
+        }
     }
     if (CLEAR && t < n_items) {
         double clr = INFINITY;
@@ -223,21 +236,25 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
     return r;
 }
 
+// exact FP64 sequence over obstacle points [m_begin, m_end): bit 0 = some q < lo (a certain hit), bit 1 = some q < hi
+// (lo = hi = thr when the centres carry the caller's own cos / sin; the yaw_bounds pair otherwise)
 template <int NC>
-__device__ __noinline__ bool exact_tile_hit(const CircleSpec &cs, const double *cx, const double *cy,
+__device__ __noinline__ int exact_tile_bits(const double *lo, const double *hi, const double *cx, const double *cy,
                                             const double2 *__restrict__ obs, int m_begin, int m_end)
 {
-    bool hit = false;
+    bool hit = false, maybe = false;
     for (int o = m_begin; o < m_end; ++o) {
         const double2 ob = obs[o];
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             const double dx = __dsub_rn(ob.x, cx[k]);
             const double dy = __dsub_rn(ob.y, cy[k]);
-            hit |= __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < cs.thr[k];
+            const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            hit |= q < lo[k];
+            maybe |= q < hi[k];
         }
     }
-    return hit;
+    return (hit ? 1 : 0) | (maybe ? 2 : 0);
 }
 
 template <int NC>
@@ -245,7 +262,7 @@ __global__ void __launch_bounds__(kColBlock)
 collision_filter_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, const double *__restrict__ px,
                         const double *__restrict__ py, const double *__restrict__ pcos, const double *__restrict__ psin,
                         const double *__restrict__ pyaw, int yaw_stride, int M, const double2 *__restrict__ obs,
-                        unsigned char *free_out)
+                        unsigned char *free_out, YawFix yf)
 {
     __shared__ __align__(16) float2 tile[kFTile];
     __shared__ int s_amax;
@@ -309,7 +326,11 @@ collision_filter_kernel(int n_items, int n_pts, const __grid_constant__ CircleSp
             ac = fmax(ac, m);
         }
         const double u = 5.9604644775390625e-08;   // 2^-24
-        const double e0 = 2.0 * u * ((double)__int_as_float(s_amax) + ac) * 1.000001 + 1.0e-18;
+        double e0 = 2.0 * u * ((double)__int_as_float(s_amax) + ac) * 1.000001 + 1.0e-18;
+        if (yf.list) {   // centres from the device's sincos: the band also covers any host trigonometry (yaw_bounds)
+            double l64[NC], h64[NC];
+            e0 += yaw_bounds<NC>(cs, cx, cy, l64, h64);
+        }
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             const double r = cs.rad[k];
@@ -365,7 +386,18 @@ collision_filter_kernel(int n_items, int n_pts, const __grid_constant__ CircleSp
         hit |= mn[k] < lo[k];
         undecided |= !(mn[k] >= hi[k]);
     }
-    if (!hit && undecided) hit = exact_tile_hit<NC>(cs, cx, cy, obs, m0, m0 + m1);
+    if (!hit && undecided) {
+        int bits;
+        if (yf.list) {
+            double l64[NC], h64[NC];
+            yaw_bounds<NC>(cs, cx, cy, l64, h64);
+            bits = exact_tile_bits<NC>(l64, h64, cx, cy, obs, m0, m0 + m1);
+        } else {
+            bits = exact_tile_bits<NC>(cs.thr, cs.thr, cx, cy, obs, m0, m0 + m1);
+        }
+        hit = bits & 1;
+        if (bits == 2) yaw_fix_append(yf, t);   // within ~1e-13 m of a circle: the caller decides with host cos / sin
+    }
     if (hit) free_out[p] = 0;
 }
 
@@ -587,7 +619,7 @@ collision_cull_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec
                       const double *__restrict__ py, const double *__restrict__ pcos, const double *__restrict__ psin,
                       const double *__restrict__ pyaw, int yaw_stride, int M, const double2 *__restrict__ obs,
                       const float2 *__restrict__ pts, const float4 *__restrict__ boxes, ObsPrep *prep,
-                      unsigned char *free_out)
+                      unsigned char *free_out, YawFix yf)
 {
     const int t = blockIdx.x * kColBlock + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -629,7 +661,11 @@ collision_cull_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec
             ac = fmax(ac, fmax(fabs(rx), fabs(ry)));
         }
         const double u = 5.9604644775390625e-08;   // 2^-24
-        const double e0 = 2.0 * u * ((double)*(volatile float *)&prep->amax + ac) * 1.000001 + 1.0e-18;
+        double e0 = 2.0 * u * ((double)*(volatile float *)&prep->amax + ac) * 1.000001 + 1.0e-18;
+        if (yf.list) {   // centres from the device's sincos: the band also covers any host trigonometry (yaw_bounds)
+            double l64[NC], h64[NC];
+            e0 += yaw_bounds<NC>(cs, cx, cy, l64, h64);
+        }
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             const double r = cs.rad[k];
@@ -703,11 +739,54 @@ collision_cull_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec
     }
     if (!hit && undecided) {
         // exact FP64 sequence over the chunks that overlap this thread's own box (the others are certainly free)
-        for (int c = c_begin; c < c_end && !hit; ++c) {
+        double l64[NC], h64[NC];
+        if (yf.list) {
+            yaw_bounds<NC>(cs, cx, cy, l64, h64);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) l64[k] = h64[k] = cs.thr[k];
+        }
+        int bits = 0;
+        for (int c = c_begin; c < c_end && !(bits & 1); ++c) {
             const float4 b = boxes[c];
             if (b.x > bx1 || b.z < bx0 || b.y > by1 || b.w < by0) continue;
-            hit = exact_tile_hit<NC>(cs, cx, cy, obs, c * 32, min(M, c * 32 + 32));
+            bits |= exact_tile_bits<NC>(l64, h64, cx, cy, obs, c * 32, min(M, c * 32 + 32));
             atomicAdd(&prep->rechecked, 1ULL);
+        }
+        hit = bits & 1;
+        if (bits == 2) yaw_fix_append(yf, t);   // within ~1e-13 m of a circle: the caller decides with host cos / sin
+    }
+    if (hit) free_out[p] = 0;
+}
+
+// Resolves the path points the yaw-mode kernels left undecided: one CTA per listed item, exact FP64 sequence against
+// every obstacle point with the cos / sin the caller evaluated on the host for exactly these points.
+template <int NC>
+__global__ void __launch_bounds__(128)
+collision_resolve_kernel(int n_list, const int *__restrict__ items, const double *__restrict__ cos_sin, int n_pts,
+                         const __grid_constant__ CircleSpec cs, const double *__restrict__ px, const double *__restrict__ py,
+                         int M, const double2 *__restrict__ obs, unsigned char *free_out)
+{
+    const int i = blockIdx.x;
+    if (i >= n_list) return;
+    const int t = items[i];
+    const int p = t / n_pts;
+    if (((volatile unsigned char *)free_out)[p] == 0) return;
+    const double x = px[t], y = py[t], c = cos_sin[i], s = cos_sin[n_list + i];
+    double cx[NC], cy[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        cx[k] = __dadd_rn(x, __dmul_rn(cs.off[k], c));
+        cy[k] = __dadd_rn(y, __dmul_rn(cs.off[k], s));
+    }
+    bool hit = false;
+    for (int o = threadIdx.x; o < M; o += blockDim.x) {
+        const double2 ob = obs[o];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const double dx = __dsub_rn(ob.x, cx[k]);
+            const double dy = __dsub_rn(ob.y, cy[k]);
+            hit |= __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < cs.thr[k];
         }
     }
     if (hit) free_out[p] = 0;
@@ -725,7 +804,8 @@ __global__ void clearance_reduce_kernel(int P, int n_pts, const double *__restri
 template <int NC>
 static int launch_collision_nc(int device, cudaStream_t st, int P, int n_pts, const CircleSpec &cs, const double *px,
                                const double *py, const double *pcos, const double *psin, const double *pyaw,
-                               int yaw_stride, int M, const double *obs, unsigned char *free_out, double *min_clear)
+                               int yaw_stride, int M, const double *obs, unsigned char *free_out, double *min_clear,
+                               YawFix yf, int mode)
 {
     const long long items = (long long)P * n_pts;
     const int grid = (int)((items + kColBlock - 1) / kColBlock);
@@ -733,7 +813,7 @@ static int launch_collision_nc(int device, cudaStream_t st, int P, int n_pts, co
         void *scratch = nullptr;
         int rc = ensure_scratch(device, sizeof(double) * (size_t)items, &scratch);
         if (rc) return rc;
-        if (collision_mode() == B200MP_COLLISION_FP64_ONLY)
+        if (mode == B200MP_COLLISION_FP64_ONLY)
             collision_kernel<NC, true><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
                                                                   M, (const double2 *)obs, free_out, (double *)scratch);
         else
@@ -741,14 +821,18 @@ static int launch_collision_nc(int device, cudaStream_t st, int P, int n_pts, co
                                                                    M, (const double2 *)obs, free_out, (double *)scratch);
         B200MP_CUDA(cudaGetLastError());
         clearance_reduce_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, n_pts, (const double *)scratch, min_clear);
-    } else if (collision_mode() == B200MP_COLLISION_FP64_ONLY) {
-        collision_kernel<NC, false><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
-                                                               M, (const double2 *)obs, free_out, nullptr);
-    } else if (collision_mode() == B200MP_COLLISION_SCREEN_ONLY || items * (long long)M < (1LL << 22)) {
+    } else if (mode == B200MP_COLLISION_FP64_ONLY) {
+        if (yf.list)
+            collision_kernel<NC, false, true><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw,
+                                                                         yaw_stride, M, (const double2 *)obs, free_out, nullptr, yf);
+        else
+            collision_kernel<NC, false><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
+                                                                   M, (const double2 *)obs, free_out, nullptr);
+    } else if (mode == B200MP_COLLISION_SCREEN_ONLY || items * (long long)M < (1LL << 22)) {
         // (also for small problems such as the planner's own 7 paths x 106 points: one launch, no prepare pass)
         const dim3 g2(grid, (M + kFTile - 1) / kFTile);
         collision_filter_kernel<NC><<<g2, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride, M,
-                                                             (const double2 *)obs, free_out);
+                                                             (const double2 *)obs, free_out, yf);
     } else {
         const int n_chunks = (M + 31) / 32;
         const size_t pts_bytes = sizeof(float2) * 32 * (size_t)n_chunks, box_bytes = sizeof(float4) * (size_t)n_chunks;
@@ -766,42 +850,71 @@ static int launch_collision_nc(int device, cudaStream_t st, int P, int n_pts, co
         int gy = (148 * 8 + grid - 1) / grid;
         gy = gy < 1 ? 1 : (gy > groups ? groups : gy);
         collision_cull_kernel<NC><<<dim3(grid, gy), kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
-                                                                     M, (const double2 *)obs, pts, boxes, prep, free_out);
+                                                                     M, (const double2 *)obs, pts, boxes, prep, free_out, yf);
+        // the statistics of THIS launch sit at this offset until the next user of the scratch area overwrites them
+        DeviceState &ds = dev_state(device);
+        ds.cull_stats_offset = pts_bytes + box_bytes;
+        ds.cull_stats_valid = true;
     }
     B200MP_CUDA(cudaGetLastError());
     return 0;
 }
 
-// last launch's broad-phase statistics (synchronises the stream)
+// last launch's broad-phase statistics (synchronises the stream); zeros unless the broad-phase kernel was the last
+// user of the device's scratch area
 int collision_stats(int device, cudaStream_t st, int M, unsigned long long out[2])
 {
+    (void)M;
     DeviceState &ds = dev_state(device);
     out[0] = out[1] = 0;
-    if (!ds.scratch || M <= 0) return 0;
-    const int n_chunks = (M + 31) / 32;
-    const size_t off = sizeof(float2) * 32 * (size_t)n_chunks + sizeof(float4) * (size_t)n_chunks;
+    if (!ds.scratch || !ds.cull_stats_valid) return 0;
     ObsPrep h;
-    B200MP_CUDA(cudaMemcpyAsync(&h, (char *)ds.scratch + off, sizeof(h), cudaMemcpyDeviceToHost, st));
+    B200MP_CUDA(cudaMemcpyAsync(&h, (char *)ds.scratch + ds.cull_stats_offset, sizeof(h), cudaMemcpyDeviceToHost, st));
     B200MP_CUDA(cudaStreamSynchronize(st));
     out[0] = h.screened;
     out[1] = h.rechecked;
     return 0;
 }
 
-int launch_collision_f64(int device, cudaStream_t st, int P, int n_pts, int n_circ, const double *off,
-                         const double *rad, const double *px, const double *py, const double *pcos,
-                         const double *psin, const double *pyaw, int yaw_stride, int M, const double *obs,
-                         unsigned char *free_out, double *min_clear)
+static int collision_args_ok(int P, int n_pts, int n_circ, int M, const double *off, const double *rad,
+                             const unsigned char *free_out)
 {
     if (P < 0 || n_pts < 0 || M < 0 || n_circ < 1 || n_circ > kMaxCircles) {
         set_error("collision_check: bad sizes P=%d n_pts=%d n_circ=%d (1..%d) M=%d", P, n_pts, n_circ, kMaxCircles, M);
         return B200MP_E_ARG;
     }
-    if (P == 0) return 0;
-    if (!off || !rad || !free_out) {
+    if (P > 0 && (!off || !rad || !free_out)) {
         set_error("collision_check: off, rad and free_out must be non-NULL");
         return B200MP_E_ARG;
     }
+    if ((long long)P * n_pts > 0x7fffffffLL) {
+        set_error("collision_check: P*n_pts exceeds 2^31-1");
+        return B200MP_E_ARG;
+    }
+    return 0;
+}
+
+static CircleSpec make_circle_spec(int n_circ, const double *off, const double *rad)
+{
+    CircleSpec cs{};
+    for (int k = 0; k < n_circ; ++k) {
+        cs.off[k] = off[k];
+        cs.rad[k] = rad[k];
+        cs.thr[k] = sqrt_threshold(rad[k]);
+    }
+    return cs;
+}
+
+int launch_collision_f64(int device, cudaStream_t st, int P, int n_pts, int n_circ, const double *off,
+                         const double *rad, const double *px, const double *py, const double *pcos,
+                         const double *psin, const double *pyaw, int yaw_stride, int M, const double *obs,
+                         unsigned char *free_out, double *min_clear, int *undecided, int undecided_capacity, int mode)
+{
+    int rc = collision_args_ok(P, n_pts, n_circ, M, off, rad, free_out);
+    if (rc) return rc;
+    if (mode < 0) mode = collision_mode();
+    if (undecided) B200MP_CUDA(cudaMemsetAsync(undecided, 0, sizeof(int), st));
+    if (P == 0) return 0;
     // every path starts collision-free (empty path or empty obstacle list -> True, as the reference)
     B200MP_CUDA(cudaMemsetAsync(free_out, 1, (size_t)P, st));
     if (n_pts == 0 || M == 0) {
@@ -816,28 +929,51 @@ int launch_collision_f64(int device, cudaStream_t st, int P, int n_pts, int n_ci
         set_error("collision_check: px, py, obs and (pcos, psin) or pyaw must be non-NULL");
         return B200MP_E_ARG;
     }
-    if ((long long)P * n_pts > 0x7fffffffLL) {
-        set_error("collision_check: P*n_pts exceeds 2^31-1");
-        return B200MP_E_ARG;
-    }
     if ((((size_t)obs) & 15) != 0) {
         set_error("collision_check: obs must be 16-byte aligned");
         return B200MP_E_ARG;
     }
-    CircleSpec cs{};
-    for (int k = 0; k < n_circ; ++k) {
-        cs.off[k] = off[k];
-        cs.rad[k] = rad[k];
-        cs.thr[k] = sqrt_threshold(rad[k]);
+    if (undecided && (min_clear || (pcos && psin) || undecided_capacity < 0)) {
+        set_error("collision_check: the undecided list goes with pyaw input and flags only");
+        return B200MP_E_ARG;
     }
+    const CircleSpec cs = make_circle_spec(n_circ, off, rad);
     if (!pcos || !psin) pcos = psin = nullptr;
+    const YawFix yf{undecided, undecided_capacity};
     switch (n_circ) {
 #define B200MP_NC(N) \
-    case N: return launch_collision_nc<N>(device, st, P, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride, M, obs, free_out, min_clear);
+    case N: return launch_collision_nc<N>(device, st, P, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride, M, obs, free_out, min_clear, yf, mode);
         B200MP_NC(1) B200MP_NC(2) B200MP_NC(3) B200MP_NC(4) B200MP_NC(5) B200MP_NC(6) B200MP_NC(7) B200MP_NC(8)
 #undef B200MP_NC
     }
     return B200MP_E_ARG;
+}
+
+int launch_collision_resolve_f64(int device, cudaStream_t st, int n_list, const int *items, const double *cos_sin, int P,
+                                 int n_pts, int n_circ, const double *off, const double *rad, const double *px,
+                                 const double *py, int M, const double *obs, unsigned char *free_out)
+{
+    (void)device;
+    int rc = collision_args_ok(P, n_pts, n_circ, M, off, rad, free_out);
+    if (rc) return rc;
+    if (n_list < 0 || (n_list > 0 && (!items || !cos_sin || !px || !py))) {
+        set_error("collision_resolve: bad list (n_list=%d)", n_list);
+        return B200MP_E_ARG;
+    }
+    if (n_list == 0 || M == 0 || P == 0) return 0;
+    if (!obs || (((size_t)obs) & 15) != 0) {
+        set_error("collision_resolve: obs must be non-NULL and 16-byte aligned");
+        return B200MP_E_ARG;
+    }
+    const CircleSpec cs = make_circle_spec(n_circ, off, rad);
+    switch (n_circ) {
+#define B200MP_NC(N) \
+    case N: collision_resolve_kernel<N><<<n_list, 128, 0, st>>>(n_list, items, cos_sin, n_pts, cs, px, py, M, (const double2 *)obs, free_out); break;
+        B200MP_NC(1) B200MP_NC(2) B200MP_NC(3) B200MP_NC(4) B200MP_NC(5) B200MP_NC(6) B200MP_NC(7) B200MP_NC(8)
+#undef B200MP_NC
+    }
+    B200MP_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -868,7 +1004,9 @@ select_score_kernel(int P, const double *__restrict__ ex, const double *__restri
     const int lane = threadIdx.x & 31;
     if (i >= P) return;
     const double xi = ex[i], yi = ey[i];
-    const bool fi = free_in[i] != 0;
+    // free_in: 1 = collision-free candidate, 0 = colliding (penalises the others), any other value = excluded: neither a
+    // candidate nor a penalty term -- a path the planner dropped before the selection (local_planner.py:317-323)
+    const bool fi = free_in[i] == 1;
     double score = norm2_host_form(__dsub_rn(xi, gx), __dsub_rn(yi, gy), mode);   // collision_checker.py:175
     if (fi) {                                                                       // a colliding i scores +inf (:196)
         for (int j0 = 0; j0 < P; j0 += 32) {

@@ -174,20 +174,22 @@ def plan_lattice_sharded(engine, goals_local, ego, obstacles, offsets, radii, go
     """``Engine.plan_lattice`` with the goal states sharded over the ranks: every rank optimises, samples and checks its
     block of goal states (``goals_local`` is the FULL ``[3, P]`` array on every rank), then the flags and path end
     points are all-gathered (P bytes + 16 P bytes) and the path selection runs replicated, so every rank returns the
-    same ``(best index or None, free[P], end_xy[2, P])``."""
+    same ``(best index into the full goal list or None, free[P], end_xy[2, P])``; dropped spirals are excluded from the
+    selection exactly as in ``Engine.plan_lattice``."""
     rank, ws = world()
     g = engine.dev(goals_local)
     P = g.shape[1]
     lo, hi = shard_range(P, rank, ws)
     gl = g[:, lo:hi].contiguous()
     opt = engine.optimize_spirals(gl[0], gl[1], gl[2], n_samples)
-    lat = engine.sample_lattice(opt["p"][0], opt["p"][1], opt["p"][2], ego=ego, n_samples=n_samples)
-    free_l = engine.collision_check_batch(lat["px"], lat["py"], None, obstacles, offsets, radii,
-                                          trig=(lat["pcos"], lat["psin"])) & opt["valid"]
-    free = gather_flags(free_l, P, group=group)
+    lat = engine.sample_lattice(opt["p"][0], opt["p"][1], opt["p"][2], ego=ego, n_samples=n_samples, want_trig=False)
+    free_l = engine.collision_check_batch(lat["px"], lat["py"], lat["pyaw"], obstacles, offsets, radii)
+    # a spiral that fails the acceptance test is dropped by the planner (local_planner.py:317-323): state 2 = excluded
+    state_l = torch.where(opt["valid"] != 0, free_l, torch.full_like(free_l, 2))
+    state = gather_flags(state_l, P, group=group)
     end_xy = gather_shards(lat["end_xy"], P, group=group)
-    best = engine.select_best_path_index_batch(end_xy[0].contiguous(), end_xy[1].contiguous(), free, goal_xy, weight)
-    return best, free, end_xy
+    best = engine.select_best_path_index_batch(end_xy[0].contiguous(), end_xy[1].contiguous(), state, goal_xy, weight)
+    return best, (state == 1).to(torch.uint8), end_xy
 
 
 def track_sharded(engine, state0, waypoints, dt, n_steps, target_vel=25.0, wp_count=None, vehicles_per_set=None, gather=False,

@@ -402,13 +402,24 @@ class Engine:
         yaw = np.asarray(pyaw, dtype=np.float64)[:, :n]
         return self.dev(np.cos(yaw)), self.dev(np.sin(yaw))
 
-    def collision_check_batch(self, px, py, pyaw, obstacles, offsets: Sequence[float], radii: Sequence[float],
-                              want_clearance: bool = False, device_trig: bool = False, trig=None):
-        """``free[P]`` (uint8, 1 = collision-free) for P paths at once (``b200mp_collision_check_f64``).
+    _UNDECIDED_CAPACITY = 8192
+    _COLLISION_MODES = {None: -1, "auto": 0, "fp64": 1, "screen": 2}
 
-        px, py ``[P,n]``; pyaw ``[P,>=n]`` (first n used).  By default cos/sin of the yaws are evaluated on the
-        host with numpy -- exactly what the reference does (collision_checker.py:88-89) -- which makes the
-        booleans bit-exact; ``device_trig=True`` evaluates them in the kernel instead (<= 1-2 ulp).
+    def collision_check_batch(self, px, py, pyaw, obstacles, offsets: Sequence[float], radii: Sequence[float],
+                              want_clearance: bool = False, device_trig: bool = False, trig=None, host_trig: bool = False,
+                              mode: Optional[str] = None):
+        """``free[P]`` (uint8, 1 = collision-free) for P paths at once.
+
+        px, py ``[P,n]``; pyaw ``[P,>=n]`` (first n used).  Default: the yaws go to the device
+        (``b200mp_collision_check_yaw_f64``); every verdict the kernel writes is proven to equal the reference's, whose
+        circle centres carry numpy's ``cos`` / ``sin`` roundings (collision_checker.py:88-89), and the few path points it
+        cannot prove -- an obstacle point within ~1e-13 m of a circle -- are decided with host-evaluated numpy
+        ``cos`` / ``sin`` of exactly those yaws (``b200mp_collision_resolve_f64``).  The flags are bit-exact and only a
+        4-byte count crosses the bus on the way back.  ``trig=(cos, sin)`` uses the caller's values as they are;
+        ``host_trig=True`` evaluates all yaws with numpy on the host (the former default; what ``want_clearance`` uses, because
+        the minimum clearance is a double that depends on every centre's last bit); ``device_trig=True`` is the unproven
+        device-only path (kept for A/B).  ``mode`` = ``"auto" | "screen" | "fp64"`` for this call (default: the
+        process-wide mode).  ``self.last_collision_undecided`` = number of host-resolved path points of the last call.
         """
         pxt, pyt = self.dev(px), self.dev(py)
         if pxt.dim() != 2:
@@ -421,23 +432,64 @@ class Engine:
         rad = (C.c_double * len(radii))(*[float(v) for v in radii])
         if len(offsets) != len(radii):
             raise ValueError("circle_offsets and circle_radii must have the same length")
+        if mode not in self._COLLISION_MODES:
+            raise ValueError(f"collision mode must be one of {sorted(k for k in self._COLLISION_MODES if k)}")
+        self.last_collision_undecided = 0
+        free = self.empty(P, dtype=torch.uint8)
+        exact_yaw = trig is None and not host_trig and not device_trig and not want_clearance
+        if exact_yaw:
+            yaw_t = self.dev(pyaw)
+            if yaw_t.dim() != 2 or yaw_t.shape[0] != P or yaw_t.shape[1] < n:
+                raise ValueError("pyaw must be [P, >= n_pts]")
+            cap = self._UNDECIDED_CAPACITY
+            if getattr(self, "_und", None) is None:
+                self._und = self.empty(1 + cap, dtype=torch.int32)
+                self._und_host = torch.empty(1, dtype=torch.int32).pin_memory()
+            check(self.lib.b200mp_collision_check_yaw_f64(self.device, self._stream(), P, n, len(offsets), off, rad,
+                                                          self._ptr(pxt), self._ptr(pyt), self._ptr(yaw_t), yaw_t.shape[1], M,
+                                                          self._ptr(obs), self._ptr(free), self._ptr(self._und), cap,
+                                                          self._COLLISION_MODES[mode]), "b200mp_collision_check_yaw_f64")
+            self._und_host.copy_(self._und[:1], non_blocking=True)
+            torch.cuda.current_stream(self.tdev).synchronize()
+            count = int(self._und_host[0])
+            self.last_collision_undecided = count
+            if count == 0:
+                return free
+            if count <= cap:
+                items = torch.unique(self._und[1:1 + count])
+                jj, pp = items % n, items // n
+                yaws = yaw_t[pp.long(), jj.long()].cpu().numpy()
+                cs_host = np.stack([np.cos(yaws), np.sin(yaws)])          # numpy on the host: the reference's own values
+                cs_dev = self.dev(cs_host)
+                check(self.lib.b200mp_collision_resolve_f64(self.device, self._stream(), int(items.numel()), self._ptr(items),
+                                                            self._ptr(cs_dev), P, n, len(offsets), off, rad, self._ptr(pxt),
+                                                            self._ptr(pyt), M, self._ptr(obs), self._ptr(free)),
+                      "b200mp_collision_resolve_f64")
+                return free
+            host_trig = True        # more undecided points than the list holds: evaluate every yaw on the host
         pc = ps = yaw_t = None
         stride = 0
-        if device_trig:
-            yaw_t = self.dev(pyaw)
-            stride = yaw_t.shape[1]
-        elif trig is not None:
+        if trig is not None:
             pc, ps = self.dev(trig[0]), self.dev(trig[1])
             if pc.shape != (P, n) or ps.shape != (P, n):
                 raise ValueError("trig must be (cos[P,n], sin[P,n])")
+        elif device_trig and not host_trig:
+            yaw_t = self.dev(pyaw)
+            stride = yaw_t.shape[1]
         else:
             pc, ps = self.path_trig(pyaw, n)
-        free = self.empty(P, dtype=torch.uint8)
         clr = self.empty(P) if want_clearance else None
-        check(self.lib.b200mp_collision_check_f64(self.device, self._stream(), P, n, len(offsets), off, rad,
-                                                  self._ptr(pxt), self._ptr(pyt), self._ptr(pc), self._ptr(ps),
-                                                  self._ptr(yaw_t), stride, M, self._ptr(obs), self._ptr(free),
-                                                  self._ptr(clr)), "b200mp_collision_check_f64")
+        prev = None
+        if mode is not None:
+            prev = self.set_collision_mode(mode)
+        try:
+            check(self.lib.b200mp_collision_check_f64(self.device, self._stream(), P, n, len(offsets), off, rad,
+                                                      self._ptr(pxt), self._ptr(pyt), self._ptr(pc), self._ptr(ps),
+                                                      self._ptr(yaw_t), stride, M, self._ptr(obs), self._ptr(free),
+                                                      self._ptr(clr)), "b200mp_collision_check_f64")
+        finally:
+            if prev is not None:
+                self.set_collision_mode(prev)
         return (free, clr) if want_clearance else free
 
     def sample_lattice(self, kappa1, kappa2, sf, ego=None, n_samples: int = 50, want_trig: bool = True,
@@ -496,19 +548,25 @@ class Engine:
                      weight: float, n_samples: int = 50):
         """The planner's numeric core on the device, end to end (local_planner.py:367-379): optimise one spiral per
         goal state (vehicle frame ``goals_local [3,P]`` = xf, yf, tf), sample and transform the spirals with ``ego`` =
-        (x, y, yaw), test them against ``obstacles [M,2]`` and select the best path index.  Paths whose optimisation fails
-        the planner's acceptance test are treated as colliding (the reference drops them from the list, :317-323, so
-        the returned index refers to the FULL goal list).  Returns ``(best_index or None, dict of device tensors)``."""
+        (x, y, yaw), test them against ``obstacles [M,2]`` and select the best path index.
+
+        A path whose optimisation fails the planner's acceptance test is DROPPED, as ``plan_paths`` does
+        (local_planner.py:317-323): it is neither a candidate nor a penalty term of ``select_best_path_index``
+        (``free`` value 2 = excluded).  Returns ``(best, out)``: ``best`` indexes the FULL goal list (the device arrays in
+        ``out`` are full-size); ``out["best_filtered"]`` is the same path's index in the reference's filtered ``paths``
+        list (what ``MotionPlanner`` returns, :379-421); both ``None`` when nothing is free."""
         g = self.dev(goals_local)
         if g.dim() != 2 or g.shape[0] != 3:
             raise ValueError("goals_local must be [3, P]")
         opt = self.optimize_spirals(g[0], g[1], g[2], n_samples)
-        lat = self.sample_lattice(opt["p"][0], opt["p"][1], opt["p"][2], ego=ego, n_samples=n_samples)
-        free = self.collision_check_batch(lat["px"], lat["py"], None, obstacles, offsets, radii, trig=(lat["pcos"], lat["psin"]))
-        free = free & opt["valid"]
-        best = self.select_best_path_index_batch(lat["end_xy"][0], lat["end_xy"][1], free, goal_xy, weight)
+        lat = self.sample_lattice(opt["p"][0], opt["p"][1], opt["p"][2], ego=ego, n_samples=n_samples, want_trig=False)
+        free = self.collision_check_batch(lat["px"], lat["py"], lat["pyaw"], obstacles, offsets, radii)
+        state = torch.where(opt["valid"] != 0, free, torch.full_like(free, 2))
+        best = self.select_best_path_index_batch(lat["end_xy"][0], lat["end_xy"][1], state, goal_xy, weight)
         lat.update(opt)
-        lat["free"] = free
+        lat["free"] = free & opt["valid"]
+        lat["select_state"] = state
+        lat["best_filtered"] = None if best is None else int(opt["valid"][:best].sum().item())
         return best, lat
 
     def set_friction_mode(self, mode: str) -> str:
@@ -537,7 +595,8 @@ class Engine:
 
     def select_best_path_index_batch(self, end_x, end_y, free, goal_xy, weight: float, norm_mode: Optional[int] = None,
                                      want_scores: bool = False):
-        """``select_best_path_index`` on end points; returns ``int`` or ``None`` (synchronises)."""
+        """``select_best_path_index`` on end points; returns ``int`` or ``None`` (synchronises).  ``free``: bool, or
+        uint8 with 1 = free, 0 = colliding, 2 = excluded (dropped by the planner: no candidate, no penalty)."""
         ex, ey = self.dev(end_x), self.dev(end_y)
         fr = self.dev(free, torch.uint8) if not (isinstance(free, torch.Tensor) and free.dtype == torch.bool) \
             else free.to(self.tdev).to(torch.uint8)

@@ -213,3 +213,23 @@ def test_closed_loop_planner_flags_vs_literal(golden):
         assert np.array_equal(free, g["plan_flags"][f]), f
         best = cn.select_best_path_index(px[:, -1], py[:, -1], free, g["plan_goal"][f], wl.PATH_SELECT_WEIGHT)
         assert (-1 if best is None else best) == g["plan_best"][f], f
+
+
+def test_planner_core_with_dropped_paths_vs_literal(golden):
+    """plan_invalid.npz (literal plan_paths -> transform_paths -> collision_check -> select_best_path_index with
+    unreachable goals): the oracle pipeline applied to the FILTERED list reproduces flags and index, and treating a
+    dropped path as "excluded" in the full list (what the device does) picks the same path."""
+    g = golden("plan_invalid.npz")
+    mode = cn.probe_norm2_mode()
+    for c in range(int(g["n_cases"])):
+        validity, flags, want = g[f"c{c}_validity"], g[f"c{c}_flags"], int(g[f"c{c}_best"])
+        ends, goal = g[f"c{c}_ends"], g[f"c{c}_goal_state"]
+        assert len(flags) == int(validity.sum()) == len(ends)
+        if len(ends) == 0:
+            assert want == -1
+            continue
+        if mode is not None and mode == int(g["norm2_mode"]):
+            got, _ = c_oracle.select_best(ends[:, 0], ends[:, 1], flags, goal[:2], float(g["weight"]), mode)
+            assert (-1 if got is None else got) == want, c
+        got_np = cn.select_best_path_index(ends[:, 0], ends[:, 1], flags, goal[:2], float(g["weight"]))
+        assert (-1 if got_np is None else got_np) == want, c
