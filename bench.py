@@ -373,11 +373,28 @@ def run_gpu(args):
         t_m = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device=dev)
         dist.all_reduce(t_m, op=dist.ReduceOp.MAX)
         ms_plan = float(t_m.item()) / n_plans
+        # the kernels of one rank's shard alone (sample + rollout with cost + winner record; no collective, no host read)
+        pl = eng._mpc_planners[next(iter(eng._mpc_planners))]
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(n_plans):
+            eng.mpc_sample_controls_into(pl.delta, pl.torque, pl.seed, rollout0=pl.lo, delta_mean=cfg4["delta_mean"],
+                                         delta_sigma=cfg4["delta_sigma"], delta_clip=cfg4["delta_clip"],
+                                         torque_mean=cfg4["torque_mean"], torque_sigma=cfg4["torque_sigma"])
+            eng.rollout(pl.state0, pl.delta, pl.torque, pl.dt, pl.n_steps, hold=1, cost_ref=pl.cost_ref, w_u=cfg4["w_u"],
+                        u_ref=cfg4["u_ref"], state_broadcast=True, cost_out=pl.cost, state_out=pl.state_end)
+            eng.mpc_winner(pl.cost, pl.delta, pl.torque, index_offset=pl.lo, record_out=pl.rec)
+        k1.record()
+        barrier()
+        t_k = torch.tensor([k0.elapsed_time(k1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_k, op=dist.ReduceOp.MAX)
         mpc_sharded = {"value": cfg4["B"] * cfg4["n_steps"] / (ms_plan * 1e-3), "unit": UNIT, "ms_per_plan": ms_plan,
+                       "kernels_only_ms_per_plan": float(t_k.item()) / n_plans,
                        "sequences_total": cfg4["B"], "horizon": cfg4["n_steps"], "scaling": "strong", "n_gpus": world,
                        "best_index": int(plan["index"]), "best_cost": float(plan["cost"]), "owner_rank": int(plan["owner"]),
-                       "includes": "sampling + rollout with cost + argmin kernels, ONE NCCL all-gather of per-rank winner records "
-                                   "(cost, index, control sequence) and the host read of the winner"}
+                       "includes": "resident MpcPlanner: sampling + rollout with cost (broadcast start state) + winner-record kernels, ONE "
+                                   "NCCL all_gather_into_tensor of per-rank winner records (cost, index, control sequence) and one "
+                                   "pinned device->host read of the records, every plan synchronised on the host"}
 
     line = None
     if rank == 0:
@@ -708,20 +725,20 @@ def secondary_metrics(eng, wl, np, torch):
     # cost, lowest-index argmin; the controls are drawn on the device (Philox keyed by the global rollout index)
     cfg = wl.config4_mpc(B=1 << 20)
     Bm, Nm = cfg["B"], cfg["n_steps"]
-    s0m = eng.dev(cfg["state0"]).reshape(12, 1).expand(12, Bm).contiguous()
-    cref = eng.dev(cfg["cost_ref"])
-    for k in range(4):
-        if k == 3:
-            ev0.record()
-        dm, tm = eng.mpc_sample_controls(Bm, Nm, cfg["seed"])
-        r = eng.rollout(s0m, dm, tm, DT, Nm, hold=1, cost_ref=cref, w_u=cfg["w_u"], u_ref=cfg["u_ref"])
-        mn, ix = eng.argmin(r.cost)
-    ev1.record()
+    from python_motionplanning_b200 import distributed as D
+    pl = D.MpcPlanner(eng, cfg)
+    for _ in range(3):
+        plan = pl.plan()
     torch.cuda.synchronize()
-    out["mpc_sample_rollout_cost_argmin"] = {"value": Bm * Nm / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT, "ms": ev0.elapsed_time(ev1),
-                                             "sequences": Bm, "horizon": Nm, "best_index": int(ix.item()), "best_cost": float(mn.item()),
-                                             "includes": "control sampling kernel + rollout with running cost + argmin kernels"}
-    del dm, tm, r, s0m
+    t0 = time.perf_counter()
+    for _ in range(5):
+        plan = pl.plan()
+    ms_plan = (time.perf_counter() - t0) / 5 * 1e3
+    out["mpc_sample_rollout_cost_argmin"] = {"value": Bm * Nm / (ms_plan * 1e-3), "unit": UNIT, "ms": ms_plan,
+                                             "sequences": Bm, "horizon": Nm, "best_index": int(plan["index"]), "best_cost": float(plan["cost"]),
+                                             "includes": "resident MpcPlanner.plan(): control sampling + rollout with running cost (broadcast start "
+                                                         "state) + winner record kernels + the pinned read of the record, host-synchronised per plan"}
+    del pl, plan
     # config 5 (FP64 leg): 256 tyre-coefficient sets x 4,096 manoeuvres, per-rollout parameter sets (set-major), 100 steps
     sets, st5, dl5, tq5, ps5 = wl.config5_sweep()
     p5 = mp.VehicleParameters()

@@ -93,6 +93,8 @@ typedef struct B200mpRolloutArgs {
     const void *cost_ref;
     double w_u;
     double u_ref;
+    int state_broadcast;   /* 1: state0 is [12][1], one start state for every rollout (sampling MPC: no [12][B] copy) */
+    int friction_override; /* 0: the process-wide mode of b200mp_set_friction_mode; else 1 + B200MP_FRICTION_* for THIS launch */
 } B200mpRolloutArgs;
 
 int b200mp_version(void);
@@ -131,6 +133,14 @@ int b200mp_mpc_sample_controls_f64(int device, void *stream, int B, int n_seg, u
  * -1 when nothing is finite). */
 int b200mp_argmin_f64(int device, void *stream, long long n, const double *cost, long long index_offset,
                       double *min_out, long long *idx_out);
+
+/* Winner record of a sampling-MPC plan in ONE call: lowest-index argmin over cost[B] (NaN = +inf) and a gather of the
+ * winner's control sequence.  record dev [2 + 2 n_seg] = [min cost, global index = local index + index_offset (as a
+ * double, exact below 2^53; -1 when nothing is finite), delta[n_seg], torque[n_seg]] with delta / torque dev
+ * [n_seg][1][B] as written by b200mp_mpc_sample_controls_f64.  The records of the ranks are what one all-gather
+ * exchanges (python_motionplanning_b200/distributed.py). */
+int b200mp_mpc_winner_f64(int device, void *stream, long long B, int n_seg, const double *cost, const double *delta,
+                          const double *torque, long long index_offset, double *record);
 
 /* Circle-offset collision test for P paths at once: replaces Pool.starmap(collision_check, ...)
  * (local_planner.py:369-372) over CollisionChecker.collision_check (collision_checker.py:32-117).
@@ -263,6 +273,7 @@ typedef struct B200mpTrackArgs {
     int *target_idx;
     double *state_end;
     double *ctrl_end;
+    int friction_override; /* 0: the process-wide friction mode; else 1 + B200MP_FRICTION_* for THIS launch */
 } B200mpTrackArgs;
 #define B200MP_N_LOG 45 /* columns of the reference's DataLog (drive.py:44, plots.py:19-27) */
 int b200mp_track_closed_loop_f64(int device, void *stream, const B200mpTrackArgs *args);

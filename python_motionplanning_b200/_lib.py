@@ -33,7 +33,7 @@ class RolloutArgsC(C.Structure):
         ("delta_ch", C.c_int), ("torque_ch", C.c_int), ("ctrl_broadcast", C.c_int), ("store_stride", C.c_int),
         ("mu", C.c_void_p), ("param_set", C.c_void_p), ("traj", C.c_void_p), ("aux", C.c_void_p),
         ("state_end", C.c_void_p), ("cost", C.c_void_p), ("cost_in", C.c_void_p), ("cost_ref", C.c_void_p),
-        ("w_u", C.c_double), ("u_ref", C.c_double),
+        ("w_u", C.c_double), ("u_ref", C.c_double), ("state_broadcast", C.c_int), ("friction_override", C.c_int),
     ]
 
 
@@ -44,7 +44,7 @@ class TrackArgsC(C.Structure):
         (n, C.c_double) for n in ("dt", "target_vel", "k", "k_soft", "max_steer", "kp", "ki", "kd", "lookahead", "deadband",
                                   "steer_filter")] + [
         (n, C.c_void_p) for n in ("state0", "ctrl0", "waypoints", "wp_count", "traj", "log", "target_idx", "state_end",
-                                  "ctrl_end")]
+                                  "ctrl_end")] + [("friction_override", C.c_int)]
 
 
 # every symbol include/b200mp.h declares: name -> (restype, argtypes)
@@ -60,6 +60,7 @@ PROTOTYPES = {
     "b200mp_planar_model_f64": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200mp_mpc_sample_controls_f64": (_i, [_i, _vp, _i, _i, _ull, _ll, _d, _d, _d, _d, _d, _vp, _vp]),
     "b200mp_argmin_f64": (_i, [_i, _vp, _ll, _vp, _ll, _vp, _vp]),
+    "b200mp_mpc_winner_f64": (_i, [_i, _vp, _ll, _i, _vp, _vp, _vp, _ll, _vp]),
     "b200mp_collision_check_f64": (_i, [_i, _vp, _i, _i, _i, _dp, _dp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "b200mp_collision_check_yaw_f64": (_i, [_i, _vp, _i, _i, _i, _dp, _dp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i]),
     "b200mp_collision_resolve_f64": (_i, [_i, _vp, _i, _vp, _vp, _i, _i, _i, _dp, _dp, _vp, _vp, _i, _vp, _vp]),

@@ -43,25 +43,41 @@ int collision_mode() { return g_collision_mode.load(std::memory_order_relaxed); 
 
 DeviceState &dev_state(int device) { return g_states[(device >= 0 && device < kMaxDevices) ? device : 0]; }
 
-int ensure_scratch(int device, size_t bytes, void **out)
+int ensure_scratch(int device, cudaStream_t stream, size_t bytes, void **out)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     DeviceState &ds = dev_state(device);
     if (bytes < 4096) bytes = 4096;
-    ds.cull_stats_valid = false;   // whoever asks is about to overwrite the area (the broad-phase launcher re-arms it)
-    if (ds.scratch_bytes < bytes) {
-        if (ds.scratch) {
-            // a larger area is needed: wait for work that may still use the old one
-            B200MP_CUDA(cudaDeviceSynchronize());
-            B200MP_CUDA(cudaFree(ds.scratch));
-            ds.scratch = nullptr;
-            ds.scratch_bytes = 0;
+    if (ds.cull_stats_stream == stream) ds.cull_stats_ptr = nullptr;   // this stream's area is about to be overwritten
+    DeviceState::Scratch *slot = nullptr, *lru = nullptr;
+    for (auto &sc : ds.scratch) {
+        if (sc.used && sc.stream == stream) slot = &sc;
+        if (!lru || (!sc.used && lru->used) || (sc.used == lru->used && sc.last_use < lru->last_use)) lru = &sc;
+    }
+    if (!slot) {
+        slot = lru;
+        if (slot->used) {
+            // more streams than slots: the least recently used area changes hands once its stream has drained
+            B200MP_CUDA(cudaStreamSynchronize(slot->stream));
+            if (ds.cull_stats_stream == slot->stream) ds.cull_stats_ptr = nullptr;
+        }
+        slot->stream = stream;
+        slot->used = true;
+    }
+    slot->last_use = ++ds.scratch_clock;
+    if (slot->bytes < bytes) {
+        if (slot->ptr) {
+            // a larger area is needed: wait for the work of this stream that may still use the old one
+            B200MP_CUDA(cudaStreamSynchronize(stream));
+            B200MP_CUDA(cudaFree(slot->ptr));
+            slot->ptr = nullptr;
+            slot->bytes = 0;
         }
         const size_t want = bytes + bytes / 2;
-        B200MP_CUDA(cudaMalloc(&ds.scratch, want));
-        ds.scratch_bytes = want;
+        B200MP_CUDA(cudaMalloc(&slot->ptr, want));
+        slot->bytes = want;
     }
-    *out = ds.scratch;
+    *out = slot->ptr;
     return 0;
 }
 
@@ -302,6 +318,13 @@ int b200mp_argmin_f64(int device, void *stream, long long n, const double *cost,
     return launch_argmin_f64(device, (cudaStream_t)stream, n, cost, index_offset, min_out, idx_out);
 }
 
+int b200mp_mpc_winner_f64(int device, void *stream, long long B, int n_seg, const double *cost, const double *delta,
+                          const double *torque, long long index_offset, double *record)
+{
+    B200MP_ENTER(device);
+    return launch_mpc_winner_f64(device, (cudaStream_t)stream, B, n_seg, cost, delta, torque, index_offset, record);
+}
+
 int b200mp_collision_check_f64(int device, void *stream, int P, int n_pts, int n_circ, const double *off,
                                const double *rad, const double *px, const double *py, const double *pcos,
                                const double *psin, const double *pyaw, int yaw_stride, int M, const double *obs,
@@ -423,12 +446,15 @@ int b200mp_shutdown(void)
     (void)cudaGetDevice(&prev);
     for (int d = 0; d < n && d < kMaxDevices; ++d) {
         DeviceState &ds = g_states[d];
-        if (!ds.table64 && !ds.table32 && !ds.scratch && !ds.sched_ring && !ds.mu_table && !ds.set_tables) continue;
+        bool any_scratch = false;
+        for (auto &sc : ds.scratch) any_scratch = any_scratch || sc.ptr;
+        if (!ds.table64 && !ds.table32 && !any_scratch && !ds.sched_ring && !ds.mu_table && !ds.set_tables) continue;
         if (cudaSetDevice(d) != cudaSuccess) continue;
         (void)cudaDeviceSynchronize();
         if (ds.table64) (void)cudaFree(ds.table64);
         if (ds.table32) (void)cudaFree(ds.table32);
-        if (ds.scratch) (void)cudaFree(ds.scratch);
+        for (auto &sc : ds.scratch)
+            if (sc.ptr) (void)cudaFree(sc.ptr);
         if (ds.mu_table) (void)cudaFree(ds.mu_table);
         if (ds.mu_table_f32) (void)cudaFree(ds.mu_table_f32);
         if (ds.set_tables) (void)cudaFree(ds.set_tables);

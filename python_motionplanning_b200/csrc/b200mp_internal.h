@@ -42,11 +42,22 @@ struct DeviceState {
     float *set_tables_f32 = nullptr;   // FP32 twins [n_sets][kMuTableFloats]; a set has one iff set_B2 > 0 (both are built or neither)
     double *set_B2 = nullptr;
     int set_tables_n = 0;
-    void *scratch = nullptr;
-    size_t scratch_bytes = 0;
-    // where the broad-phase statistics of the last collision launch sit in `scratch`; cleared by every other scratch user
-    size_t cull_stats_offset = 0;
-    bool cull_stats_valid = false;
+    // scratch areas, ONE PER STREAM that has asked for one (the ABI is asynchronous on the caller's stream, so two calls
+    // on different streams of one device must not share an area while their kernels are in flight); work on one stream
+    // is ordered, so an area is reused by the next call on the same stream without synchronisation
+    static constexpr int kScratchStreams = 8;
+    struct Scratch {
+        cudaStream_t stream = nullptr;
+        void *ptr = nullptr;
+        size_t bytes = 0;
+        unsigned long long last_use = 0;
+        bool used = false;
+    };
+    Scratch scratch[kScratchStreams];
+    unsigned long long scratch_clock = 0;
+    // where the broad-phase statistics of the last collision launch sit; cleared by the next scratch user of that stream
+    void *cull_stats_ptr = nullptr;
+    cudaStream_t cull_stats_stream = nullptr;
     // ring of small work-queue areas for time-sliced rollout launches (one per launch in flight)
     void *sched_ring = nullptr;
     cudaEvent_t sched_event[kSchedSlots] = {};
@@ -54,7 +65,8 @@ struct DeviceState {
     int sched_next = 0;
 };
 DeviceState &dev_state(int device);
-int ensure_scratch(int device, size_t bytes, void **out);
+// a device area of at least `bytes` owned by (device, stream) until the next ensure_scratch on that stream
+int ensure_scratch(int device, cudaStream_t stream, size_t bytes, void **out);
 // A zero-initialisable kSchedSlotBytes device area that no launch still in flight is using; the caller
 // records `*done` on its stream after the launch that uses the area.
 int acquire_sched_slot(int device, void **area, cudaEvent_t *done);
@@ -102,6 +114,8 @@ int argmin_launch(cudaStream_t st, long long n, const double *cost, long long in
 int launch_mpc_sample_f64(cudaStream_t st, int B, int n_seg, unsigned long long seed, long long rollout0,
                           double delta_mean, double delta_sigma, double delta_clip, double torque_mean,
                           double torque_sigma, double *delta, double *torque);
+int launch_mpc_winner_f64(int device, cudaStream_t st, long long B, int n_seg, const double *cost, const double *delta,
+                          const double *torque, long long index_offset, double *record);
 int run_fma_peak(int dtype_bits, int reps, double *tflops_out);
 int launch_lattice_f64(int device, cudaStream_t st, int P, int n_samples, const double *k1, const double *k2,
                        const double *sf, const double *ego_x, const double *ego_y, const double *ego_yaw,

@@ -249,6 +249,14 @@ template <> struct Math<double> {
         return true;
 #endif
     }
+    // sin e, cos e of a small increment alone (the caller works in the frame of the step's heading)
+    static B200MP_HD bool small_sincos_core(double e, double *se, double *ce)
+    {
+        const double u = e * e;
+        *se = fma(e * u, -1.0 / 6, e);
+        *ce = fma(u, fma(u, 1.0 / 24, -0.5), 1.0);
+        return ::fabs(e) <= 0.0009765625;
+    }
     static B200MP_HD bool rotate_core(double sa, double ca, double e, double *s, double *c)
     {
         const double u = e * e;
@@ -409,6 +417,13 @@ template <> struct Math<float> {
             *c = ::cosf(x);
 #endif
         }
+    }
+    static B200MP_HD bool small_sincos_core(float e, float *se, float *ce)
+    {
+        const float u = e * e;
+        *se = fmaf(e * u, -1.0f / 6, e);
+        *ce = fmaf(u, fmaf(u, 1.0f / 24, -0.5f), 1.0f);
+        return ::fabsf(e) <= 0.015625f;
     }
     static B200MP_HD bool rotate_core(float sa, float ca, float e, float *s, float *c)
     {

@@ -811,7 +811,7 @@ static int launch_collision_nc(int device, cudaStream_t st, int P, int n_pts, co
     const int grid = (int)((items + kColBlock - 1) / kColBlock);
     if (min_clear) {
         void *scratch = nullptr;
-        int rc = ensure_scratch(device, sizeof(double) * (size_t)items, &scratch);
+        int rc = ensure_scratch(device, st, sizeof(double) * (size_t)items, &scratch);
         if (rc) return rc;
         if (mode == B200MP_COLLISION_FP64_ONLY)
             collision_kernel<NC, true><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
@@ -837,7 +837,7 @@ static int launch_collision_nc(int device, cudaStream_t st, int P, int n_pts, co
         const int n_chunks = (M + 31) / 32;
         const size_t pts_bytes = sizeof(float2) * 32 * (size_t)n_chunks, box_bytes = sizeof(float4) * (size_t)n_chunks;
         void *scratch = nullptr;
-        int rc = ensure_scratch(device, pts_bytes + box_bytes + sizeof(ObsPrep), &scratch);
+        int rc = ensure_scratch(device, st, pts_bytes + box_bytes + sizeof(ObsPrep), &scratch);
         if (rc) return rc;
         float2 *pts = (float2 *)scratch;
         float4 *boxes = (float4 *)((char *)scratch + pts_bytes);
@@ -853,23 +853,23 @@ static int launch_collision_nc(int device, cudaStream_t st, int P, int n_pts, co
                                                                      M, (const double2 *)obs, pts, boxes, prep, free_out, yf);
         // the statistics of THIS launch sit at this offset until the next user of the scratch area overwrites them
         DeviceState &ds = dev_state(device);
-        ds.cull_stats_offset = pts_bytes + box_bytes;
-        ds.cull_stats_valid = true;
+        ds.cull_stats_ptr = prep;
+        ds.cull_stats_stream = st;
     }
     B200MP_CUDA(cudaGetLastError());
     return 0;
 }
 
 // last launch's broad-phase statistics (synchronises the stream); zeros unless the broad-phase kernel was the last
-// user of the device's scratch area
+// user of this stream's scratch area
 int collision_stats(int device, cudaStream_t st, int M, unsigned long long out[2])
 {
     (void)M;
     DeviceState &ds = dev_state(device);
     out[0] = out[1] = 0;
-    if (!ds.scratch || !ds.cull_stats_valid) return 0;
+    if (!ds.cull_stats_ptr || ds.cull_stats_stream != st) return 0;
     ObsPrep h;
-    B200MP_CUDA(cudaMemcpyAsync(&h, (char *)ds.scratch + ds.cull_stats_offset, sizeof(h), cudaMemcpyDeviceToHost, st));
+    B200MP_CUDA(cudaMemcpyAsync(&h, ds.cull_stats_ptr, sizeof(h), cudaMemcpyDeviceToHost, st));
     B200MP_CUDA(cudaStreamSynchronize(st));
     out[0] = h.screened;
     out[1] = h.rechecked;
@@ -1033,7 +1033,7 @@ int launch_select_best_f64(int device, cudaStream_t st, int P, const double *ex,
     // scratch: [P] scores (when the caller does not want them) followed by the argmin partials
     void *scratch = nullptr;
     const size_t score_bytes = (sizeof(double) * (size_t)P + 255) & ~(size_t)255;
-    int rc = ensure_scratch(device, score_bytes + argmin_scratch_bytes(P), &scratch);
+    int rc = ensure_scratch(device, st, score_bytes + argmin_scratch_bytes(P), &scratch);
     if (rc) return rc;
     double *scores = scores_out ? scores_out : (double *)scratch;
     if (P > 0) {

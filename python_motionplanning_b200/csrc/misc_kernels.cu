@@ -89,6 +89,30 @@ argmin_final_kernel(int n_partial, const MinIdx *__restrict__ partial, long long
     }
 }
 
+// argmin_final_kernel + gather of the winner's control sequence into one record (see b200mp_mpc_winner_f64)
+__global__ void __launch_bounds__(kArgminBlock)
+mpc_winner_final_kernel(int n_partial, const MinIdx *__restrict__ partial, long long index_offset, long long B, int n_seg,
+                        const double *__restrict__ delta, const double *__restrict__ torque, double *__restrict__ record)
+{
+    __shared__ long long s_win;
+    MinIdx m;
+    m.v = INFINITY;
+    m.i = -1;
+    for (int i = threadIdx.x; i < n_partial; i += kArgminBlock) m = better(m, partial[i]);
+    m = block_min(m);
+    if (threadIdx.x == 0) {
+        s_win = m.i;
+        record[0] = m.i < 0 ? INFINITY : m.v;
+        record[1] = m.i < 0 ? -1.0 : (double)(m.i + index_offset);
+    }
+    __syncthreads();
+    const long long w = s_win;
+    for (int s = threadIdx.x; s < n_seg; s += kArgminBlock) {
+        record[2 + s] = w < 0 ? 0.0 : delta[(size_t)s * B + w];
+        record[2 + n_seg + s] = w < 0 ? 0.0 : torque[(size_t)s * B + w];
+    }
+}
+
 static int argmin_blocks(long long n)
 {
     long long b = (n + kArgminBlock - 1) / kArgminBlock;
@@ -118,9 +142,27 @@ int launch_argmin_f64(int device, cudaStream_t st, long long n, const double *co
         return B200MP_E_ARG;
     }
     void *scratch = nullptr;
-    int rc = ensure_scratch(device, argmin_scratch_bytes(n), &scratch);
+    int rc = ensure_scratch(device, st, argmin_scratch_bytes(n), &scratch);
     if (rc) return rc;
     return argmin_launch(st, n, cost, index_offset, scratch, min_out, idx_out, nullptr);
+}
+
+int launch_mpc_winner_f64(int device, cudaStream_t st, long long B, int n_seg, const double *cost, const double *delta,
+                          const double *torque, long long index_offset, double *record)
+{
+    if (B < 1 || n_seg < 0 || !cost || !record || (n_seg > 0 && (!delta || !torque))) {
+        set_error("mpc_winner: bad arguments (B=%lld, n_seg=%d)", B, n_seg);
+        return B200MP_E_ARG;
+    }
+    void *scratch = nullptr;
+    int rc = ensure_scratch(device, st, argmin_scratch_bytes(B), &scratch);
+    if (rc) return rc;
+    const int nb = argmin_blocks(B);
+    argmin_partial_kernel<<<nb, kArgminBlock, 0, st>>>(B, cost, (MinIdx *)scratch);
+    B200MP_CUDA(cudaGetLastError());
+    mpc_winner_final_kernel<<<1, kArgminBlock, 0, st>>>(nb, (const MinIdx *)scratch, index_offset, B, n_seg, delta, torque, record);
+    B200MP_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // --------------------------------------------------------------------------- MPC control sampling

@@ -52,7 +52,9 @@ template <typename R> struct RolloutDev {
     R dt;
     const R *state0, *delta, *torque, *mu;
     size_t ctrl_bstride;  // B, or 0 when one control sequence is broadcast to all rollouts
+    int state_broadcast;  // 1: state0 is [12][1], shared by every rollout
     const int *param_set;
+    int n_sets;           // parameter sets in `table`: a param_set entry outside [0, n_sets) is clamped (never read out of bounds)
     const DevParams<R> *table;
     R *traj, *aux, *state_end, *cost;
     const R *cost_in, *cost_ref;
@@ -67,7 +69,11 @@ template <typename R> struct RolloutDev {
 // thread 14 warps fit on an SM and the batch is exactly one wave (no tail); above that the second wave
 // runs at 15 % occupancy.  Tunables are macros so tools/kbench can sweep them.
 #ifndef B200MP_ROLLOUT_BLOCK
+#if B200MP_MU_DEG5
+#define B200MP_ROLLOUT_BLOCK 128   /* 96 KB friction table per CTA: two CTAs per SM */
+#else
 #define B200MP_ROLLOUT_BLOCK 64
+#endif
 #endif
 #ifndef B200MP_ROLLOUT_MAXNREG
 #define B200MP_ROLLOUT_MAXNREG 0
@@ -100,7 +106,10 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
 {
     __shared__ int s_item, s_set, s_cur_set;
     constexpr int kTabWords = MuTab<R>::kBytes / 8;
-    __shared__ __align__(16) double s_mu[TAB ? kTabWords : 2];
+    // the friction table is DYNAMIC shared memory (48 KB in FP64: with the three words above it is past the static limit);
+    // launches pass MuTab<R>::kBytes for TAB kernels and 0 otherwise
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    double *s_mu = reinterpret_cast<double *>(s_dyn);
     MuTableView T;
     T.c = s_mu;
     T.B2 = a.mu_B2;
@@ -139,7 +148,7 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
         // otherwise it takes the closed-form step.  The choice is uniform over the CTA.
         bool use_tab = TAB && !GENERIC;
         if (TAB && GENERIC) {
-            const int myset = r < a.B ? (a.param_set ? a.param_set[r] : 0) : -1;
+            const int myset = r < a.B ? (a.param_set ? min(max(a.param_set[r], 0), a.n_sets - 1) : 0) : -1;
             if (threadIdx.x == 0) s_set = myset;
             __syncthreads();
             const int set0 = s_set, cur = s_cur_set;
@@ -159,10 +168,11 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
         if (r < a.B) {
             R y[10], ax, ay;
             if (!SLICED || chunk_idx == 0) {
+                const size_t sB = a.state_broadcast ? 1 : B, sr = a.state_broadcast ? 0 : (size_t)r;
 #pragma unroll
-                for (int c = 0; c < 10; ++c) y[c] = a.state0[c * B + r];
-                ax = a.state0[10 * B + r];
-                ay = a.state0[11 * B + r];
+                for (int c = 0; c < 10; ++c) y[c] = a.state0[c * sB + sr];
+                ax = a.state0[10 * sB + sr];
+                ay = a.state0[11 * sB + sr];
             } else {   // carried state, written by another SM: read through L2
 #pragma unroll
                 for (int c = 0; c < 10; ++c) y[c] = __ldcg(a.state_end + c * B + r);
@@ -174,7 +184,7 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
             DevParams<R> Pl;
             R Dl[4];
             if (GENERIC) {
-                Pl = a.param_set ? a.table[a.param_set[r]] : P0;
+                Pl = a.param_set ? a.table[min(max(a.param_set[r], 0), a.n_sets - 1)] : P0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) Dl[i] = a.mu ? a.mu[i * B + r] : Pl.Dc[i];   // vehicle_model.py:232-235
             }
@@ -320,25 +330,44 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
     }
 }
 
+// zero-step launch with a broadcast start state: state_end[c][r] = state0[c] (the state "passes through")
+template <typename R> __global__ void broadcast_state_kernel(int B, const R *__restrict__ s0, R *__restrict__ out)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) out[(size_t)c * B + r] = s0[c];
+}
+
 // Resident CTAs per device for one kernel instantiation (cached per function pointer).
-template <typename K> static int resident_ctas(K kernel, int *out)
+template <typename K> static int resident_ctas(K kernel, size_t smem, int *out)
 {
     int dev = 0, sms = 0, occ = 0;
     B200MP_CUDA(cudaGetDevice(&dev));
     B200MP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    B200MP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kRolloutBlock, 0));
+    B200MP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kRolloutBlock, smem));
     *out = sms * (occ > 0 ? occ : 1);
+    return 0;
+}
+
+// dynamic shared memory beyond the default 48 KB carve-out needs a per-function opt-in (once per function and device)
+template <typename K> static int allow_dynamic_smem(K kernel, size_t smem)
+{
+    if (smem == 0) return 0;
+    B200MP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return 0;
 }
 
 // Chooses the time slicing of a launch (see SliceSched) and starts the kernel.
 template <typename R, typename K>
 static int start_rollout(K kernel, K kernel_sliced, int device, cudaStream_t st, const RolloutDev<R> &a,
-                         const DevParams<R> &P0)
+                         const DevParams<R> &P0, size_t smem)
 {
     const int n_blocks = (a.B + kRolloutBlock - 1) / kRolloutBlock;
     int resident = 0;
-    int rc = resident_ctas(kernel_sliced, &resident);
+    int rc = allow_dynamic_smem(kernel, smem);
+    if (!rc) rc = allow_dynamic_smem(kernel_sliced, smem);
+    if (!rc) rc = resident_ctas(kernel_sliced, smem, &resident);
     if (rc) return rc;
     SliceSched sc{nullptr, nullptr, n_blocks, 1, a.n_steps};
     // slice only when the batch is more than one wave but too few waves for the tail to vanish
@@ -369,9 +398,9 @@ static int start_rollout(K kernel, K kernel_sliced, int device, cudaStream_t st,
         grid = n_blocks * sc.n_chunks < resident ? n_blocks * sc.n_chunks : resident;
     }
     if (sc.n_chunks > 1)
-        kernel_sliced<<<grid, kRolloutBlock, 0, st>>>(a, P0, sc);
+        kernel_sliced<<<grid, kRolloutBlock, smem, st>>>(a, P0, sc);
     else
-        kernel<<<grid, kRolloutBlock, 0, st>>>(a, P0, sc);
+        kernel<<<grid, kRolloutBlock, smem, st>>>(a, P0, sc);
     cudaError_t e = cudaGetLastError();
     if (sched_mem) {
         cudaError_t e2 = cudaEventRecord(sched_done, st);
@@ -410,11 +439,22 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
         set_error("rk4_rollout: no parameter table on device %d (call b200mp_set_params first)", device);
         return B200MP_E_PARAMS;
     }
+    if (g.friction_override < 0 || g.friction_override > 2 || (g.state_broadcast != 0 && g.state_broadcast != 1)) {
+        set_error("rk4_rollout: friction_override must be 0..2 and state_broadcast 0 or 1 (got %d, %d)", g.friction_override,
+                  g.state_broadcast);
+        return B200MP_E_ARG;
+    }
     if (g.B == 0 || g.n_steps == 0) {
-        if (g.B > 0 && g.state_end != g.state0)
-            B200MP_CUDA(cudaMemcpyAsync(g.state_end, g.state0, sizeof(R) * 12 * (size_t)g.B, cudaMemcpyDeviceToDevice, st));
+        if (g.B > 0 && g.state_end != g.state0) {
+            if (g.state_broadcast) {
+                broadcast_state_kernel<R><<<(g.B + 255) / 256, 256, 0, st>>>(g.B, (const R *)g.state0, (R *)g.state_end);
+                B200MP_CUDA(cudaGetLastError());
+            } else
+                B200MP_CUDA(cudaMemcpyAsync(g.state_end, g.state0, sizeof(R) * 12 * (size_t)g.B, cudaMemcpyDeviceToDevice, st));
+        }
         return 0;
     }
+    const int fmode = g.friction_override ? g.friction_override - 1 : friction_mode();
     RolloutDev<R> a;
     a.B = g.B;
     a.n_steps = g.n_steps;
@@ -428,7 +468,9 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
     a.torque = (const R *)g.torque;
     a.mu = (const R *)g.mu;
     a.ctrl_bstride = g.ctrl_broadcast ? 0 : (size_t)g.B;
+    a.state_broadcast = g.state_broadcast;
     a.param_set = g.param_set;
+    a.n_sets = ds.n_sets;
     a.table = sizeof(R) == 8 ? (const DevParams<R> *)ds.table64 : (const DevParams<R> *)ds.table32;
     a.traj = (R *)g.traj;
     a.aux = (R *)g.aux;
@@ -451,21 +493,23 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
     const bool aux = g.aux != nullptr;
     // tabulated friction: FP64 fast path only, when set_params could build the table of set 0
     const bool have_table = sizeof(R) == 8 ? (ds.mu_table && ds.mu_table_B2 > 0.0) : ds.mu_table_f32_ok;
-    const bool tab = !generic && !aux && have_table && friction_mode() == B200MP_FRICTION_AUTO;
+    const bool tab = !generic && !aux && have_table && fmode == B200MP_FRICTION_AUTO;
     a.mu_table = sizeof(R) == 8 ? (const void *)ds.mu_table : (const void *)ds.mu_table_f32;
     a.mu_B2 = ds.mu_table_B2;
     a.set_tables = sizeof(R) == 8 ? (const void *)ds.set_tables : (const void *)ds.set_tables_f32;
     a.set_B2 = ds.set_B2;
     // per-set tables: generic FP64 launches whose blocks turn out to be set-uniform take the tabulated step
     const bool set_tables_ok = ds.set_tables && ds.set_tables_f32 && ds.set_tables_n == ds.n_sets &&
-                               friction_mode() == B200MP_FRICTION_AUTO;
+                               fmode == B200MP_FRICTION_AUTO;
     const bool tabg = generic && !aux && set_tables_ok;
     // FP64 logging launches that store a subset of the steps: tabulated step between the stored ones
     const bool tab_aux = aux && sizeof(R) == 8 && set_tables_ok && g.store_stride > 1;
 #define B200MP_START2(REAR0, GENERIC, AUX, TAB, COST) \
-    start_rollout<R>(rk4_rollout_kernel<R, REAR0, GENERIC, AUX, false, TAB, COST>, rk4_rollout_kernel<R, REAR0, GENERIC, AUX, true, TAB, COST>, device, st, a, P0)
+    start_rollout<R>(rk4_rollout_kernel<R, REAR0, GENERIC, AUX, false, TAB, COST>, rk4_rollout_kernel<R, REAR0, GENERIC, AUX, true, TAB, COST>, device, st, a, P0, \
+                     (TAB) ? (size_t)MuTab<R>::kBytes : (size_t)0)
 #define B200MP_START_H1(TAB, COST) \
-    start_rollout<R>(rk4_rollout_kernel<R, true, false, false, false, TAB, COST, true>, rk4_rollout_kernel<R, true, false, false, true, TAB, COST, true>, device, st, a, P0)
+    start_rollout<R>(rk4_rollout_kernel<R, true, false, false, false, TAB, COST, true>, rk4_rollout_kernel<R, true, false, false, true, TAB, COST, true>, device, st, a, P0, \
+                     (TAB) ? (size_t)MuTab<R>::kBytes : (size_t)0)
 #define B200MP_START(REAR0, GENERIC, AUX, TAB) \
     ((AUX) || g.cost ? B200MP_START2(REAR0, GENERIC, AUX, TAB, true) : B200MP_START2(REAR0, GENERIC, AUX, TAB, (AUX)))
     if (aux && tab_aux) return rear0 ? B200MP_START(true, true, true, (sizeof(R) == 8)) : B200MP_START(false, true, true, (sizeof(R) == 8));
@@ -500,13 +544,13 @@ int launch_rollout_f32(int device, cudaStream_t st, const B200mpRolloutArgs &a) 
 __global__ void __launch_bounds__(128)
 planar_model_kernel(int B, const double *__restrict__ state, const double *__restrict__ torque,
                     const double *__restrict__ mu, const double *__restrict__ delta, const double *__restrict__ axay,
-                    const int *__restrict__ param_set, const DevParams<double> *__restrict__ table,
+                    const int *__restrict__ param_set, int n_sets, const DevParams<double> *__restrict__ table,
                     double *__restrict__ state_dot, double *__restrict__ misc, double *__restrict__ outputs)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= B) return;
     const size_t Bs = (size_t)B;
-    const DevParams<double> P = table[param_set ? param_set[r] : 0];
+    const DevParams<double> P = table[param_set ? min(max(param_set[r], 0), n_sets - 1) : 0];   // clamped: never out of bounds
     double y[10], D[4], dl[4], tau[4], Fz[4], k[10], out[18], axc, ayc;
     WheelCtrl<double> c;
     for (int i = 0; i < 10; ++i) y[i] = state[i * Bs + r];
@@ -549,7 +593,7 @@ int launch_planar_model_f64(int device, cudaStream_t st, int B, const double *st
         return B200MP_E_PARAMS;
     }
     if (B == 0) return 0;
-    planar_model_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, state, torque, mu, delta, axay, param_set, ds.table64,
+    planar_model_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, state, torque, mu, delta, axay, param_set, ds.n_sets, ds.table64,
                                                         state_dot, misc, outputs);
     B200MP_CUDA(cudaGetLastError());
     return 0;

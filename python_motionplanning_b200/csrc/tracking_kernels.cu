@@ -298,7 +298,8 @@ template <bool LOG, bool TAB>
 __global__ void __launch_bounds__(kTrackBlock)
 track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevParams<double> P0)
 {
-    __shared__ __align__(16) double s_mu[TAB ? kMuTableDoubles : 2];
+    extern __shared__ __align__(16) unsigned char s_dyn[];   // the friction table (dynamic: 48 KB and more)
+    double *s_mu = reinterpret_cast<double *>(s_dyn);
     MuTableView T;
     T.c = s_mu;
     T.B2 = a.mu_B2;
@@ -474,7 +475,7 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     const size_t per = (size_t)g.n_sets * (size_t)(g.w_max > 0 ? g.w_max : 1);
     const int heads_stride = (g.w_max + kFine - 1) / kFine + (g.w_max + kCoarse - 1) / kCoarse + 1;
     void *scratch = nullptr;
-    int rc = ensure_scratch(device, sizeof(double) * (3 * per + 4 * (size_t)g.n_sets + 2) + sizeof(double2) * (size_t)g.n_sets * (size_t)heads_stride, &scratch);
+    int rc = ensure_scratch(device, st, sizeof(double) * (3 * per + 4 * (size_t)g.n_sets + 2) + sizeof(double2) * (size_t)g.n_sets * (size_t)heads_stride, &scratch);
     if (rc) return rc;
     TrackDev a;
     a.V = g.V;
@@ -526,13 +527,19 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     }
     a.mu_table = ds.mu_table;
     a.mu_B2 = ds.mu_table_B2;
-    const bool tab = ds.mu_table && ds.mu_table_B2 > 0.0 && friction_mode() == B200MP_FRICTION_AUTO;
+    const int fmode = (g.friction_override >= 1 && g.friction_override <= 2) ? g.friction_override - 1 : friction_mode();
+    const bool tab = ds.mu_table && ds.mu_table_B2 > 0.0 && fmode == B200MP_FRICTION_AUTO;
+    const size_t smem = sizeof(double) * kMuTableDoubles;
+    if (tab) {   // dynamic shared memory beyond 48 KB is an opt-in per function
+        B200MP_CUDA(cudaFuncSetAttribute(track_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200MP_CUDA(cudaFuncSetAttribute(track_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     if (g.log && tab && g.store_stride > 1)   // logging launch that stores a subset of the steps
-        track_kernel<true, true><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
+        track_kernel<true, true><<<(int)grid, kTrackBlock, smem, st>>>(a, P0);
     else if (g.log)
         track_kernel<true, false><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
     else if (tab)
-        track_kernel<false, true><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
+        track_kernel<false, true><<<(int)grid, kTrackBlock, smem, st>>>(a, P0);
     else
         track_kernel<false, false><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
     B200MP_CUDA(cudaGetLastError());

@@ -85,25 +85,57 @@ template <typename R> inline DevParams<R> derive_params(const HostParams &p)
 // realistic B; 896 rows = 42 KB); anything outside, NaN included, clears the speculative step's `ok` flag
 // and the step is repeated on the closed-form path.
 // Cost per wheel-stage from q = sx^2 + sy^2 on: 7 FP64 instructions + 2 conversions instead of 49.
-constexpr int kMuBits = 6;                                // leading mantissa bits used for the interval index
-constexpr int kMuPerBinade = 1 << kMuBits;                // 64
+// B200MP_MU_DEG5: 128 intervals per binade and a degree-5 polynomial entirely in FP64 (5 DFMA, six doubles per row, no
+// FP32 tail: two F2F conversions and two FFMA fewer per wheel-stage for one more DFMA); the table is twice as large
+// (96 KB with MASKIDX), so the rollout kernels then run 128-thread CTAs, two per SM.
+#ifndef B200MP_MU_DEG5
+#define B200MP_MU_DEG5 0
+#endif
+constexpr bool kMuDeg5 = B200MP_MU_DEG5 != 0;
+constexpr int kMuBits = kMuDeg5 ? 7 : 6;                  // leading mantissa bits used for the interval index
+constexpr int kMuPerBinade = 1 << kMuBits;                // 64 (128)
 constexpr int kMuBinades = 14;
-constexpr int kMuIntervals = kMuPerBinade * kMuBinades;   // 896 rows = 42 KB
-constexpr int kMuCoefD = 4;                               // degrees 0..3 in FP64
-constexpr int kMuCoefF = 3;                               // degrees 4..6 in FP32
-constexpr int kMuCoef = kMuCoefD + kMuCoefF;              // degree 6
+constexpr int kMuIntervals = kMuPerBinade * kMuBinades;   // 896 rows = 42 KB (1,792 rows = 84 KB)
+constexpr int kMuCoefD = kMuDeg5 ? 6 : 4;                 // degrees 0..3 (0..5) in FP64
+constexpr int kMuCoefF = kMuDeg5 ? 0 : 3;                 // degrees 4..6 in FP32
+constexpr int kMuCoef = kMuCoefD + kMuCoefF;              // degree 6 (5)
 constexpr int kMuStride = 6;                              // row stride in doubles (48 bytes)
-constexpr int kMuTableDoubles = kMuIntervals * kMuStride;
+// Row addressing.  MASKIDX: the row of x is selected by the raw bit field [low 4 exponent bits | kMuBits leading mantissa
+// bits] of x (one LOP3), its byte offset is one IMAD.HI of that field, and the table holds 16 binades' worth of rows in
+// the order of that field (row = ((e + 15) & 15) * 64 + m for x in binade e; the two unused binades are zero rows) --
+// 48 KB instead of 42 KB, but no subtract / shift / clamp-select per wheel-stage: whatever the bits of x are, the
+// address is inside the table, and "x is in the tabulated range" is a single unsigned compare of the high word.
+#ifndef B200MP_MU_MASKIDX
+#define B200MP_MU_MASKIDX 0
+#endif
+constexpr bool kMuMaskIdx = B200MP_MU_MASKIDX != 0;
+constexpr int kMuRows = kMuMaskIdx ? (16 << kMuBits) : kMuIntervals;
+constexpr int kMuTableDoubles = kMuRows * kMuStride;
+constexpr int kMuKeyShift = 20 - kMuBits;
+constexpr unsigned kMuKeyMask = (unsigned)((16 << kMuBits) - 1) << kMuKeyShift;
+constexpr unsigned kMuKeyToBytes = (unsigned)(kMuStride * 8) << (32 - kMuKeyShift);   // umulhi(key, .) = row * 48
+static_assert((unsigned long long)(kMuStride * 8) << (32 - kMuKeyShift) < (1ull << 32), "byte-offset multiplier must fit 32 bits");
+// memory row of interval k = e * kMuPerBinade + m
+inline constexpr int mu_row_of(int k)
+{
+    return kMuMaskIdx ? (((((k >> kMuBits) + 15) & 15) << kMuBits) | (k & (kMuPerBinade - 1))) : k;
+}
 #ifndef B200MP_MU_CACHE_ROWS
 #define B200MP_MU_CACHE_ROWS 1
 #endif
 constexpr bool kMuCacheRows = B200MP_MU_CACHE_ROWS != 0;
 
 // One table row as it sits in memory (16-byte aligned, loaded as three 128-bit words).
+#if B200MP_MU_DEG5
+struct alignas(16) MuRow {
+    double c3, c2, c1, c0, c5, c4;
+};
+#else
 struct alignas(16) MuRow {
     double c3, c2, c1, c0;
     float c6, c5, c4, pad;
 };
+#endif
 static_assert(sizeof(MuRow) == kMuStride * sizeof(double), "MuRow must be 48 bytes");
 
 struct MuTableView {
@@ -114,23 +146,44 @@ struct MuTableView {
 // Evaluation of one table row exactly as the device does it (also used by the host audit and hostsim).
 B200MP_HD double mu_row_eval(const MuRow &r, double t)
 {
+#if B200MP_MU_DEG5
+    return fma(fma(fma(fma(fma(r.c5, t, r.c4), t, r.c3), t, r.c2), t, r.c1), t, r.c0);
+#else
     const float tf = (float)t;
     const float tail = fmaf(fmaf(r.c6, tf, r.c5), tf, r.c4);
     return fma(fma(fma(fma((double)tail, t, r.c3), t, r.c2), t, r.c1), t, r.c0);
+#endif
 }
 
 // 128-bit loads of one row (the compiler will not merge scalar shared-memory loads on its own)
+B200MP_HD unsigned mu_key_to_bytes(int key)   // key = the masked high-word bits of x (MASKIDX)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi((unsigned)key, kMuKeyToBytes);
+#else
+    return (unsigned)(((unsigned long long)(unsigned)key * kMuKeyToBytes) >> 32);
+#endif
+}
+
+// k: row index, or (MASKIDX) the key returned by MuTab<double>::locate
 B200MP_HD MuRow mu_row_load(const double *table, int k)
 {
     MuRow r;
 #if defined(__CUDA_ARCH__)
-    const double2 *p = reinterpret_cast<const double2 *>(table + k * kMuStride);
+    const double2 *p = kMuMaskIdx ? reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(table) + mu_key_to_bytes(k))
+                                  : reinterpret_cast<const double2 *>(table + k * kMuStride);
     const double2 a = p[0], b = p[1];
-    const float4 f = *reinterpret_cast<const float4 *>(p + 2);
     r.c3 = a.x; r.c2 = a.y; r.c1 = b.x; r.c0 = b.y;
-    r.c6 = f.x; r.c5 = f.y; r.c4 = f.z; r.pad = 0.0f;
+#if B200MP_MU_DEG5
+    const double2 c = p[2];
+    r.c5 = c.x; r.c4 = c.y;
 #else
-    r = *reinterpret_cast<const MuRow *>(table + k * kMuStride);
+    const float4 f = *reinterpret_cast<const float4 *>(p + 2);
+    r.c6 = f.x; r.c5 = f.y; r.c4 = f.z; r.pad = 0.0f;
+#endif
+#else
+    r = kMuMaskIdx ? *reinterpret_cast<const MuRow *>(reinterpret_cast<const char *>(table) + mu_key_to_bytes(k))
+                   : *reinterpret_cast<const MuRow *>(table + k * kMuStride);
 #endif
     return r;
 }
@@ -204,21 +257,27 @@ inline double build_mu_table(double B, double C, double D, double *table)
     typedef long double L;
     const MuFunction G{B, C, D};
     double worst = 0.0;
+    for (int i = 0; i < kMuTableDoubles; ++i) table[i] = 0.0;
     for (int k = 0; k < kMuIntervals; ++k) {
         const int e = k / kMuPerBinade, m = k % kMuPerBinade;
         const L lo = ldexpl(1.0L + (L)m / kMuPerBinade, e), hi = ldexpl(1.0L + (L)(m + 1) / kMuPerBinade, e);
         L mono[16], mid;
         mu_fit_interval(G, lo, hi, kMuCoef, mono, &mid);
-        double *row = table + k * kMuStride;
+        double *row = table + mu_row_of(k) * kMuStride;
         MuRow *mr = reinterpret_cast<MuRow *>(row);
         mr->c3 = (double)mono[3];
         mr->c2 = (double)mono[2];
         mr->c1 = (double)mono[1];
         mr->c0 = (double)mono[0];
+#if B200MP_MU_DEG5
+        mr->c5 = (double)mono[5];
+        mr->c4 = (double)mono[4];
+#else
         mr->c6 = (float)mono[6];
         mr->c5 = (float)mono[5];
         mr->c4 = (float)mono[4];
         mr->pad = 0.0f;
+#endif
         for (int i = 0; i <= 32; ++i) {                   // audit: the device scheme vs the long-double function
             const double x = (double)(lo + (hi - lo) * i / 32.0L * 0.999999L);
             const double g = mu_table_eval(row, x - (double)mid);
@@ -286,14 +345,21 @@ template <> struct MuTab<double> {
     typedef MuRow Row;
     static constexpr int kIntervals = kMuIntervals;
     static constexpr int kBytes = kMuTableDoubles * 8;
-    // interval index (unclamped) and t = x - midpoint from the bit pattern of x = 1 + B^2 q
-    static B200MP_HD int locate(double q, double B2, double *t)
+    // row key (a valid row whatever x is), t = x - midpoint and "x is inside the table" from the bit pattern of
+    // x = 1 + B^2 q >= 1 (or NaN)
+    static B200MP_HD int locate(double q, double B2, double *t, bool *inside)
     {
         const double x = fma(q, B2, 1.0);
         const int hi = Math<double>::hi_word(x);
         const int keep = (int)(0xFFFFFFFFu << (20 - kMuBits));
         *t = x - Math<double>::from_words((hi & keep) | (1 << (19 - kMuBits)), 0);
-        return (hi - 0x3FF00000) >> (20 - kMuBits);              // exponent + leading mantissa bits
+        if (kMuMaskIdx) {
+            *inside = (unsigned)hi < 0x3FF00000u + ((unsigned)kMuBinades << 20);   // x < 2^14; NaN and negative fail
+            return (int)((unsigned)hi & kMuKeyMask);
+        }
+        const int kraw = (hi - 0x3FF00000) >> (20 - kMuBits);                      // exponent + leading mantissa bits
+        *inside = (unsigned)kraw < (unsigned)kIntervals;
+        return *inside ? kraw : 0;
     }
     static B200MP_HD Row load(const void *table, int k) { return mu_row_load(static_cast<const double *>(table), k); }
 };
@@ -301,13 +367,15 @@ template <> struct MuTab<float> {
     typedef MuRowF Row;
     static constexpr int kIntervals = kMuIntervalsF;
     static constexpr int kBytes = kMuTableFloats * 4;
-    static B200MP_HD int locate(float q, float B2, float *t)
+    static B200MP_HD int locate(float q, float B2, float *t, bool *inside)
     {
         const float x = fmaf(q, B2, 1.0f);
         const int b = Math<float>::bits(x);
         const int keep = (int)(0xFFFFFFFFu << (23 - kMuBitsF));
         *t = x - Math<float>::from_bits((b & keep) | (1 << (22 - kMuBitsF)));
-        return (b - 0x3F800000) >> (23 - kMuBitsF);
+        const int kraw = (b - 0x3F800000) >> (23 - kMuBitsF);
+        *inside = (unsigned)kraw < (unsigned)kIntervals;
+        return *inside ? kraw : 0;
     }
     static B200MP_HD Row load(const void *table, int k) { return mu_row_load(static_cast<const float *>(table), k); }
 };
@@ -351,9 +419,40 @@ B200MP_HD void normal_loads(const DevParams<R> &P, R ax_prev, R ay_prev, R Fz[4]
 
 // Tyre of wheel I: slips -> combined-slip Pacejka friction -> forces in the chassis frame.
 // TY1: all four tyres share one (B, C) pair -- read entry 0 so the kernel carries 2 constants, not 8.
-template <typename R, int I, bool REAR0, bool TY1, bool TAB, bool FIRST = true>
+// Longitudinal speed of wheel I in its own frame (:274-281); the same expression as in wheel_forces, so the two merge.
+template <typename R, int I, bool REAR0>
+B200MP_HD R wheel_vx(R vxc, R vyc, R cd, R sd)
+{
+    return (REAR0 && I >= 2) ? vxc : vxc * cd + vyc * sd;
+}
+
+// The four reciprocals 1/vx of a stage from ONE hardware reciprocal: 1/(v0 v1 v2 v3) and nine multiplies (a two-level
+// product tree) instead of four MUFU seeds with their zero-low-word moves and four Newton corrections; the FP64
+// instruction count is the same (12), 3 MUFU + 6 MOV fewer per stage.  Each result carries three more roundings
+// (~2 ulp).  A zero or non-finite vx makes all four NaN/Inf -- as it makes the whole state after the reference's step.
+#ifndef B200MP_BATCH_RCP
+#define B200MP_BATCH_RCP 0
+#endif
+#ifndef B200MP_HEADING_FRAME
+#define B200MP_HEADING_FRAME 0
+#endif
+template <typename R>
+B200MP_HD void rcp4(const R v[4], R r[4])
+{
+    typedef Math<R> M;
+    const R p01 = v[0] * v[1], p23 = v[2] * v[3];
+    const R inv = M::rcp(p01 * p23);
+    const R r01 = inv * p23, r23 = inv * p01;
+    r[0] = r01 * v[1];
+    r[1] = r01 * v[0];
+    r[2] = r23 * v[3];
+    r[3] = r23 * v[2];
+}
+
+template <typename R, int I, bool REAR0, bool TY1, bool TAB, bool FIRST = true, bool EXT_R = false>
 B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd, R sd, R Fz,
-                            R &fx, R &fy, R &fxt, R &fyt, R &s, const MuTableView &T, bool &ok, MuRowCacheT<typename MuTab<R>::Row> *RC = nullptr)
+                            R &fx, R &fy, R &fxt, R &fyt, R &s, const MuTableView &T, bool &ok, MuRowCacheT<typename MuTab<R>::Row> *RC = nullptr,
+                            R r_ext = (R)0)
 {
     constexpr int J = TY1 ? 0 : I;
     typedef Math<R> M;
@@ -365,7 +464,7 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
         vx = vxc * cd + vyc * sd;        // :274-281
         vy = vyc * cd - vxc * sd;
     }
-    const R r = M::rcp(vx);
+    const R r = EXT_R ? r_ext : M::rcp(vx);
     // (rw*w - vx)/vx instead of rw*w/vx - 1 (:284-287): same value, no cancellation after the divide,
     // and exactly 0 when the rounded product equals vx (the reference's zero-slip equilibrium)
     const R sx = (M::mul_rn(P.rw, w) - vx) * r;
@@ -376,9 +475,9 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
         // tabulated G(x) = D B sin(C atan(B s)) / (B s), x = 1 + (B s)^2: no sqrt, no reciprocal, no atan, no sin
         typedef MuTab<R> MT;
         R t;
-        const int kraw = MT::locate(q, (R)T.B2, &t);
-        ok &= (unsigned)kraw < (unsigned)MT::kIntervals;                   // NaN / Inf / beyond the table: repeat the step exactly
-        const int k = (unsigned)kraw < (unsigned)MT::kIntervals ? kraw : 0;   // any valid row: the step is repeated anyway
+        bool inside;
+        const int k = MT::locate(q, (R)T.B2, &t, &inside);   // always a valid row; NaN / Inf / beyond the table: the step is repeated exactly
+        ok &= inside;
         R g;
         if (RC) {
             if (FIRST || k != RC->k[I]) {                 // stage 1: always; later stages: only lanes that changed interval
@@ -426,10 +525,18 @@ B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R 
     const R vxL = U - hw, vxR = U + hw;
     const R vyF = V + P.a * wz, vyR = V - P.b * wz;
     R fx[4], fy[4], fxt[4], fyt[4], s[4];
-    wheel_forces<R, 0, REAR0, TY1, TAB, FIRST>(P, D[TY1 ? 0 : 0], vxL, vyF, y8[3], c.cd[0], c.sd[0], Fz[0], fx[0], fy[0], fxt[0], fyt[0], s[0], T, ok, RC);
-    wheel_forces<R, 1, REAR0, TY1, TAB, FIRST>(P, D[TY1 ? 0 : 1], vxR, vyF, y8[4], c.cd[1], c.sd[1], Fz[1], fx[1], fy[1], fxt[1], fyt[1], s[1], T, ok, RC);
-    wheel_forces<R, 2, REAR0, TY1, TAB, FIRST>(P, D[TY1 ? 0 : 2], vxL, vyR, y8[5], c.cd[2], c.sd[2], Fz[2], fx[2], fy[2], fxt[2], fyt[2], s[2], T, ok, RC);
-    wheel_forces<R, 3, REAR0, TY1, TAB, FIRST>(P, D[TY1 ? 0 : 3], vxR, vyR, y8[6], c.cd[3], c.sd[3], Fz[3], fx[3], fy[3], fxt[3], fyt[3], s[3], T, ok, RC);
+    // the tabulated FP64 step shares one hardware reciprocal between the four wheels (rcp4)
+    constexpr bool kBatch = B200MP_BATCH_RCP != 0 && TAB && sizeof(R) == 8;
+    R ri[4] = {(R)0, (R)0, (R)0, (R)0};
+    if (kBatch) {
+        const R v4[4] = {wheel_vx<R, 0, REAR0>(vxL, vyF, c.cd[0], c.sd[0]), wheel_vx<R, 1, REAR0>(vxR, vyF, c.cd[1], c.sd[1]),
+                         wheel_vx<R, 2, REAR0>(vxL, vyR, c.cd[2], c.sd[2]), wheel_vx<R, 3, REAR0>(vxR, vyR, c.cd[3], c.sd[3])};
+        rcp4(v4, ri);
+    }
+    wheel_forces<R, 0, REAR0, TY1, TAB, FIRST, kBatch>(P, D[TY1 ? 0 : 0], vxL, vyF, y8[3], c.cd[0], c.sd[0], Fz[0], fx[0], fy[0], fxt[0], fyt[0], s[0], T, ok, RC, ri[0]);
+    wheel_forces<R, 1, REAR0, TY1, TAB, FIRST, kBatch>(P, D[TY1 ? 0 : 1], vxR, vyF, y8[4], c.cd[1], c.sd[1], Fz[1], fx[1], fy[1], fxt[1], fyt[1], s[1], T, ok, RC, ri[1]);
+    wheel_forces<R, 2, REAR0, TY1, TAB, FIRST, kBatch>(P, D[TY1 ? 0 : 2], vxL, vyR, y8[5], c.cd[2], c.sd[2], Fz[2], fx[2], fy[2], fxt[2], fyt[2], s[2], T, ok, RC, ri[2]);
+    wheel_forces<R, 3, REAR0, TY1, TAB, FIRST, kBatch>(P, D[TY1 ? 0 : 3], vxR, vyR, y8[6], c.cd[3], c.sd[3], Fz[3], fx[3], fy[3], fxt[3], fyt[3], s[3], T, ok, RC, ri[3]);
 
     const R Vwz = V * wz, Uwz = U * wz;
     // pair sums shared between the force balance and the yaw moment (the reference adds left to right, :376-378;
@@ -485,7 +592,11 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     R acc[10], ys[8], k[10], o[AUX ? 18 : 1], axc, ayc, sax, say;
     const R h2 = h * (R)0.5;
     // heading trigonometry: one sincos per step; the three later stage headings are yaw + e with
-    // e = h/2*wz or h*wz (tiny), obtained by a small-angle rotation of (s0, c0)
+    // e = h/2*wz or h*wz (tiny), obtained by a small-angle rotation of (s0, c0).
+    // FRAME (the speculative fast path): x_dot, y_dot of every stage are formed in the frame of the STEP's heading --
+    // k8 = U cos e - V sin e, k9 = U sin e + V cos e -- and the RK4 sum is rotated into the world frame once at the end
+    // (x, y never feed back), which spares composing (s0, c0) with (sin e, cos e) in stages 2-4 and the products of stage 1.
+    constexpr bool FRAME = B200MP_HEADING_FRAME != 0 && SPEC && !AUX;
     R s0, c0, sj, cj;
     bool ok = true;
     if (SPEC)
@@ -496,10 +607,11 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     // rows cached across the stages (and, when the caller keeps the cache, across steps: RCX->k starts at -1)
     MuRowCacheT<typename MuTab<R>::Row> rc_store;
     MuRowCacheT<typename MuTab<R>::Row> *RC = (TAB && kMuCacheRows) ? (RCX ? RCX : &rc_store) : nullptr;
+    const R s1 = FRAME ? (R)0 : s0, c1 = FRAME ? (R)1 : c0;
     if (RCX)
-        planar_rhs<R, REAR0, AUX, TY1, TAB, false>(P, D, y, s0, c0, c, Fz, k, axc, ayc, o, T, &ok, RC);
+        planar_rhs<R, REAR0, AUX, TY1, TAB, false>(P, D, y, s1, c1, c, Fz, k, axc, ayc, o, T, &ok, RC);
     else
-        planar_rhs<R, REAR0, AUX, TY1, TAB, true>(P, D, y, s0, c0, c, Fz, k, axc, ayc, o, T, &ok, RC);
+        planar_rhs<R, REAR0, AUX, TY1, TAB, true>(P, D, y, s1, c1, c, Fz, k, axc, ayc, o, T, &ok, RC);
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] = k[i];
 #pragma unroll
@@ -508,7 +620,9 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     say = ayc;
     if (AUX)
         for (int i = 0; i < 18; ++i) outs[i] = o[i];
-    if (SPEC)
+    if (FRAME)
+        ok &= M::small_sincos_core(h2 * k[7], &sj, &cj);
+    else if (SPEC)
         ok &= M::rotate_core(s0, c0, h2 * k[7], &sj, &cj);
     else if (!M::rotate_small(s0, c0, h2 * k[7], &sj, &cj))
         M::sincos(ys[7], &sj, &cj);
@@ -522,7 +636,9 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     say += (R)2 * ayc;
     if (AUX)
         for (int i = 0; i < 18; ++i) outs[i] += (R)2 * o[i];
-    if (SPEC)
+    if (FRAME)
+        ok &= M::small_sincos_core(h2 * k[7], &sj, &cj);
+    else if (SPEC)
         ok &= M::rotate_core(s0, c0, h2 * k[7], &sj, &cj);
     else if (!M::rotate_small(s0, c0, h2 * k[7], &sj, &cj))
         M::sincos(ys[7], &sj, &cj);
@@ -536,7 +652,9 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     say += (R)2 * ayc;
     if (AUX)
         for (int i = 0; i < 18; ++i) outs[i] += (R)2 * o[i];
-    if (SPEC)
+    if (FRAME)
+        ok &= M::small_sincos_core(h * k[7], &sj, &cj);
+    else if (SPEC)
         ok &= M::rotate_core(s0, c0, h * k[7], &sj, &cj);
     else if (!M::rotate_small(s0, c0, h * k[7], &sj, &cj))
         M::sincos(ys[7], &sj, &cj);
@@ -546,10 +664,15 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     const R h6 = (R)(1.0 / 6) * h;       // :438  state + 1/6*h*(K1+2K2+2K3+K4)
     const R sixth = (R)(1.0 / 6);
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < (FRAME ? 8 : 10); ++i) {
         const R sum = acc[i] + k[i];
         y[i] = y[i] + h6 * sum;
         if (AUX) sdot[i] = sum * sixth;
+    }
+    if (FRAME) {   // the RK4 sum of (x_dot, y_dot) in the step's heading frame -> world frame
+        const R sa = acc[8] + k[8], sb = acc[9] + k[9];
+        y[8] = y[8] + h6 * (c0 * sa - s0 * sb);
+        y[9] = y[9] + h6 * (s0 * sa + c0 * sb);
     }
     ax = (sax + axc) * sixth;            // :442-443
     ay = (say + ayc) * sixth;

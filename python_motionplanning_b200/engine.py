@@ -62,7 +62,7 @@ _UPLOADED = {}      # device -> (signature bytes, upload counter)
 
 def uploaded_token(device: int) -> int:
     """Counter that changes whenever a new parameter table is uploaded to ``device``."""
-    return _UPLOADED.get(device, (None, 0))[1]
+    return _UPLOADED.get(device, (None, 0, 0))[1]
 
 
 @dataclass
@@ -139,10 +139,10 @@ class Engine:
         """Upload parameter set(s) (reference ``VehicleParameters`` objects); returns the number of sets."""
         arr = p if isinstance(p, C.Array) else pack_params(p)
         sig = bytes(arr)
-        old_sig, token = _UPLOADED.get(self.device, (None, 0))
+        old_sig, token = _UPLOADED.get(self.device, (None, 0, 0))[:2]
         if sig != old_sig:
             check(self.lib.b200mp_set_params(self.device, arr, len(arr)), "b200mp_set_params")
-            _UPLOADED[self.device] = (sig, token + 1)
+            _UPLOADED[self.device] = (sig, token + 1, len(arr))
         return len(arr)
 
     # ------------------------------------------------------------------ rollouts
@@ -150,11 +150,14 @@ class Engine:
                 store_stride: int = 0, want_aux: bool = False, dtype: str = "f64", ctrl_broadcast: bool = False,
                 cost_ref=None, cost_in=None, w_u: float = 0.1, u_ref: float = 25.0, step0: int = 0,
                 traj_out: Optional[torch.Tensor] = None, state_out: Optional[torch.Tensor] = None,
-                aux_out: Optional[torch.Tensor] = None) -> RolloutResult:
+                aux_out: Optional[torch.Tensor] = None, state_broadcast: bool = False, friction: Optional[str] = None,
+                cost_out: Optional[torch.Tensor] = None) -> RolloutResult:
         """Batched open-loop RK4 rollouts (``b200mp_rk4_rollout_f64/_f32``), asynchronous on the current stream.
 
         state0 ``[12,B]`` (or ``[10,B]``: ax_prev = ay_prev = 0, drive.py:60-61); delta ``[n_seg,1|4,B]``;
         torque ``[n_seg,1|4,B]`` (``[n_seg,ch,1]`` with ``ctrl_broadcast``); segment of step n = (step0+n)//hold.
+        ``state_broadcast``: state0 is ``[12,1]``, one start state for all B rollouts (B is taken from the controls).
+        ``friction`` = ``"auto" | "closed_form"`` for THIS launch (default: the process-wide mode).
         """
         td = torch.float64 if dtype == "f64" else torch.float32
         fn = self.lib.b200mp_rk4_rollout_f64 if dtype == "f64" else self.lib.b200mp_rk4_rollout_f32
@@ -167,6 +170,12 @@ class Engine:
         dl, tq = self.dev(delta, td), self.dev(torque, td)
         if dl.dim() != 3 or tq.dim() != 3:
             raise ValueError("delta and torque must be [n_seg, channels, B]")
+        if state_broadcast:
+            if B != 1 or ctrl_broadcast:
+                raise ValueError("state_broadcast takes state0 [12,1] and per-rollout controls")
+            B = dl.shape[2]
+        if friction not in (None, "auto", "closed_form"):
+            raise ValueError("friction must be 'auto' or 'closed_form'")
         need_seg = -(-(step0 + n_steps) // hold) if n_steps else 0
         cb = 1 if ctrl_broadcast else B
         if dl.shape[0] < need_seg or tq.shape[0] < need_seg or dl.shape[2] != cb or tq.shape[2] != cb:
@@ -185,13 +194,16 @@ class Engine:
                     raise ValueError("aux_out has the wrong shape/dtype")
         end = state_out if state_out is not None else self.empty(12, B, dtype=td)
         mu_t = None if mu is None else self.dev(mu, td)
+        self._check_param_set(param_set)
         ps_t = None if param_set is None else self.dev(param_set, torch.int32)
         cref = cost = cin = None
         if cost_ref is not None:
             cref = self.dev(cost_ref, td)
             if cref.shape[0] < step0 + n_steps:
                 raise ValueError("cost_ref must have one (x, y) row per step")
-            cost = self.empty(B, dtype=td)
+            cost = cost_out if cost_out is not None else self.empty(B, dtype=td)
+            if cost.shape != (B,) or cost.dtype != td or not cost.is_contiguous():
+                raise ValueError("cost_out has the wrong shape/dtype")
             cin = None if cost_in is None else self.dev(cost_in, td)
         a = RolloutArgsC(B=B, n_steps=int(n_steps), step0=int(step0), hold=int(hold), dt=float(dt),
                          state0=s0.data_ptr(), delta=dl.data_ptr(), torque=tq.data_ptr(),
@@ -202,9 +214,21 @@ class Engine:
                          traj=None if traj is None else traj.data_ptr(), aux=None if aux is None else aux.data_ptr(),
                          state_end=end.data_ptr(), cost=None if cost is None else cost.data_ptr(),
                          cost_in=None if cin is None else cin.data_ptr(),
-                         cost_ref=None if cref is None else cref.data_ptr(), w_u=float(w_u), u_ref=float(u_ref))
+                         cost_ref=None if cref is None else cref.data_ptr(), w_u=float(w_u), u_ref=float(u_ref),
+                         state_broadcast=int(bool(state_broadcast)),
+                         friction_override={None: 0, "auto": 1, "closed_form": 2}[friction])
         check(fn(self.device, self._stream(), C.byref(a)), "b200mp_rk4_rollout_" + dtype)
         return RolloutResult(state_end=end, traj=traj, aux=aux, cost=cost)
+
+    def _check_param_set(self, param_set):
+        """Host-side range check of per-rollout parameter-set indices given as host data (a device tensor is not read back:
+        the kernels clamp indices to the uploaded table, so an out-of-range entry can never read out of bounds)."""
+        if param_set is None or isinstance(param_set, torch.Tensor) and param_set.is_cuda:
+            return
+        a = np.asarray(param_set)
+        n = _UPLOADED.get(self.device, (None, 0, 0))[2]
+        if a.size and n and (a.min() < 0 or a.max() >= n):
+            raise ValueError(f"param_set entries must be in [0, {n}) (the uploaded table has {n} sets); got [{a.min()}, {a.max()}]")
 
     def rollout_to_host(self, state0_host: torch.Tensor, delta_host: torch.Tensor, torque_host: torch.Tensor,
                         dt: float, n_steps: int, hold: int, traj_host: torch.Tensor, chunk_steps: int = 50,
@@ -279,15 +303,17 @@ class Engine:
                 ev = torch.cuda.Event()
                 ev.record(copy)
                 ready.append(ev)
-        n0, k = 0, 0
+        n0 = 0
         while n0 < n_steps:
             nc = min(chunk_steps, n_steps - n0)
-            compute.wait_event(ready[min(k, len(ready) - 1)])
+            # the launch reads control segments up to ceil((n0 + nc) / hold) - 1: wait for the upload that covers the last one
+            last_seg = -(-(n0 + nc) // hold) - 1
+            compute.wait_event(ready[min(last_seg // seg_per_chunk, len(ready) - 1)])
             s = self.rollout(s, dl, tq, dt, nc, hold=hold, store_stride=0, dtype=dtype, step0=n0).state_end
             n0 += nc
-            k += 1
         state_end_host.copy_(s, non_blocking=True)
         compute.synchronize()
+        copy.synchronize()          # uploads of segments beyond the last step must not outlive dl / tq
         return s
 
     def _copy_stream(self):
@@ -312,6 +338,7 @@ class Engine:
         mu_t = None if mu is None else self.dev(mu)
         if axay is None:
             axay = torch.stack([self.dev(ax_prev).reshape(B), self.dev(ay_prev).reshape(B)]).contiguous()
+        self._check_param_set(param_set)
         ps = None if param_set is None else self.dev(param_set, torch.int32)
         sd, misc, out = out if out is not None else (self.empty(10, B), self.empty(6, B), self.empty(18, B))
         check(self.lib.b200mp_planar_model_f64(self.device, self._stream(), B, self._ptr(st), self._ptr(tq),
@@ -323,7 +350,7 @@ class Engine:
     def track_closed_loop(self, state0, waypoints, dt: float, n_steps: int, target_vel: float = 25.0,
                           gains: Optional[TrackGains] = None, ctrl0=None, wp_count=None, vehicles_per_set: Optional[int] = None,
                           ctrl_every: int = 10, store_stride: int = 0, want_log: bool = False, want_target_idx: bool = False,
-                          step0: int = 0, norm_mode: Optional[int] = None) -> TrackResult:
+                          step0: int = 0, norm_mode: Optional[int] = None, friction: Optional[str] = None) -> TrackResult:
         """Batched Stanley + PID closed loop around the RK4 step (``b200mp_track_closed_loop_f64``): what
         ``Car.drive`` does between two planner calls (drive.py:126-151), for V vehicles at once.
 
@@ -372,7 +399,8 @@ class Engine:
                        norm_mode=int(norm_mode), dt=float(dt), target_vel=float(target_vel), k=g.k, k_soft=g.k_soft,
                        max_steer=g.max_steer, kp=g.kp, ki=g.ki, kd=g.kd, lookahead=g.lookahead, deadband=g.deadband,
                        steer_filter=g.steer_filter, state0=p(s0), ctrl0=p(c0), waypoints=p(wp), wp_count=p(cnt),
-                       traj=p(traj), log=p(log), target_idx=p(tid), state_end=p(end), ctrl_end=p(cend))
+                       traj=p(traj), log=p(log), target_idx=p(tid), state_end=p(end), ctrl_end=p(cend),
+                       friction_override={None: 0, "auto": 1, "closed_form": 2}[friction])
         check(self.lib.b200mp_track_closed_loop_f64(self.device, self._stream(), C.byref(a)), "b200mp_track_closed_loop_f64")
         return TrackResult(state_end=end, ctrl_end=cend, traj=traj, log=log, target_idx=tid)
 
@@ -384,6 +412,24 @@ class Engine:
                                                       delta_mean, delta_sigma, delta_clip, torque_mean, torque_sigma,
                                                       self._ptr(delta), self._ptr(torque)), "b200mp_mpc_sample_controls_f64")
         return delta, torque
+
+    def mpc_sample_controls_into(self, delta: torch.Tensor, torque: torch.Tensor, seed: int, rollout0: int = 0, delta_mean=0.0,
+                                 delta_sigma=0.02, delta_clip=0.5235987755982988, torque_mean=0.0, torque_sigma=50.0):
+        """``mpc_sample_controls`` into caller-owned ``[n_seg,1,B]`` buffers (no allocation: resident MPC planners)."""
+        n_seg, _, B = delta.shape
+        check(self.lib.b200mp_mpc_sample_controls_f64(self.device, self._stream(), B, n_seg, int(seed), int(rollout0),
+                                                      delta_mean, delta_sigma, delta_clip, torque_mean, torque_sigma,
+                                                      self._ptr(delta), self._ptr(torque)), "b200mp_mpc_sample_controls_f64")
+
+    def mpc_winner(self, cost: torch.Tensor, delta: torch.Tensor, torque: torch.Tensor, index_offset: int = 0,
+                   record_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Winner record ``[min cost, global index, delta[n_seg], torque[n_seg]]`` of a sampled batch in one call
+        (``b200mp_mpc_winner_f64``: lowest-index argmin + gather of the winner's controls); device tensor, async."""
+        n_seg, B = delta.shape[0], delta.shape[-1]
+        rec = record_out if record_out is not None else self.empty(2 + 2 * n_seg)
+        check(self.lib.b200mp_mpc_winner_f64(self.device, self._stream(), B, n_seg, self._ptr(cost), self._ptr(delta),
+                                             self._ptr(torque), int(index_offset), self._ptr(rec)), "b200mp_mpc_winner_f64")
+        return rec
 
     def argmin(self, cost: torch.Tensor, index_offset: int = 0):
         """Device-side lowest-index argmin; returns device tensors ``(min[1] f64, idx[1] i64)`` (async)."""

@@ -51,7 +51,7 @@ def test_mpc_result_independent_of_rank_count(engine):
         assert torch.equal(torch.cat(costs), cost1)          # bit-identical per-rollout costs
     # the single-process mpc_plan entry point agrees
     plan = D.mpc_plan(engine, cfg)
-    assert plan["index"] == ix1 and plan["cost"] == mn1 and torch.equal(plan["delta"], d1[:, 0, ix1])
+    assert plan["index"] == ix1 and plan["cost"] == mn1 and torch.equal(plan["delta"], d1[:, 0, ix1].cpu())
 
 
 def test_collision_sharded_equals_unsharded(engine):

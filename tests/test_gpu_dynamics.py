@@ -355,3 +355,46 @@ def test_logging_rollout_with_stride_vs_c_oracle(engine):
     d4, t4 = np.concatenate([d, d, z, z], axis=1), np.repeat(t, 4, axis=1)
     got4 = engine.rollout(s0, d4, t4, DT, N, hold=wl.HOLD, store_stride=stride, want_aux=True)
     assert rel_err(got4.aux.cpu().numpy(), ref["aux"]).max() < REL_TOL_F64
+
+
+def test_state_broadcast_winner_record_and_per_call_friction(engine):
+    """The resident sampling-MPC pieces: a [12,1] start state read with a zero batch stride gives the same bits as the
+    materialised [12,B] copy; ``b200mp_mpc_winner_f64`` = lowest-index argmin + the winner's control sequence; the
+    per-launch friction override equals the process-wide mode."""
+    cfg = wl.config4_mpc(B=4096 + 37, n_steps=40)
+    B, N = cfg["B"], cfg["n_steps"]
+    engine.set_params(_params())
+    d, t = engine.mpc_sample_controls(B, N, cfg["seed"])
+    s0 = np.repeat(cfg["state0"][:, None], B, axis=1)
+    kw = dict(hold=1, cost_ref=cfg["cost_ref"], w_u=cfg["w_u"], u_ref=cfg["u_ref"])
+    full = engine.rollout(s0, d, t, DT, N, **kw)
+    bc = engine.rollout(cfg["state0"][:, None], d, t, DT, N, state_broadcast=True, **kw)
+    assert torch.equal(full.cost, bc.cost) and torch.equal(full.state_end, bc.state_end)
+    # hold = 10 (the sliced / plain kernels) and a zero-step launch
+    full10 = engine.rollout(s0, d, t, DT, N, hold=10)
+    bc10 = engine.rollout(cfg["state0"][:, None], d, t, DT, N, hold=10, state_broadcast=True)
+    assert torch.equal(full10.state_end, bc10.state_end)
+    z = engine.rollout(cfg["state0"][:, None], d, t, DT, 0, hold=1, state_broadcast=True)
+    assert np.array_equal(z.state_end.cpu().numpy(), s0)
+    with pytest.raises(ValueError):
+        engine.rollout(s0, d, t, DT, N, state_broadcast=True, **kw)
+    cost = bc.cost.cpu().numpy()
+    i = mpc_numpy.argmin_lowest(cost)
+    rec = engine.mpc_winner(bc.cost, d, t, index_offset=1000).cpu().numpy()
+    assert rec[0] == cost[i] and rec[1] == i + 1000
+    assert np.array_equal(rec[2:2 + N], d[:, 0, i].cpu().numpy()) and np.array_equal(rec[2 + N:], t[:, 0, i].cpu().numpy())
+    tie = bc.cost.clone()
+    tie[7] = tie[3000] = -1.0                       # ties -> lowest index; NaN never wins
+    tie[5] = float("nan")
+    assert engine.mpc_winner(tie, d, t).cpu().numpy()[1] == 7
+    none = engine.mpc_winner(torch.full((B,), float("inf"), dtype=torch.float64, device="cuda"), d, t).cpu().numpy()
+    assert none[1] == -1 and np.isinf(none[0]) and not none[2:].any()
+    # per-launch friction override == process-wide mode, both ways
+    for mode in ("auto", "closed_form"):
+        a = engine.rollout(s0, d, t, DT, N, hold=10, friction=mode)
+        prev = engine.set_friction_mode(mode)
+        b = engine.rollout(s0, d, t, DT, N, hold=10)
+        engine.set_friction_mode(prev)
+        assert torch.equal(a.state_end, b.state_end)
+    with pytest.raises(ValueError):
+        engine.rollout(s0, d, t, DT, N, friction="table")

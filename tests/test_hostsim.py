@@ -17,7 +17,8 @@ from python_motionplanning_b200 import workloads as wl
 @pytest.fixture(scope="module")
 def hostsim(tmp_path_factory):
     out = tmp_path_factory.mktemp("hostsim") / "libhostsim.so"
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+    # HOSTSIM_FLAGS: extra -D tunables of the device headers (e.g. -DB200MP_MU_DEG5=1) for A/B checks on the CPU
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", *os.environ.get("HOSTSIM_FLAGS", "").split(),
                     os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp"), "-o", str(out)], check=True)
     return C.CDLL(str(out))
 

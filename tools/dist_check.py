@@ -31,7 +31,7 @@ def main():
     res = eng.rollout(s0, d, t, wl.DT, 100, hold=1, cost_ref=cfg["cost_ref"], w_u=cfg["w_u"], u_ref=cfg["u_ref"])
     mn, ix = eng.argmin(res.cost)
     assert plan["index"] == int(ix.item()) and plan["cost"] == float(mn.item()), (plan["index"], int(ix.item()))
-    assert torch.equal(plan["delta"], d[:, 0, plan["index"]]) and torch.equal(plan["torque"], t[:, 0, plan["index"]])
+    assert torch.equal(plan["delta"], d[:, 0, plan["index"]].cpu()) and torch.equal(plan["torque"], t[:, 0, plan["index"]].cpu())
     lo, hi = plan["shard"]
     assert torch.equal(plan["local_cost"], res.cost[lo:hi])
     w = wl.config3_lattice(P=4096, M=10000)
