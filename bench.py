@@ -338,6 +338,31 @@ def run_gpu(args):
     e2e_value = world * units_per_step * e2e_steps / float(t_e.item())
     h2d = int(hs.numel() + hd.numel() + ht.numel()) * 8
     d2h = int(traj_host.numel()) * 8
+    # what the box allows for that read-back: every rank copies one 50-step slab (262 MB) device -> pinned host, all ranks at
+    # once, nothing else running.  The step time is a max over ranks, so the bound on the aggregate is N x the SLOWEST rank's rate.
+    cp = torch.cuda.Stream(dev)
+    barrier()
+    with torch.cuda.stream(cp):
+        for _ in range(2):
+            traj_host[:50].copy_(traj[:50], non_blocking=True)
+        cp.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            traj_host[:50].copy_(traj[:50], non_blocking=True)
+        cp.synchronize()
+    my_rate = torch.tensor([10 * traj[:50].numel() * 8 / (time.perf_counter() - t0) / 1e9], dtype=torch.float64, device=dev)
+    rates = [my_rate.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(rates, my_rate)
+    rates = [float(r.item()) for r in rates]
+    e2e_gbs = e2e_value * ALG_BYTES_PER_STEP / 1e9
+    d2h_ceiling = {"gbs_per_gpu_all_ranks_at_once": [round(r, 2) for r in rates], "gbs_aggregate": round(sum(rates), 2),
+                   "gbs_bound_by_slowest_rank": round(world * min(rates), 2), "e2e_d2h_gbs": round(e2e_gbs, 2),
+                   "frac_of_d2h_ceiling": e2e_gbs / (world * min(rates)),
+                   "note": "concurrent cudaMemcpyAsync device -> pinned host of one 262 MB slab per rank, measured in this run; a "
+                           "single B200 reads back at ~56 GB/s alone (PCIe Gen5 x16), eight at once share the host's write path "
+                           "(profiles/r02_d2h_ceiling.md)"}
     # supplementary: the same host-buffer call when only the final states are read back (no trajectory D2H); the
     # controls are uploaded chunk by chunk behind the kernels
     end_host = torch.empty(12, B, dtype=torch.float64).pin_memory()
@@ -460,7 +485,8 @@ def run_gpu(args):
             "config": bench_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "Engine.rollout_to_host: pinned host inputs -> H2D, 10 time-chunks of 50 steps, D2H of the full trajectory overlapped on a copy stream",
-                    "bound": "PCIe: 2.62 GB of trajectory per step at ~55 GB/s",
+                    "bound": "device -> host read-back of 2.62 GB of trajectory per step and GPU", "d2h_ceiling": d2h_ceiling,
+                    "frac_of_d2h_ceiling": d2h_ceiling["frac_of_d2h_ceiling"],
                     "endstate_only": {"value": e2e_end_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12 * B * 8,
                                       "api": "Engine.rollout_endstate_to_host: same host inputs, controls uploaded in 5 time-chunks behind "
                                              "the kernels, only the [12, B] end states read back"}},

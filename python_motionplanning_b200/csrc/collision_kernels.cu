@@ -792,6 +792,146 @@ collision_resolve_kernel(int n_list, const int *__restrict__ items, const double
     if (hit) free_out[p] = 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Exact minimum clearance with the broad phase: the two FP32 sweeps of clearance_screen_kernel (pass A: min q32 per
+// circle; pass B: exact q64 for the points with q32 <= T) visit only the 32-point obstacle chunks whose bounding box can
+// still matter.  For a thread with circle centres inside [tx0, tx1] x [ty0, ty1] (FP32, relative to the origin) and a
+// chunk box [bx0, bx1] x [by0, by1], every point p of the chunk has |p.x - c.x| >= gx = max(0, bx0 - tx1, tx0 - bx1)
+// for every circle (likewise y), and because FP32 subtraction, multiplication and FMA are monotone, the q32 the sweep
+// would compute is >= lb = fma_rd(gy, gy, mul_rd(gx, gx)) with gx, gy rounded DOWN.  Pass A skips a chunk when
+// lb > max_k(current min q32_k) -- it cannot lower any minimum -- and pass B when lb > max_k T_k -- it holds no
+// candidate.  Both tests are strict and NaN-safe (an undecidable comparison evaluates the chunk), non-sharp threads have
+// T = +inf and visit everything, so the doubles returned are those of clearance_screen_kernel / collision_kernel<NC, true>
+// for every input.  Obstacle outlines are spatially coherent, so after the first few chunks the running minimum prunes
+// nearly all of the rest: config 3 evaluates a few per cent of the 313 chunks per path point.
+template <int NC>
+__global__ void __launch_bounds__(kColBlock)
+clearance_cull_kernel(int n_items, int n_pts, const __grid_constant__ CircleSpec cs, const double *__restrict__ px,
+                      const double *__restrict__ py, const double *__restrict__ pcos, const double *__restrict__ psin,
+                      const double *__restrict__ pyaw, int yaw_stride, int M, const double2 *__restrict__ obs,
+                      const float2 *__restrict__ pts, const float4 *__restrict__ boxes, const ObsPrep *__restrict__ prep,
+                      unsigned char *free_out, double *__restrict__ clear_pts)
+{
+    const int t = blockIdx.x * kColBlock + threadIdx.x;
+    if (t >= n_items) return;
+    const int p = t / n_pts;
+    const double2 org = obs[0];
+    const int n_chunks = (M + 31) >> 5;
+    double cx[NC], cy[NC], ac = 0.0;
+    unsigned long long ncx[NC], ncy[NC];
+    float tx0 = INFINITY, tx1 = -INFINITY, ty0 = INFINITY, ty1 = -INFINITY;
+    bool bad = false;
+    {
+        const double x = px[t], y = py[t];
+        double c, s;
+        if (pcos) {
+            c = pcos[t];
+            s = psin[t];
+        } else {
+            sincos(pyaw[(size_t)p * yaw_stride + (t - p * n_pts)], &s, &c);
+        }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            cx[k] = __dadd_rn(x, __dmul_rn(cs.off[k], c));
+            cy[k] = __dadd_rn(y, __dmul_rn(cs.off[k], s));
+            const double rx = cx[k] - org.x, ry = cy[k] - org.y;
+            const float fx = (float)rx, fy = (float)ry;
+            ncx[k] = pack2(-fx, -fx);
+            ncy[k] = pack2(-fy, -fy);
+            tx0 = fminf(tx0, fx);
+            tx1 = fmaxf(tx1, fx);
+            ty0 = fminf(ty0, fy);
+            ty1 = fmaxf(ty1, fy);
+            bad |= !(fabs(rx) <= 1.0e30) | !(fabs(ry) <= 1.0e30);   // NaN / Inf / beyond FP32 range
+            ac = fmax(ac, fmax(fabs(rx), fabs(ry)));
+        }
+        if (bad) tx0 = ty0 = tx1 = ty1 = __int_as_float(0x7fc00000);   // every bound test undecidable -> every chunk visited
+    }
+    const float4 *pts4 = reinterpret_cast<const float4 *>(pts);
+    // lower bound of q32 over the points of chunk c, for every circle of this thread (rounded down)
+    auto chunk_lb = [&](int c) {
+        const float4 b = boxes[c];
+        const float gx = fmaxf(0.0f, fmaxf(__fsub_rd(b.x, tx1), __fsub_rd(tx0, b.z)));
+        const float gy = fmaxf(0.0f, fmaxf(__fsub_rd(b.y, ty1), __fsub_rd(ty0, b.w)));
+        return __fmaf_rd(gy, gy, __fmul_rd(gx, gx));
+    };
+
+    // ---- pass A: min q32 per circle
+    float mn[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) mn[k] = INFINITY;
+    for (int c = 0; c < n_chunks; ++c) {
+        float mx = mn[0];
+#pragma unroll
+        for (int k = 1; k < NC; ++k) mx = fmaxf(mx, mn[k]);
+        if (chunk_lb(c) > mx && !bad) continue;
+#pragma unroll 4
+        for (int o = 0; o < 16; ++o) {
+            const float4 ob = pts4[c * 16 + o];                        // two points: (xa, ya, xb, yb)
+            const unsigned long long X = pack2(ob.x, ob.z), Y = pack2(ob.y, ob.w);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                const unsigned long long dx = add2(X, ncx[k]), dy = add2(Y, ncy[k]);
+                const unsigned long long q = fma2(dy, dy, mul2(dx, dx));
+                mn[k] = fminf(mn[k], fminf(lo2(q), hi2(q)));
+            }
+        }
+    }
+
+    // ---- candidate thresholds (as in clearance_screen_kernel)
+    float T[NC], maxT = 0.0f;
+    {
+        const double u = 5.9604644775390625e-08;   // 2^-24
+        const double e0 = 2.0 * u * ((double)prep->amax + ac) * 1.000001 + 1.0e-18;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const double b = (sqrt((double)mn[k]) * (1.0 + 4.0 * u) + 2.0 * e0) / (1.0 - 4.0 * u);
+            const bool sharp = !bad && e0 < 1.0e30 && mn[k] < INFINITY;
+            T[k] = sharp ? __double2float_ru(b * b * 1.000001) : INFINITY;
+            maxT = fmaxf(maxT, T[k]);
+        }
+    }
+
+    // ---- pass B: exact q64 for the candidates only
+    double qmin[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) qmin[k] = INFINITY;
+    for (int c = 0; c < n_chunks; ++c) {
+        if (chunk_lb(c) > maxT && !bad) continue;
+        for (int o = 0; o < 16; ++o) {
+            const float4 ob = pts4[c * 16 + o];
+            const unsigned long long X = pack2(ob.x, ob.z), Y = pack2(ob.y, ob.w);
+            bool cand = false;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                const unsigned long long dx = add2(X, ncx[k]), dy = add2(Y, ncy[k]);
+                const unsigned long long q = fma2(dy, dy, mul2(dx, dx));
+                cand |= !(fminf(lo2(q), hi2(q)) > T[k]);   // NaN counts as a candidate (it drops out in fmin below)
+            }
+            if (cand) {
+                for (int i = c * 32 + 2 * o; i < c * 32 + 2 * o + 2 && i < M; ++i) {
+                    const double2 e = obs[i];
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        const double dx = __dsub_rn(e.x, cx[k]);
+                        const double dy = __dsub_rn(e.y, cy[k]);
+                        qmin[k] = fmin(qmin[k], __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                    }
+                }
+            }
+        }
+    }
+    bool hit = false;
+    double clr = INFINITY;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        hit |= qmin[k] < cs.thr[k];                                              // sqrt_rn(q) - r < 0  <=>  q < thr
+        clr = fmin(clr, __dsub_rn(__dsqrt_rn(qmin[k]), cs.rad[k]));             // collision_checker.py:101-105
+    }
+    if (hit) free_out[p] = 0;
+    clear_pts[t] = clr;
+}
+
 __global__ void clearance_reduce_kernel(int P, int n_pts, const double *__restrict__ clear_pts, double *__restrict__ out)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -813,12 +953,28 @@ static int launch_collision_nc(int device, cudaStream_t st, int P, int n_pts, co
         void *scratch = nullptr;
         int rc = ensure_scratch(device, st, sizeof(double) * (size_t)items, &scratch);
         if (rc) return rc;
-        if (mode == B200MP_COLLISION_FP64_ONLY)
+        if (mode == B200MP_COLLISION_FP64_ONLY) {
             collision_kernel<NC, true><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
                                                                   M, (const double2 *)obs, free_out, (double *)scratch);
-        else
+        } else if (mode == B200MP_COLLISION_SCREEN_ONLY || items * (long long)M < (1LL << 22)) {
             clearance_screen_kernel<NC><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
                                                                    M, (const double2 *)obs, free_out, (double *)scratch);
+        } else {
+            // broad phase: FP32 points + chunk boxes behind the per-point clearances in the same scratch area
+            const int n_chunks = (M + 31) / 32;
+            const size_t clr_bytes = (sizeof(double) * (size_t)items + 255) & ~(size_t)255;
+            const size_t pts_bytes = sizeof(float2) * 32 * (size_t)n_chunks, box_bytes = sizeof(float4) * (size_t)n_chunks;
+            rc = ensure_scratch(device, st, clr_bytes + pts_bytes + box_bytes + sizeof(ObsPrep), &scratch);
+            if (rc) return rc;
+            float2 *pts = (float2 *)((char *)scratch + clr_bytes);
+            float4 *boxes = (float4 *)((char *)scratch + clr_bytes + pts_bytes);
+            ObsPrep *prep = (ObsPrep *)((char *)scratch + clr_bytes + pts_bytes + box_bytes);
+            B200MP_CUDA(cudaMemsetAsync(prep, 0, sizeof(ObsPrep), st));
+            obstacle_prepare_kernel<<<(n_chunks * 32 + 127) / 128, 128, 0, st>>>(M, (const double2 *)obs, pts, boxes, prep);
+            B200MP_CUDA(cudaGetLastError());
+            clearance_cull_kernel<NC><<<grid, kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride, M,
+                                                                 (const double2 *)obs, pts, boxes, prep, free_out, (double *)scratch);
+        }
         B200MP_CUDA(cudaGetLastError());
         clearance_reduce_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, n_pts, (const double *)scratch, min_clear);
     } else if (mode == B200MP_COLLISION_FP64_ONLY) {

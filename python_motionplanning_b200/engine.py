@@ -232,9 +232,9 @@ class Engine:
 
     def rollout_to_host(self, state0_host: torch.Tensor, delta_host: torch.Tensor, torque_host: torch.Tensor,
                         dt: float, n_steps: int, hold: int, traj_host: torch.Tensor, chunk_steps: int = 50,
-                        dtype: str = "f64", state_end_host: Optional[torch.Tensor] = None):
+                        dtype: str = "f64", state_end_host: Optional[torch.Tensor] = None, n_slabs: int = 2):
         """End-to-end rollout with HOST buffers: H2D of the inputs, time-chunked kernels, D2H of the full
-        trajectory overlapped with the next chunk (two device slabs, two streams).
+        trajectory overlapped with the next chunks (``n_slabs`` device slabs in a ring, two streams).
 
         ``*_host`` are pinned CPU tensors; ``traj_host`` is ``[n_steps, 10, B]``.  Rollouts are resumable
         (``state_end`` of one chunk is ``state0`` of the next), which is what makes the time split exact.
@@ -249,14 +249,15 @@ class Engine:
         s = state0_host.to(self.tdev, non_blocking=True)
         dl = delta_host.to(self.tdev, non_blocking=True)
         tq = torque_host.to(self.tdev, non_blocking=True)
-        slabs = self._slabs(min(chunk_steps, n_steps), B, td)
-        slab_free = [None, None]
+        n_slabs = max(2, int(n_slabs))
+        slabs = self._slabs(min(chunk_steps, n_steps), B, td, n_slabs)
+        slab_free = [None] * n_slabs
         n0, k = 0, 0
         while n0 < n_steps:
             nc = min(chunk_steps, n_steps - n0)
-            slab = slabs[k & 1][:nc]
-            if slab_free[k & 1] is not None:
-                compute.wait_event(slab_free[k & 1])            # D2H of the chunk that used this slab is done
+            slab = slabs[k % n_slabs][:nc]
+            if slab_free[k % n_slabs] is not None:
+                compute.wait_event(slab_free[k % n_slabs])      # D2H of the chunk that used this slab is done
             res = self.rollout(s, dl, tq, dt, nc, hold=hold, store_stride=1, dtype=dtype, step0=n0, traj_out=slab)
             s = res.state_end
             done = torch.cuda.Event()
@@ -266,7 +267,7 @@ class Engine:
                 traj_host[n0:n0 + nc].copy_(slab, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
-            slab_free[k & 1] = ev
+            slab_free[k % n_slabs] = ev
             n0 += nc
             k += 1
         if state_end_host is not None:
@@ -321,12 +322,18 @@ class Engine:
             self._cstream = torch.cuda.Stream(self.tdev)
         return self._cstream
 
-    def _slabs(self, steps, B, td):
-        key = (steps, B, td)
+    def _slabs(self, steps, B, td, n=2):
+        key = (steps, B, td, n)
         if getattr(self, "_slab_key", None) != key:
-            self._slab = [self.empty(steps, 10, B, dtype=td) for _ in range(2)]
+            self._slab = None
+            self._slab = [self.empty(steps, 10, B, dtype=td) for _ in range(n)]
             self._slab_key = key
         return self._slab
+
+    def pinned_empty(self, *shape, dtype=torch.float64, numa_local: bool = True) -> torch.Tensor:
+        """Page-locked host tensor for the ``*_to_host`` calls, placed on this GPU's NUMA node when the host allows it."""
+        from . import hostmem
+        return hostmem.pinned_empty(*shape, dtype=dtype, numa_node=hostmem.gpu_numa_node(self.device) if numa_local else -1)
 
     def planar_model_batch(self, state, torque, mu, delta, ax_prev, ay_prev, param_set=None, axay=None, out=None):
         """Batched ``VehicleModel.planar_model``: returns ``(state_dot[10,B], misc[6,B], outputs[18,B])``.

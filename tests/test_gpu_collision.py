@@ -251,11 +251,14 @@ def test_collision_filter_adversarial_bands(engine, scale_shift):
         assert np.array_equal(got1, ref1), p
 
 
-def test_collision_filter_exceptional_values(engine):
-    """NaN / Inf / huge coordinates and degenerate radii: the screened kernel must fall back to the exact
-    sequence wherever single precision cannot bound its own error."""
+@pytest.mark.parametrize("size", [(128, 512), (192, 1024)], ids=["single-launch", "broad-phase"])
+def test_collision_filter_exceptional_values(engine, size):
+    """NaN / Inf / huge coordinates and degenerate radii: the screened kernels must fall back to the exact
+    sequence wherever single precision cannot bound its own error.  The second size is past the 4 M point-pair
+    threshold, i.e. flags AND min-clearance take the bounding-box broad phase (collision_cull_kernel /
+    clearance_cull_kernel)."""
     rng = np.random.default_rng(11)
-    w = wl.config3_lattice(P=128, M=512)
+    w = wl.config3_lattice(P=size[0], M=size[1])
     px, py, pyaw, obs = w["px"].copy(), w["py"].copy(), w["pyaw"], w["obstacles"].copy()
 
     def both(px, py, obs, off=OFF, rad=RAD, what=""):
@@ -280,7 +283,7 @@ def test_collision_filter_exceptional_values(engine):
         o[rng.integers(1, len(o), 20), rng.integers(0, 2, 20)] = bad
         both(px, py, o, what=f"obstacles {bad}")
         x = px.copy()
-        x[rng.integers(0, 128, 10), rng.integers(0, 49, 10)] = bad
+        x[rng.integers(0, size[0], 10), rng.integers(0, 49, 10)] = bad
         both(x, py, obs, what=f"path {bad}")
     # both far away and close together: differences are small, magnitudes beyond FP32 range
     both(px + 1.0e39, py, obs + np.array([1.0e39, 0.0]), what="1e39")

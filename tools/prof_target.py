@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Short single-GPU program for ncu captures: a few launches of one hot-path kernel at full size.
 
-    python tools/prof_target.py rollout|rollout_f32|collision|collision_clear|mpc|track|track_log [--launches 3]
+    python tools/prof_target.py rollout|rollout_f32|collision|collision_clear|planner|mpc|track|track_log [--launches 3]
 """
 import argparse
 import os
@@ -43,6 +43,23 @@ def main():
         for _ in range(a.launches):
             eng.track_closed_loop(s, w, wl.DT, 100, 25.0, vehicles_per_set=4096,
                                   **({"store_stride": 10, "want_log": True} if a.what.endswith("log") else {}))
+    elif a.what == "planner":
+        # one launch of every planner-side kernel at config-3 size: obstacle_prepare + collision_cull<3> (flags from yaws),
+        # obstacle_prepare + clearance_cull<3> (+ reduce), select_score + argmin, lattice_kernel, spiral_opt_kernel
+        import numpy as np
+        w = wl.config3_lattice()
+        px, py, yaw, obs = eng.dev(w["px"]), eng.dev(w["py"]), eng.dev(w["pyaw"]), eng.dev(w["obstacles"])
+        trig = eng.path_trig(w["pyaw"], w["px"].shape[1])
+        par = w["spiral_params"]
+        k1d, k2d, sfd = eng.dev(par[0]), eng.dev(par[1]), eng.dev(par[2])
+        lat0 = eng.sample_lattice(k1d, k2d, sfd, ego=None, want_trig=False)
+        tf_goal = eng.dev(3.0 * (par[0] + par[1]) * par[2] / 8.0)
+        for _ in range(a.launches):
+            free = eng.collision_check_batch(px, py, yaw, obs, w["offsets"], w["radii"])
+            eng.collision_check_batch(px, py, None, obs, w["offsets"], w["radii"], trig=trig, want_clearance=True)
+            eng.select_best_path_index_batch(px[:, -1].contiguous(), py[:, -1].contiguous(), free, w["goal"], w["weight"])
+            eng.sample_lattice(k1d, k2d, sfd, ego=eng.dev(w["ego"]))
+            eng.optimize_spirals(lat0["end_xy"][0], lat0["end_xy"][1], tf_goal)
     elif a.what == "mpc":
         cfg = wl.config4_mpc(B=1 << 20)
         d, t = eng.mpc_sample_controls(cfg["B"], 100, cfg["seed"])
