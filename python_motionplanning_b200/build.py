@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libb200mp.so")
 SOURCES = ["b200mp_api.cu", "rollout_kernels_f64.cu", "rollout_kernels_f32.cu", "collision_kernels.cu", "misc_kernels.cu", "tracking_kernels.cu", "lattice_kernels.cu"]
-HEADERS = ["b200mp_internal.h", "b200mp_math.cuh", "vehicle_rhs.cuh", "rollout_kernels.cuh", os.path.join("..", "..", "include", "b200mp.h")]
+HEADERS = ["b200mp_internal.h", "b200mp_math.cuh", "vehicle_rhs.cuh", "rollout_kernels.cuh", "slice_sched.cuh", os.path.join("..", "..", "include", "b200mp.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -29,6 +29,7 @@
 #include <math.h>
 
 #include "b200mp_internal.h"
+#include "slice_sched.cuh"
 
 namespace b200mp {
 
@@ -50,6 +51,7 @@ struct TrackDev {
     int *target_idx;
     const double *mu_table;   // friction table of parameter set 0 (vehicle_rhs.cuh), used by the no-log kernel
     double mu_B2;
+    int2 *hint;               // [V] (nearest waypoint, previous look-ahead index) handed from one time slice to the next
 };
 
 __device__ __forceinline__ double host_sq(double v0, double v1, int mode)
@@ -294,10 +296,18 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
     return la;
 }
 
+// The launch is cut into (vehicle block, time chunk) items claimed by persistent CTAs through a ticket, exactly as the
+// rollout kernel does (slice_sched.cuh): 65,536 vehicles at 8 warps/SM are 1.73 waves, i.e. the second wave used to run at
+// 73 % occupancy for a whole launch.  A chunk is a multiple of ctrl_every and of store_stride, so a slice starts on a
+// control update and a stored step; the carried state goes through state_end / ctrl_end / hint in L2.  Launches that are not
+// sliced run the SAME kernel with one block per CTA (sc.counter == NULL, a run-time switch): one compiled instruction
+// sequence for every launch shape, so the compiler's FMA contraction choices -- and with them the last bits -- do not depend
+// on the fleet size (a separately compiled plain kernel differed from the sliced one by 1 ulp in 6 % of the vehicles).
 template <bool LOG, bool TAB>
 __global__ void __launch_bounds__(kTrackBlock)
-track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevParams<double> P0)
+track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevParams<double> P0, const __grid_constant__ SliceSched sc)
 {
+    __shared__ int s_item;
     extern __shared__ __align__(16) unsigned char s_dyn[];   // the friction table (dynamic: 48 KB and more)
     double *s_mu = reinterpret_cast<double *>(s_dyn);
     MuTableView T;
@@ -307,123 +317,167 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
         for (int i = threadIdx.x; i < kMuTableDoubles; i += kTrackBlock) s_mu[i] = a.mu_table[i];
         __syncthreads();
     }
-    const int set = blockIdx.x / a.blocks_per_set;
-    const int local = (blockIdx.x - set * a.blocks_per_set) * kTrackBlock + threadIdx.x;
-    const int r = set * a.vps + local;
-    if (local >= a.vps || r >= a.V) return;
     const size_t V = (size_t)a.V;
-    const double2 *w = a.wp + (size_t)set * a.w_max;
-    const double *hd = a.head + (size_t)set * a.w_max;
-    const int W = a.wp_count[set];
-    SetView sv;
-    sv.w = w;
-    sv.fh = a.heads + (size_t)set * a.heads_stride;
-    sv.ch = sv.fh + (a.w_max + kFine - 1) / kFine;
-    sv.sg = a.seg + (size_t)set * a.w_max;
-    sv.cm = a.cum + (size_t)set * a.w_max;
-    sv.W = W;
-    sv.rfine = a.rmax[2 * set];
-    sv.rcoarse = a.rmax[2 * set + 1];
-    sv.clean = a.clean[set] != 0.0;
-    int nearest = -1, la_prev = -1;
+    const bool SLICED = sc.counter != nullptr;   // run-time: one-chunk launches take one block per CTA, no ticket
+    int item = blockIdx.x;
+    for (;;) {
+        if (SLICED) {
+            if (threadIdx.x == 0) s_item = atomicAdd(sc.counter, 1);
+            __syncthreads();
+            item = s_item;
+            __syncthreads();   // s_item is rewritten by the next round
+            if (item >= sc.n_blocks * sc.n_chunks) break;
+        }
+        const int chunk_idx = SLICED ? item / sc.n_blocks : 0;
+        const int blk = SLICED ? item - chunk_idx * sc.n_blocks : item;
+        const int n_begin = SLICED ? chunk_idx * sc.chunk : 0;
+        const int n_stop = SLICED ? min(a.n_steps, n_begin + sc.chunk) : a.n_steps;
+        if (SLICED && chunk_idx > 0) {   // wait for this block's previous time-chunk
+            if (threadIdx.x == 0)
+                while (ld_acquire(sc.done + blk) < chunk_idx) __nanosleep(100);
+            __syncthreads();
+        }
+        const int set = blk / a.blocks_per_set;
+        const int local = (blk - set * a.blocks_per_set) * kTrackBlock + threadIdx.x;
+        const int r = set * a.vps + local;
+        if (local < a.vps && r < a.V) {
+            const double2 *w = a.wp + (size_t)set * a.w_max;
+            const double *hd = a.head + (size_t)set * a.w_max;
+            const int W = a.wp_count[set];
+            SetView sv;
+            sv.w = w;
+            sv.fh = a.heads + (size_t)set * a.heads_stride;
+            sv.ch = sv.fh + (a.w_max + kFine - 1) / kFine;
+            sv.sg = a.seg + (size_t)set * a.w_max;
+            sv.cm = a.cum + (size_t)set * a.w_max;
+            sv.W = W;
+            sv.rfine = a.rmax[2 * set];
+            sv.rcoarse = a.rmax[2 * set + 1];
+            sv.clean = a.clean[set] != 0.0;
+            int nearest = -1, la_prev = -1;
 
-    double y[10], ax, ay;
+            double y[10], ax, ay, x_del, e_int, prev_v;
+            if (!SLICED || chunk_idx == 0) {
 #pragma unroll
-    for (int c = 0; c < 10; ++c) y[c] = a.state0[c * V + r];
-    ax = a.state0[10 * V + r];
-    ay = a.state0[11 * V + r];
-    double x_del = a.ctrl0[r], e_int = a.ctrl0[V + r], prev_v = a.ctrl0[2 * V + r];
-    double delta = 0.0, tau = 0.0, cte = 0.0;
-    WheelCtrl<double> c;
-    set_steer<double, true>(c, &delta);
-    c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = 0.0;
-
-    double *tp = a.traj ? a.traj + r : nullptr;
-    double *lp = (LOG && a.log) ? a.log + r : nullptr;
-    int until_store = a.store_stride;
-
-    int n = 0;
-    while (n < a.n_steps) {
-        {   // ---- controllers (drive.py:128-138) on the current state
-            const double v = y[0], yaw = y[7], px = y[8], py = y[9];
-            int ce = 0;
-            double raw;
-            if (W > 0) {
-                ce = lookahead_index(sv, px, py, a.lookahead, a.norm_mode, nearest, la_prev, &nearest);
-                la_prev = ce;
-                double sn, cs;
-                sincos(yaw, &sn, &cs);
-                const double2 t = w[ce];
-                const double cv0 = __dsub_rn(__dsub_rn(t.x, px), __dmul_rn(a.lookahead, cs));   // :88-92
-                const double cv1 = __dsub_rn(__dsub_rn(t.y, py), __dmul_rn(a.lookahead, sn));
-                cte = __dsqrt_rn(host_sq(cv0, cv1, a.norm_mode));
-                if (cte < a.deadband) cte = 0.0;                                               // :95-96
-                double che = atan2(cv1, cv0) - yaw;                                            // :99-102
-                che = py_mod(che + kPi, 2.0 * kPi) - kPi;
-                const double sgn = che > 0.0 ? 1.0 : (che < 0.0 ? -1.0 : che);
-                double he = hd[ce] - yaw;                                                      // :107-121
-                he = py_mod(he + kPi, 2.0 * kPi) - kPi;
-                const double steer = he + atan(__ddiv_rn(__dmul_rn(__dmul_rn(a.k, sgn), cte), v + a.k_soft));   // :122-124
-                raw = fmin(fmax(steer, -a.max_steer), a.max_steer);                            // :126
-                if (steer != steer) raw = steer;                                               // np.clip keeps NaN
-            } else {
-                raw = 0.0;
-                cte = 0.0;
+                for (int c = 0; c < 10; ++c) y[c] = a.state0[c * V + r];
+                ax = a.state0[10 * V + r];
+                ay = a.state0[11 * V + r];
+                x_del = a.ctrl0[r];
+                e_int = a.ctrl0[V + r];
+                prev_v = a.ctrl0[2 * V + r];
+            } else {   // carried state, written by another SM: read through L2
+#pragma unroll
+                for (int c = 0; c < 10; ++c) y[c] = __ldcg(a.state_end + c * V + r);
+                ax = __ldcg(a.state_end + 10 * V + r);
+                ay = __ldcg(a.state_end + 11 * V + r);
+                x_del = __ldcg(a.ctrl_end + r);
+                e_int = __ldcg(a.ctrl_end + V + r);
+                prev_v = __ldcg(a.ctrl_end + 2 * V + r);
+                const int2 h = __ldcg(a.hint + r);   // search hints only: the indices found do not depend on them
+                nearest = h.x;
+                la_prev = h.y;
             }
-            const double vel_error = a.target_vel - v;                                         // :149-155
-            e_int = __dadd_rn(e_int, __dmul_rn(vel_error, a.dt));
-            const double pp = __dmul_rn(a.kp, vel_error), ii = __dmul_rn(a.ki, e_int);
-            const double dd = __ddiv_rn(__dmul_rn(a.kd, v - prev_v), a.dt);
-            tau = __dadd_rn(__dadd_rn(pp, ii), dd);
-            if (v <= 0.01) tau = fabs(tau);                                                    // :157-158
-            prev_v = v;
-            x_del = __dadd_rn(__dmul_rn(1.0 - a.alpha, x_del), __dmul_rn(a.alpha, raw));       // drive.py:137
-            delta = x_del;
+            double delta = 0.0, tau = 0.0, cte = 0.0;
+            WheelCtrl<double> c;
             set_steer<double, true>(c, &delta);
-            c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = tau * P0.inv_Jw;
-            if (a.target_idx) a.target_idx[(size_t)(n / a.ctrl_every) * V + r] = ce;
-        }
-        const int n_end = min(a.n_steps, n + a.ctrl_every);
-#pragma unroll 1
-        for (; n < n_end; ++n) {
-            double sdot[LOG ? 10 : 1], outs[LOG ? 18 : 1];
-            // the DataLog needs state_dot and the 18 outputs (combined slips included) only for the steps it stores:
-            // those take the closed-form logging step, every other step of a logging launch the tabulated one
-            if (LOG && !(TAB && !(a.store_stride > 0 && until_store == 1)))
-                rk4_step<double, true, true, true, false, false>(P0, P0.Dc, c, a.dt, y, ax, ay, sdot, outs);
-            else
-                rk4_step<double, true, false, true, true, TAB>(P0, P0.Dc, c, a.dt, y, ax, ay, sdot, outs, T);
-            if (a.store_stride > 0 && --until_store == 0) {
-                until_store = a.store_stride;
-                if (tp) {
-#pragma unroll
-                    for (int k = 0; k < 10; ++k) tp[k * V] = y[k];
-                    tp += 10 * V;
+            c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = 0.0;
+
+            const size_t out0 = a.store_stride > 0 ? (size_t)(n_begin / a.store_stride) : 0;
+            double *tp = a.traj ? a.traj + out0 * 10 * V + r : nullptr;
+            double *lp = (LOG && a.log) ? a.log + out0 * 45 * V + r : nullptr;
+            int until_store = a.store_stride;
+
+            int n = n_begin;
+            while (n < n_stop) {
+                {   // ---- controllers (drive.py:128-138) on the current state
+                    const double v = y[0], yaw = y[7], px = y[8], py = y[9];
+                    int ce = 0;
+                    double raw;
+                    if (W > 0) {
+                        ce = lookahead_index(sv, px, py, a.lookahead, a.norm_mode, nearest, la_prev, &nearest);
+                        la_prev = ce;
+                        double sn, cs;
+                        sincos(yaw, &sn, &cs);
+                        const double2 t = w[ce];
+                        const double cv0 = __dsub_rn(__dsub_rn(t.x, px), __dmul_rn(a.lookahead, cs));   // :88-92
+                        const double cv1 = __dsub_rn(__dsub_rn(t.y, py), __dmul_rn(a.lookahead, sn));
+                        cte = __dsqrt_rn(host_sq(cv0, cv1, a.norm_mode));
+                        if (cte < a.deadband) cte = 0.0;                                               // :95-96
+                        double che = atan2(cv1, cv0) - yaw;                                            // :99-102
+                        che = py_mod(che + kPi, 2.0 * kPi) - kPi;
+                        const double sgn = che > 0.0 ? 1.0 : (che < 0.0 ? -1.0 : che);
+                        double he = hd[ce] - yaw;                                                      // :107-121
+                        he = py_mod(he + kPi, 2.0 * kPi) - kPi;
+                        const double steer = he + atan(__ddiv_rn(__dmul_rn(__dmul_rn(a.k, sgn), cte), v + a.k_soft));   // :122-124
+                        raw = fmin(fmax(steer, -a.max_steer), a.max_steer);                            // :126
+                        if (steer != steer) raw = steer;                                               // np.clip keeps NaN
+                    } else {
+                        raw = 0.0;
+                        cte = 0.0;
+                    }
+                    const double vel_error = a.target_vel - v;                                         // :149-155
+                    e_int = __dadd_rn(e_int, __dmul_rn(vel_error, a.dt));
+                    const double pp = __dmul_rn(a.kp, vel_error), ii = __dmul_rn(a.ki, e_int);
+                    const double dd = __ddiv_rn(__dmul_rn(a.kd, v - prev_v), a.dt);
+                    tau = __dadd_rn(__dadd_rn(pp, ii), dd);
+                    if (v <= 0.01) tau = fabs(tau);                                                    // :157-158
+                    prev_v = v;
+                    x_del = __dadd_rn(__dmul_rn(1.0 - a.alpha, x_del), __dmul_rn(a.alpha, raw));       // drive.py:137
+                    delta = x_del;
+                    set_steer<double, true>(c, &delta);
+                    c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = tau * P0.inv_Jw;
+                    if (a.target_idx) a.target_idx[(size_t)(n / a.ctrl_every) * V + r] = ce;
                 }
-                if (LOG && lp) {   // the DataLog row of drive.py:145-151
-                    lp[0] = __dmul_rn((double)(a.step0 + n), a.dt);
+                const int n_end = min(n_stop, n + a.ctrl_every);
+#pragma unroll 1
+                for (; n < n_end; ++n) {
+                    double sdot[LOG ? 10 : 1], outs[LOG ? 18 : 1];
+                    // the DataLog needs state_dot and the 18 outputs (combined slips included) only for the steps it stores:
+                    // those take the closed-form logging step, every other step of a logging launch the tabulated one
+                    if (LOG && !(TAB && !(a.store_stride > 0 && until_store == 1)))
+                        rk4_step<double, true, true, true, false, false>(P0, P0.Dc, c, a.dt, y, ax, ay, sdot, outs);
+                    else
+                        rk4_step<double, true, false, true, true, TAB>(P0, P0.Dc, c, a.dt, y, ax, ay, sdot, outs, T);
+                    if (a.store_stride > 0 && --until_store == 0) {
+                        until_store = a.store_stride;
+                        if (tp) {
 #pragma unroll
-                    for (int k = 0; k < 10; ++k) lp[(1 + k) * V] = y[k];
+                            for (int k = 0; k < 10; ++k) tp[k * V] = y[k];
+                            tp += 10 * V;
+                        }
+                        if (LOG && lp) {   // the DataLog row of drive.py:145-151
+                            lp[0] = __dmul_rn((double)(a.step0 + n), a.dt);
 #pragma unroll
-                    for (int k = 0; k < 10; ++k) lp[(11 + k) * V] = sdot[k];
-                    lp[21 * V] = delta;
+                            for (int k = 0; k < 10; ++k) lp[(1 + k) * V] = y[k];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) lp[(22 + k) * V] = tau;
+                            for (int k = 0; k < 10; ++k) lp[(11 + k) * V] = sdot[k];
+                            lp[21 * V] = delta;
 #pragma unroll
-                    for (int k = 0; k < 18; ++k) lp[(26 + k) * V] = outs[k];
-                    lp[44 * V] = cte;
-                    lp += 45 * V;
+                            for (int k = 0; k < 4; ++k) lp[(22 + k) * V] = tau;
+#pragma unroll
+                            for (int k = 0; k < 18; ++k) lp[(26 + k) * V] = outs[k];
+                            lp[44 * V] = cte;
+                            lp += 45 * V;
+                        }
+                    }
                 }
             }
-        }
-    }
 #pragma unroll
-    for (int k = 0; k < 10; ++k) a.state_end[k * V + r] = y[k];
-    a.state_end[10 * V + r] = ax;
-    a.state_end[11 * V + r] = ay;
-    a.ctrl_end[r] = x_del;
-    a.ctrl_end[V + r] = e_int;
-    a.ctrl_end[2 * V + r] = prev_v;
+            for (int k = 0; k < 10; ++k) a.state_end[k * V + r] = y[k];
+            a.state_end[10 * V + r] = ax;
+            a.state_end[11 * V + r] = ay;
+            a.ctrl_end[r] = x_del;
+            a.ctrl_end[V + r] = e_int;
+            a.ctrl_end[2 * V + r] = prev_v;
+            if (SLICED && chunk_idx + 1 < sc.n_chunks) a.hint[r] = make_int2(nearest, la_prev);
+        }
+        if (SLICED && chunk_idx + 1 < sc.n_chunks) {   // publish the carried state of this block
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release(sc.done + blk, chunk_idx + 1);
+        }
+        if (!SLICED) break;
+    }
 }
 
 int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
@@ -475,8 +529,10 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     const size_t per = (size_t)g.n_sets * (size_t)(g.w_max > 0 ? g.w_max : 1);
     const int heads_stride = (g.w_max + kFine - 1) / kFine + (g.w_max + kCoarse - 1) / kCoarse + 1;
     void *scratch = nullptr;
-    int rc = ensure_scratch(device, st, sizeof(double) * (3 * per + 4 * (size_t)g.n_sets + 2) + sizeof(double2) * (size_t)g.n_sets * (size_t)heads_stride, &scratch);
+    const size_t tables_bytes = (sizeof(double) * (3 * per + 4 * (size_t)g.n_sets + 2) + sizeof(double2) * (size_t)g.n_sets * (size_t)heads_stride + 15) & ~(size_t)15;
+    int rc = ensure_scratch(device, st, tables_bytes + sizeof(int2) * (size_t)g.V, &scratch);
     if (rc) return rc;
+    void *hint_area = (char *)scratch + tables_bytes;   // search hints handed between the time slices of a launch
     TrackDev a;
     a.V = g.V;
     a.n_steps = g.n_steps;
@@ -515,6 +571,7 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     a.state_end = g.state_end;
     a.ctrl_end = g.ctrl_end;
     a.target_idx = g.target_idx;
+    a.hint = nullptr;
     track_prepare_kernel<<<g.n_sets, 256, 0, st>>>(g.w_max, a.wp, g.wp_count, g.norm_mode, (double *)a.seg, (double *)a.head,
                                                    (double *)a.cum, (double *)a.rmax, (double *)a.clean,
                                                    (double2 *)a.heads, heads_stride);
@@ -529,19 +586,60 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     a.mu_B2 = ds.mu_table_B2;
     const int fmode = (g.friction_override >= 1 && g.friction_override <= 2) ? g.friction_override - 1 : friction_mode();
     const bool tab = ds.mu_table && ds.mu_table_B2 > 0.0 && fmode == B200MP_FRICTION_AUTO;
-    const size_t smem = sizeof(double) * kMuTableDoubles;
-    if (tab) {   // dynamic shared memory beyond 48 KB is an opt-in per function
-        B200MP_CUDA(cudaFuncSetAttribute(track_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        B200MP_CUDA(cudaFuncSetAttribute(track_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem_tab = sizeof(double) * kMuTableDoubles;
+    const bool log = g.log != nullptr;
+    const bool tab_used = tab && (!log || g.store_stride > 1);   // a logging launch that stores every step never takes the table
+    const size_t smem = tab_used ? smem_tab : 0;
+    // the four (LOG, TAB) combinations
+    typedef void (*Kern)(const TrackDev, const DevParams<double>, const SliceSched);
+    const Kern kern = log ? (tab_used ? (Kern)track_kernel<true, true> : (Kern)track_kernel<true, false>)
+                          : (tab_used ? (Kern)track_kernel<false, true> : (Kern)track_kernel<false, false>);
+    if (smem)   // dynamic shared memory beyond 48 KB is an opt-in per function
+        B200MP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // time slicing: only when the launch is more than one wave but too few waves for the tail to vanish
+    int dev_id = 0, sms = 0, occ = 0;
+    B200MP_CUDA(cudaGetDevice(&dev_id));
+    B200MP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
+    B200MP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTrackBlock, smem));
+    const int resident = sms * (occ > 0 ? occ : 1);
+    const int n_blocks = (int)grid;
+    SliceSched sc{nullptr, nullptr, n_blocks, 1, g.n_steps};
+    int unit = g.ctrl_every;   // a slice starts on a control update and on a stored step
+    if (a.store_stride > 1) {
+        int x = unit, y = a.store_stride;
+        while (y) { const int t = x % y; x = y; y = t; }
+        unit = unit / x * a.store_stride;
     }
-    if (g.log && tab && g.store_stride > 1)   // logging launch that stores a subset of the steps
-        track_kernel<true, true><<<(int)grid, kTrackBlock, smem, st>>>(a, P0);
-    else if (g.log)
-        track_kernel<true, false><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
-    else if (tab)
-        track_kernel<false, true><<<(int)grid, kTrackBlock, smem, st>>>(a, P0);
-    else
-        track_kernel<false, false><<<(int)grid, kTrackBlock, 0, st>>>(a, P0);
+    if (n_blocks > resident && n_blocks < 8 * resident && g.n_steps >= 4 * unit &&
+        sizeof(int) * ((size_t)n_blocks + 1) <= kSchedSlotBytes) {
+        long long want = (12LL * resident + n_blocks - 1) / n_blocks;      // ~12 rounds of items
+        int chunk = (int)((g.n_steps + want - 1) / want);
+        chunk = (chunk + unit - 1) / unit * unit;
+        if (chunk < 2 * unit) chunk = 2 * unit;
+        const int n_chunks = (g.n_steps + chunk - 1) / chunk;
+        if (n_chunks > 1) {
+            sc.n_chunks = n_chunks;
+            sc.chunk = chunk;
+        }
+    }
+    a.hint = (int2 *)hint_area;
+    if (sc.n_chunks > 1) {
+        void *sched_mem = nullptr;
+        cudaEvent_t sched_done = nullptr;
+        rc = acquire_sched_slot(device, &sched_mem, &sched_done);
+        if (rc) return rc;
+        B200MP_CUDA(cudaMemsetAsync(sched_mem, 0, sizeof(int) * ((size_t)n_blocks + 1), st));
+        sc.counter = (int *)sched_mem;
+        sc.done = (int *)sched_mem + 1;
+        const long long items = (long long)n_blocks * sc.n_chunks;
+        kern<<<(int)(items < resident ? items : resident), kTrackBlock, smem, st>>>(a, P0, sc);
+        cudaError_t e = cudaGetLastError();
+        cudaError_t e2 = cudaEventRecord(sched_done, st);
+        if (e == cudaSuccess) e = e2;
+        if (e != cudaSuccess) return cuda_fail(e, "track_kernel launch");
+        return 0;
+    }
+    kern<<<n_blocks, kTrackBlock, smem, st>>>(a, P0, sc);   // one block per CTA, one chunk: the same kernel without the ticket
     B200MP_CUDA(cudaGetLastError());
     return 0;
 }

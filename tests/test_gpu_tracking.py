@@ -161,3 +161,41 @@ def test_tracking_edge_cases(engine):
                                    ctrl_every=4, store_stride=1, want_log=True, want_target_idx=True, norm_mode=mode)
     assert np.array_equal(_np(res.target_idx), ref["target_idx"])
     assert rel_err(_np(res.log), ref["log"]).max() < REL_TOL_F64
+
+
+def test_tracking_time_sliced_launch_equals_plain_launches(engine):
+    """A launch of more than one wave of vehicles is cut into (block, time-chunk) items on persistent CTAs (the carried
+    state, controller state and search hints go through L2): every output must equal, bit for bit, what plain launches
+    (one wave each) produce -- trajectories, DataLog rows, look-ahead indices and resumable end state."""
+    _setup(engine)
+    n_sets, vps, N = 12, 4096, 200                      # 49,152 vehicles = 768 blocks: more than the 592 resident CTAs
+    V = n_sets * vps
+    st0, wps = wl.tracking_fleet(V, n_sets)
+    mode = host_norm2_mode()
+    for kw in (dict(store_stride=20, want_target_idx=True), dict(store_stride=20, want_log=True), dict()):
+        big = engine.track_closed_loop(st0, wps, DT, N, 25.0, vehicles_per_set=vps, norm_mode=mode, **kw)
+        parts = []
+        for s0 in range(0, n_sets, 4):                  # 16,384 vehicles = 256 blocks per launch: the plain kernel
+            lo, hi = s0 * vps, (s0 + 4) * vps
+            parts.append(engine.track_closed_loop(st0[:, lo:hi], wps[s0:s0 + 4], DT, N, 25.0, vehicles_per_set=vps,
+                                                  norm_mode=mode, **kw))
+        assert torch.equal(big.state_end, torch.cat([p.state_end for p in parts], dim=1))
+        assert torch.equal(big.ctrl_end, torch.cat([p.ctrl_end for p in parts], dim=1))
+        if big.traj is not None:
+            assert torch.equal(big.traj, torch.cat([p.traj for p in parts], dim=2))
+        if big.log is not None:
+            assert torch.equal(big.log, torch.cat([p.log for p in parts], dim=2))
+        if big.target_idx is not None:
+            assert torch.equal(big.target_idx, torch.cat([p.target_idx for p in parts], dim=1))
+    # and against the C oracle on a strided subsample of the big launch (the oracle scans 3,000 waypoints per update)
+    par = _setup(engine)
+    big = engine.track_closed_loop(st0, wps, DT, N, 25.0, vehicles_per_set=vps, norm_mode=mode, want_target_idx=True)
+    sub = np.arange(0, vps, 64)
+    for s in (0, 5, 11):
+        idx = s * vps + sub
+        c0 = np.zeros((3, len(idx)))
+        c0[2] = st0[0, idx]
+        ref = c_oracle.track_loop(st0[:, idx], c0, wps[s:s + 1], None, par, DT, N, 25.0, c_oracle.track_gains(), mode,
+                                  vehicles_per_set=len(idx))
+        assert np.array_equal(_np(big.target_idx)[:, idx], ref["target_idx"])
+        assert rel_err(_np(big.state_end)[:, idx], ref["state_end"]).max() < REL_TOL_F64
