@@ -23,6 +23,19 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
+#ifndef B200MP_SLICE_NANOSLEEP
+#define B200MP_SLICE_NANOSLEEP 100
+#endif
+#ifdef B200MP_SLICE_PROFILE
+// development only (tools/kbench.cu): where the time of a time-sliced launch goes besides the steps themselves
+__device__ unsigned long long g_slice_prof[8];   // spin, prologue, epilogue cycles (thread 0 of every CTA), items, spins > 0
+#define SLICE_PROF_T(var) const long long var = clock64()
+#define SLICE_PROF_ADD(i, v) do { if (threadIdx.x == 0) atomicAdd(&g_slice_prof[i], (unsigned long long)(v)); } while (0)
+#else
+#define SLICE_PROF_T(var)
+#define SLICE_PROF_ADD(i, v)
+#endif
+
 template <typename R> struct RolloutDev {
     int B, n_steps, step0, hold, store_stride, torque_ch;
     R dt;
@@ -112,11 +125,19 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
         const int blk = SLICED ? item - chunk_idx * sc.n_blocks : item;
         const int n_begin = SLICED ? chunk_idx * sc.chunk : 0;
         const int n_end = SLICED ? min(a.n_steps, n_begin + sc.chunk) : a.n_steps;
+        SLICE_PROF_T(t_claim);
         if (SLICED && chunk_idx > 0) {   // wait for this block's previous time-chunk
-            if (threadIdx.x == 0)
-                while (ld_acquire(sc.done + blk) < chunk_idx) __nanosleep(100);
+            if (threadIdx.x == 0) {
+#ifdef B200MP_SLICE_PROFILE
+                if (ld_acquire(sc.done + blk) < chunk_idx) atomicAdd(&g_slice_prof[4], 1ULL);
+#endif
+                while (ld_acquire(sc.done + blk) < chunk_idx) __nanosleep(B200MP_SLICE_NANOSLEEP);
+            }
             __syncthreads();
         }
+        SLICE_PROF_T(t_ready);
+        SLICE_PROF_ADD(0, t_ready - t_claim);
+        SLICE_PROF_ADD(3, 1);
         const int r = blk * kRolloutBlock + threadIdx.x;
         // GENERIC + TAB: per-rollout parameter sets / mu_max.  When every rollout of this block uses the same set
         // (set-major parameter sweeps; any batch with one set and per-rollout mu_max) and that set has a friction table,
@@ -249,6 +270,8 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
                     c = cn;
                 }
             }
+            SLICE_PROF_T(t_loop);
+            SLICE_PROF_ADD(1, t_loop - t_ready);
             while (!H1 && n < n_end) {
                 const int seg = (a.step0 + n) / a.hold;
                 int seg_end = (seg + 1) * a.hold - a.step0;
@@ -291,11 +314,18 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
                     step_body(n);
                 }
             }
+            SLICE_PROF_T(t_done);
 #pragma unroll
             for (int cidx = 0; cidx < 10; ++cidx) a.state_end[cidx * B + r] = y[cidx];
             a.state_end[10 * B + r] = ax;
             a.state_end[11 * B + r] = ay;
             if (COST && a.cost) a.cost[r] = J;
+#ifdef B200MP_SLICE_PROFILE
+            __threadfence();
+            __syncthreads();
+            SLICE_PROF_ADD(2, clock64() - t_done);
+            SLICE_PROF_ADD(5, t_done - t_loop);
+#endif
         }
         if (SLICED && chunk_idx + 1 < sc.n_chunks) {   // publish the carried state of this block
             __threadfence();
@@ -507,6 +537,17 @@ static int launch_rollout(int device, cudaStream_t st, const B200mpRolloutArgs &
 
 // One translation unit per precision (rollout_kernels_f64.cu / rollout_kernels_f32.cu define the macro): the two sets
 // of ~40 kernel instantiations compile in parallel.
+#if defined(B200MP_ROLLOUT_F64) && defined(B200MP_SLICE_PROFILE)
+extern "C" int b200mp_debug_slice_prof(unsigned long long *out8, int reset)
+{
+    if (out8) cudaMemcpyFromSymbol(out8, g_slice_prof, sizeof(unsigned long long) * 8);
+    if (reset) {
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_slice_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 #if defined(B200MP_ROLLOUT_F64)
 int launch_rollout_f64(int device, cudaStream_t st, const B200mpRolloutArgs &a) { return launch_rollout<double>(device, st, a); }
 #endif

@@ -295,3 +295,32 @@ def test_collision_filter_exceptional_values(engine, size):
     o = obs.copy()
     o[5] = (px[3, 7], py[3, 7])
     both(px, py, o)
+
+
+def test_calls_on_two_streams_do_not_share_scratch(engine):
+    """the ABI is asynchronous on the caller's stream; the library's scratch areas are per (device, stream), so
+    interleaved calls on two streams (broad-phase collision + min-clearance + select_best on each) give the results of the
+    same calls made one after the other."""
+    wa, wb = wl.config3_lattice(P=1024, M=6000), wl.config3_lattice(P=768, M=9000, seed=wl.SEED + 1)
+    serial = []
+    for w in (wa, wb):
+        f = engine.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD)
+        f2, c = engine.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD, want_clearance=True)
+        serial.append((f.clone(), c.clone()))
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    dev = {k: {n: engine.dev(w[n]) for n in ("px", "py", "obstacles")} for k, w in (("a", wa), ("b", wb))}
+    trig = {"a": engine.path_trig(wa["pyaw"], 49), "b": engine.path_trig(wb["pyaw"], 49)}
+    torch.cuda.synchronize()
+    out = {"a": [], "b": []}
+    for _ in range(6):                                   # interleave: neither stream waits for the other
+        for k, st in (("a", sa), ("b", sb)):
+            with torch.cuda.stream(st):
+                x = dev[k]
+                f, c = engine.collision_check_batch(x["px"], x["py"], None, x["obstacles"], OFF, RAD, trig=trig[k], want_clearance=True)
+                f1 = engine.collision_check_batch(x["px"], x["py"], None, x["obstacles"], OFF, RAD, trig=trig[k])
+                out[k].append((f1, c))
+    torch.cuda.synchronize()
+    for k, ref in (("a", serial[0]), ("b", serial[1])):
+        for f1, c in out[k]:
+            assert torch.equal(f1, ref[0]) and torch.equal(c.view(torch.int64), ref[1].view(torch.int64)), k

@@ -398,3 +398,46 @@ def test_state_broadcast_winner_record_and_per_call_friction(engine):
         assert torch.equal(a.state_end, b.state_end)
     with pytest.raises(ValueError):
         engine.rollout(s0, d, t, DT, N, friction="table")
+
+
+def test_param_set_range_and_endstate_pipeline_segments(engine):
+    """(i) per-rollout parameter-set indices outside the uploaded table are rejected on the host when they come
+    as host data and clamped in the kernel when they come as a device tensor (never an out-of-bounds read);
+    (ii) ``rollout_endstate_to_host`` with ``hold`` not dividing the chunk waits for the upload that covers the LAST
+    control segment a launch reads (n_steps = 100, hold = 30 needs segment 3)."""
+    B, N = 512, 100
+    s0, _, _ = wl.config2_rollouts(B=B, n_steps=N)
+    rng = np.random.default_rng(5)
+    sets = np.stack([rng.uniform(8.0, 25.0, 3), rng.uniform(1.2, 1.9, 3), rng.uniform(0.3, 1.2, 3)], 1)
+    p = VehicleParameters()
+    for w in ("FL", "FR", "RL", "RR"):
+        setattr(p, "B" + w, sets[:, 0]); setattr(p, "C" + w, sets[:, 1]); setattr(p, "D" + w, sets[:, 2])
+    assert engine.set_params(p) == 3
+    d = rng.uniform(-0.05, 0.05, (4, 1, B))
+    t = rng.uniform(-200.0, 200.0, (4, 1, B))
+    ps = rng.integers(0, 3, B).astype(np.int32)
+    good = engine.rollout(s0, d, t, DT, N, hold=30, param_set=ps)
+    bad = ps.copy()
+    bad[7], bad[9] = 3, -1
+    with pytest.raises(ValueError):
+        engine.rollout(s0, d, t, DT, N, hold=30, param_set=bad)
+    with pytest.raises(ValueError):
+        engine.planar_model_batch(s0[:10], np.zeros((4, B)), None, np.zeros((4, B)), np.zeros(B), np.zeros(B), param_set=bad)
+    # as a device tensor the indices are not read back: the kernel clamps them to [0, n_sets)
+    clamped = ps.copy()
+    clamped[7], clamped[9] = 2, 0
+    got = engine.rollout(s0, d, t, DT, N, hold=30, param_set=torch.from_numpy(bad).cuda())
+    want = engine.rollout(s0, d, t, DT, N, hold=30, param_set=clamped)
+    assert torch.equal(got.state_end, want.state_end)
+    keep = np.ones(B, dtype=bool)
+    keep[[7, 9]] = False
+    assert torch.equal(got.state_end[:, torch.from_numpy(keep).cuda()], good.state_end[:, torch.from_numpy(keep).cuda()])
+    # (ii) end-state pipeline, hold = 30 (segments 0..3 for 100 steps), one chunk and several chunk sizes
+    engine.set_params(_params())
+    dev = engine.rollout(s0, d, t, DT, N, hold=30)
+    hs, hd, ht = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (s0, d, t))
+    end_host = torch.empty(12, B, dtype=torch.float64).pin_memory()
+    for chunk in (100, 200, 60, 30):
+        end_host.zero_()
+        engine.rollout_endstate_to_host(hs, hd, ht, DT, N, 30, end_host, chunk_steps=chunk)
+        assert torch.equal(end_host, dev.state_end.cpu()), chunk

@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 #include "../include/b200mp.h"
 
+#ifdef B200MP_SLICE_PROFILE
+extern "C" int b200mp_debug_slice_prof(unsigned long long *, int);
+#endif
 static double lcg(unsigned long long &s) { s = s * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(s >> 11) * (1.0 / 9007199254740992.0); }
 
 int main(int argc, char **argv)
@@ -56,6 +59,18 @@ int main(int argc, char **argv)
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (i >= 3) { sum += ms; if (ms < best) best = ms; }
     }
+#ifdef B200MP_SLICE_PROFILE
+    {
+        unsigned long long q[8];
+        b200mp_debug_slice_prof(nullptr, 1);
+        b200mp_rk4_rollout_f64(0, nullptr, &a);
+        cudaDeviceSynchronize();
+        b200mp_debug_slice_prof(q, 0);
+        const double it = (double)q[3];
+        printf("   slice profile: %.0f items; per item: wait %.0f, prologue %.0f, steps %.0f, epilogue %.0f cycles; %.1f %% of the items found their predecessor unfinished\n",
+               it, q[0] / it, q[1] / it, q[5] / it, q[2] / it, 100.0 * q[4] / it);
+    }
+#endif
     std::vector<double> end((size_t)12 * B);
     cudaMemcpy(end.data(), d_end, end.size() * 8, cudaMemcpyDeviceToHost);
     double cs = 0; for (double v : end) cs += v;

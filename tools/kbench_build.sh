@@ -15,4 +15,4 @@ nvcc $F $FLAGS -Xcompiler -fPIC -c $C/b200mp_api.cu -o $OUT/api_$NAME.o &
 nvcc $F $FLAGS -c $C/tracking_kernels.cu -o $OUT/tracking_$NAME.o &
 wait
 grep -A2 "rk4_rollout_kernelIdLb1ELb0ELb0E" $OUT/ptxas_$NAME.log | grep -E "registers|spill" | tr '\n' ' '; echo
-nvcc $F tools/kbench.cu $OUT/api_$NAME.o $B/collision_kernels.o $B/misc_kernels.o $OUT/tracking_$NAME.o $B/lattice_kernels.o $B/rollout_kernels_f32.o $OUT/rollout_$NAME.o -o $OUT/kbench_$NAME
+nvcc $F $FLAGS tools/kbench.cu $OUT/api_$NAME.o $B/collision_kernels.o $B/misc_kernels.o $OUT/tracking_$NAME.o $B/lattice_kernels.o $B/rollout_kernels_f32.o $OUT/rollout_$NAME.o -o $OUT/kbench_$NAME
