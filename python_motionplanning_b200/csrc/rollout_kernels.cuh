@@ -13,6 +13,9 @@
 //   * bound: the FP64 (or FP32) CUDA-core pipe; no tensor cores (nothing is a contraction), HBM only
 //     for the 80 B/step trajectory writeback.
 #pragma once
+#include <mutex>
+#include <vector>
+
 #include "b200mp_internal.h"
 #include "slice_sched.cuh"
 
@@ -23,6 +26,33 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
+// Phase staggering.  The CTAs of a launch start together and do identical work, so the (two) warps that share a scheduler
+// run the same part of an RK4 step at the same time: both want the FP64 pipe in the wheel / polynomial sections and both
+// leave it idle in the serial sections (one wave of 37,888 rollouts x 500 steps runs at 1.93e10 steps/s, eight waves -- whose
+// CTAs start at scattered times -- at 2.08e10).  With STAGGER each CTA delays its start by a fraction of a step that depends on
+// its order of arrival on its SM (0, 1/2, 1/4, 3/4 of B200MP_STAGGER cycles), which costs < 2 us per launch.
+#ifndef B200MP_STAGGER
+#define B200MP_STAGGER 0
+#endif
+#if B200MP_STAGGER > 0
+__device__ unsigned int g_sm_arrivals[256];   // never reset: only the order modulo 4 matters
+__device__ __forceinline__ void stagger_start()
+{
+    __shared__ int s_delay;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned k = atomicAdd(&g_sm_arrivals[smid & 255], 1u) & 3u;
+        s_delay = (int)(((k & 1u) * 2u + (k >> 1)) * (B200MP_STAGGER / 4));     // k = 0,1,2,3 -> 0, 1/2, 1/4, 3/4
+    }
+    __syncthreads();
+    const long long t0 = clock64();
+    const int d = s_delay;
+    while (clock64() - t0 < d) {}
+}
+#else
+__device__ __forceinline__ void stagger_start() {}
+#endif
 #ifndef B200MP_SLICE_NANOSLEEP
 #define B200MP_SLICE_NANOSLEEP 100
 #endif
@@ -102,12 +132,15 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
     MuTableView T;
     T.c = s_mu;
     T.B2 = a.mu_B2;
-    if (TAB && !GENERIC) {   // one tyre for the whole launch: its table (D folded in) is staged once per CTA
-        const double *src = static_cast<const double *>(a.mu_table);
-        for (int i = threadIdx.x; i < kTabWords; i += kRolloutBlock) s_mu[i] = src[i];
+    if (TAB && !GENERIC) {   // one tyre for the whole launch: its table (D folded in) is staged once per CTA, 16 bytes per load
+        const double2 *src = static_cast<const double2 *>(a.mu_table);
+        double2 *dst = reinterpret_cast<double2 *>(s_mu);
+#pragma unroll 8
+        for (int i = threadIdx.x; i < kTabWords / 2; i += kRolloutBlock) dst[i] = src[i];
         __syncthreads();
     }
     if (TAB && GENERIC && threadIdx.x == 0) s_cur_set = -1;   // ordered by the barriers of the first item
+    if (!GENERIC && !AUX) stagger_start();
     const size_t B = (size_t)a.B;
     int item = blockIdx.x;
     for (;;) {
@@ -345,22 +378,36 @@ template <typename R> __global__ void broadcast_state_kernel(int B, const R *__r
     for (int c = 0; c < 12; ++c) out[(size_t)c * B + r] = s0[c];
 }
 
-// Resident CTAs per device for one kernel instantiation (cached per function pointer).
-template <typename K> static int resident_ctas(K kernel, size_t smem, int *out)
+// Resident CTAs per device for one kernel instantiation and the opt-in for dynamic shared memory beyond the default 48 KB
+// carve-out: both are queried / set ONCE per (function, shared-memory size) and cached -- the two driver calls cost tens of
+// microseconds, which is per-launch latency for the scalar drop-in path and several per cent of a one-wave launch.
+struct KernelInfo {
+    const void *fn;
+    size_t smem;
+    int resident;
+};
+template <typename K> static int kernel_info(K kernel, size_t smem, int *resident_out)
 {
-    int dev = 0, sms = 0, occ = 0;
+    static std::mutex mu;
+    static std::vector<KernelInfo> cache;
+    int dev = 0;
     B200MP_CUDA(cudaGetDevice(&dev));
+    const void *key = reinterpret_cast<const void *>(kernel);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (const KernelInfo &k : cache)
+            if (k.fn == key && k.smem == smem + ((size_t)dev << 48)) {
+                *resident_out = k.resident;
+                return 0;
+            }
+    }
+    if (smem) B200MP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0, occ = 0;
     B200MP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     B200MP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kRolloutBlock, smem));
-    *out = sms * (occ > 0 ? occ : 1);
-    return 0;
-}
-
-// dynamic shared memory beyond the default 48 KB carve-out needs a per-function opt-in (once per function and device)
-template <typename K> static int allow_dynamic_smem(K kernel, size_t smem)
-{
-    if (smem == 0) return 0;
-    B200MP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    *resident_out = sms * (occ > 0 ? occ : 1);
+    std::lock_guard<std::mutex> lock(mu);
+    cache.push_back(KernelInfo{key, smem + ((size_t)dev << 48), *resident_out});
     return 0;
 }
 
@@ -370,10 +417,9 @@ static int start_rollout(K kernel, K kernel_sliced, int device, cudaStream_t st,
                          const DevParams<R> &P0, size_t smem)
 {
     const int n_blocks = (a.B + kRolloutBlock - 1) / kRolloutBlock;
-    int resident = 0;
-    int rc = allow_dynamic_smem(kernel, smem);
-    if (!rc) rc = allow_dynamic_smem(kernel_sliced, smem);
-    if (!rc) rc = resident_ctas(kernel_sliced, smem, &resident);
+    int resident = 0, resident_plain = 0;
+    int rc = kernel_info(kernel, smem, &resident_plain);
+    if (!rc) rc = kernel_info(kernel_sliced, smem, &resident);
     if (rc) return rc;
     SliceSched sc{nullptr, nullptr, n_blocks, 1, a.n_steps};
     // slice only when the batch is more than one wave but too few waves for the tail to vanish

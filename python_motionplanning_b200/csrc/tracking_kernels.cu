@@ -28,6 +28,8 @@
 // Waypoints and per-set tables are read through L1 (a set is ~120 KB; the vehicles of a CTA share one set).
 #include <math.h>
 
+#include <mutex>
+
 #include "b200mp_internal.h"
 #include "slice_sched.cuh"
 
@@ -594,14 +596,32 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     typedef void (*Kern)(const TrackDev, const DevParams<double>, const SliceSched);
     const Kern kern = log ? (tab_used ? (Kern)track_kernel<true, true> : (Kern)track_kernel<true, false>)
                           : (tab_used ? (Kern)track_kernel<false, true> : (Kern)track_kernel<false, false>);
-    if (smem)   // dynamic shared memory beyond 48 KB is an opt-in per function
-        B200MP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // time slicing: only when the launch is more than one wave but too few waves for the tail to vanish
-    int dev_id = 0, sms = 0, occ = 0;
+    // opt-in for dynamic shared memory beyond 48 KB and the resident-CTA count: once per (kernel, device), cached
+    static std::mutex info_mu;
+    static struct { const void *fn; int dev; int resident; } info[16];
+    static int n_info = 0;
+    int dev_id = 0, resident = 0;
     B200MP_CUDA(cudaGetDevice(&dev_id));
-    B200MP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
-    B200MP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTrackBlock, smem));
-    const int resident = sms * (occ > 0 ? occ : 1);
+    {
+        std::lock_guard<std::mutex> lock(info_mu);
+        for (int i = 0; i < n_info; ++i)
+            if (info[i].fn == (const void *)kern && info[i].dev == dev_id) resident = info[i].resident;
+    }
+    if (!resident) {
+        if (smem) B200MP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int sms = 0, occ = 0;
+        B200MP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
+        B200MP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTrackBlock, smem));
+        resident = sms * (occ > 0 ? occ : 1);
+        std::lock_guard<std::mutex> lock(info_mu);
+        if (n_info < 16) {
+            info[n_info].fn = (const void *)kern;
+            info[n_info].dev = dev_id;
+            info[n_info].resident = resident;
+            ++n_info;
+        }
+    }
+    // time slicing: only when the launch is more than one wave but too few waves for the tail to vanish
     const int n_blocks = (int)grid;
     SliceSched sc{nullptr, nullptr, n_blocks, 1, g.n_steps};
     int unit = g.ctrl_every;   // a slice starts on a control update and on a stored step
