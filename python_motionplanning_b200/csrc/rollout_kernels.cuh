@@ -13,6 +13,8 @@
 //   * bound: the FP64 (or FP32) CUDA-core pipe; no tensor cores (nothing is a contraction), HBM only
 //     for the 80 B/step trajectory writeback.
 #pragma once
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -141,6 +143,11 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
     }
     if (TAB && GENERIC && threadIdx.x == 0) s_cur_set = -1;   // ordered by the barriers of the first item
     if (!GENERIC && !AUX) stagger_start();
+#ifdef B200MP_SLICE_PROFILE
+    unsigned long long gt0 = 0;
+    const long long ck0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+#endif
     const size_t B = (size_t)a.B;
     int item = blockIdx.x;
     for (;;) {
@@ -367,6 +374,14 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
         }
         if (!SLICED) break;
     }
+#ifdef B200MP_SLICE_PROFILE
+    if (threadIdx.x == 0) {   // SM clock actually delivered to this CTA: cycles elapsed per nanosecond of global time
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        atomicAdd(&g_slice_prof[6], (unsigned long long)(clock64() - ck0));
+        atomicAdd(&g_slice_prof[7], gt1 - gt0);
+    }
+#endif
 }
 
 // zero-step launch with a broadcast start state: state_end[c][r] = state0[c] (the state "passes through")
@@ -417,6 +432,9 @@ static int start_rollout(K kernel, K kernel_sliced, int device, cudaStream_t st,
                          const DevParams<R> &P0, size_t smem)
 {
     const int n_blocks = (a.B + kRolloutBlock - 1) / kRolloutBlock;
+#ifdef B200MP_SLICE_PROFILE
+    if (const char *ev = getenv("B200MP_SMEM_PAD")) smem += (size_t)atoi(ev);   // development: fewer resident CTAs per SM
+#endif
     int resident = 0, resident_plain = 0;
     int rc = kernel_info(kernel, smem, &resident_plain);
     if (!rc) rc = kernel_info(kernel_sliced, smem, &resident);

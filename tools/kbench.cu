@@ -69,6 +69,7 @@ int main(int argc, char **argv)
         const double it = (double)q[3];
         printf("   slice profile: %.0f items; per item: wait %.0f, prologue %.0f, steps %.0f, epilogue %.0f cycles; %.1f %% of the items found their predecessor unfinished\n",
                it, q[0] / it, q[1] / it, q[5] / it, q[2] / it, 100.0 * q[4] / it);
+        printf("   SM clock seen by the CTAs: %.3f GHz (cycles / globaltimer ns over each CTA's life)\n", (double)q[6] / (double)q[7]);
     }
 #endif
     std::vector<double> end((size_t)12 * B);
