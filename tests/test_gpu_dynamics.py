@@ -441,3 +441,19 @@ def test_param_set_range_and_endstate_pipeline_segments(engine):
         end_host.zero_()
         engine.rollout_endstate_to_host(hs, hd, ht, DT, N, 30, end_host, chunk_steps=chunk)
         assert torch.equal(end_host, dev.state_end.cpu()), chunk
+
+
+def test_host_pipeline_slab_ring_and_pinned_buffers(engine):
+    """``Engine.pinned_empty`` (NUMA-local when the host allows it, plain pinned memory otherwise) feeds the host-buffer
+    pipeline; any number of device slabs gives the bytes of one device launch."""
+    B, N = 4096, 120
+    s0, d, t = wl.config2_rollouts(B=B, n_steps=N)
+    engine.set_params(_params())
+    dev = engine.rollout(s0, d, t, DT, N, hold=wl.HOLD, store_stride=1)
+    hs, hd, ht = (torch.from_numpy(a).pin_memory() for a in (s0, d, t))
+    out = engine.pinned_empty(N, 10, B)
+    assert out.is_pinned() and out.shape == (N, 10, B) and hasattr(out, "numa_node")
+    for n_slabs, chunk in ((2, 30), (3, 20), (5, 10), (4, 120)):
+        out.zero_()
+        end = engine.rollout_to_host(hs, hd, ht, DT, N, wl.HOLD, out, chunk_steps=chunk, n_slabs=n_slabs)
+        assert torch.equal(out, dev.traj.cpu()) and torch.equal(end, dev.state_end), (n_slabs, chunk)
