@@ -296,14 +296,30 @@ inline double build_mu_table(double B, double C, double D, double *table)
 constexpr int kMuBitsF = 5;
 constexpr int kMuPerBinadeF = 1 << kMuBitsF;
 constexpr int kMuIntervalsF = kMuPerBinadeF * kMuBinades;   // 448
-constexpr int kMuTableFloats = kMuIntervalsF * 4;
+// Mask-indexed rows for the FP32 table (see B200MP_MU_MASKIDX): row = [low 4 exponent bits | 5 leading mantissa bits] of the
+// float x, byte offset = that field shifted into place -- one LOP3 and one shift instead of subtract / shift / compare /
+// select / scale; 512 rows = 8 KB.  K1f is issue-bound (every instruction costs a slot), so unlike K1 it gains from it.
+#ifndef B200MP_MU_MASKIDX_F32
+#define B200MP_MU_MASKIDX_F32 1
+#endif
+constexpr bool kMuMaskIdxF = B200MP_MU_MASKIDX_F32 != 0;
+constexpr int kMuRowsF = kMuMaskIdxF ? (16 << kMuBitsF) : kMuIntervalsF;
+constexpr int kMuTableFloats = kMuRowsF * 4;
+constexpr int kMuKeyShiftF = 23 - kMuBitsF;
+constexpr unsigned kMuKeyMaskF = (unsigned)((16 << kMuBitsF) - 1) << kMuKeyShiftF;
+inline constexpr int mu_row_of_f(int k)
+{
+    return kMuMaskIdxF ? (((((k >> kMuBitsF) + 15) & 15) << kMuBitsF) | (k & (kMuPerBinadeF - 1))) : k;
+}
 struct alignas(16) MuRowF {
     float c3, c2, c1, c0;
 };
 B200MP_HD float mu_row_eval(const MuRowF &r, float t) { return fmaf(fmaf(fmaf(r.c3, t, r.c2), t, r.c1), t, r.c0); }
+// k: row index, or (MASKIDX_F32) the key returned by MuTab<float>::locate (row << kMuKeyShiftF; a row is 16 bytes)
 B200MP_HD MuRowF mu_row_load(const float *table, int k)
 {
     MuRowF r;
+    if (kMuMaskIdxF) k = (int)((unsigned)k >> kMuKeyShiftF);
 #if defined(__CUDA_ARCH__)
     const float4 v = reinterpret_cast<const float4 *>(table)[k];
     r.c3 = v.x; r.c2 = v.y; r.c1 = v.z; r.c0 = v.w;
@@ -317,12 +333,13 @@ inline double build_mu_table_f32(double B, double C, double D, float *table)
     typedef long double L;
     const MuFunction G{B, C, D};
     double worst = 0.0;
+    for (int i = 0; i < kMuTableFloats; ++i) table[i] = 0.0f;
     for (int k = 0; k < kMuIntervalsF; ++k) {
         const int e = k / kMuPerBinadeF, m = k % kMuPerBinadeF;
         const L lo = ldexpl(1.0L + (L)m / kMuPerBinadeF, e), hi = ldexpl(1.0L + (L)(m + 1) / kMuPerBinadeF, e);
         L mono[16], mid;
         mu_fit_interval(G, lo, hi, 4, mono, &mid);
-        MuRowF *mr = reinterpret_cast<MuRowF *>(table) + k;
+        MuRowF *mr = reinterpret_cast<MuRowF *>(table) + mu_row_of_f(k);
         mr->c3 = (float)mono[3];
         mr->c2 = (float)mono[2];
         mr->c1 = (float)mono[1];
@@ -373,6 +390,10 @@ template <> struct MuTab<float> {
         const int b = Math<float>::bits(x);
         const int keep = (int)(0xFFFFFFFFu << (23 - kMuBitsF));
         *t = x - Math<float>::from_bits((b & keep) | (1 << (22 - kMuBitsF)));
+        if (kMuMaskIdxF) {
+            *inside = (unsigned)b < 0x3F800000u + ((unsigned)kMuBinades << 23);   // x < 2^14; NaN and negative fail
+            return (int)((unsigned)b & kMuKeyMaskF);
+        }
         const int kraw = (b - 0x3F800000) >> (23 - kMuBitsF);
         *inside = (unsigned)kraw < (unsigned)kIntervals;
         return *inside ? kraw : 0;
@@ -435,6 +456,9 @@ B200MP_HD R wheel_vx(R vxc, R vyc, R cd, R sd)
 #endif
 #ifndef B200MP_HEADING_FRAME
 #define B200MP_HEADING_FRAME 0
+#endif
+#ifndef B200MP_HEADING_FRAME_F32
+#define B200MP_HEADING_FRAME_F32 1   /* K1f is issue-bound: there the 12 instructions per step are time */
 #endif
 template <typename R>
 B200MP_HD void rcp4(const R v[4], R r[4])
@@ -596,7 +620,7 @@ B200MP_HD bool rk4_step_impl(const DevParams<R> &P, const R D[4], const WheelCtr
     // FRAME (the speculative fast path): x_dot, y_dot of every stage are formed in the frame of the STEP's heading --
     // k8 = U cos e - V sin e, k9 = U sin e + V cos e -- and the RK4 sum is rotated into the world frame once at the end
     // (x, y never feed back), which spares composing (s0, c0) with (sin e, cos e) in stages 2-4 and the products of stage 1.
-    constexpr bool FRAME = B200MP_HEADING_FRAME != 0 && SPEC && !AUX;
+    constexpr bool FRAME = (B200MP_HEADING_FRAME != 0 || (B200MP_HEADING_FRAME_F32 != 0 && sizeof(R) == 4)) && SPEC && !AUX;
     R s0, c0, sj, cj;
     bool ok = true;
     if (SPEC)

@@ -17,6 +17,10 @@ FP64 = {"DFMA", "DMUL", "DADD", "DSETP"}
 
 def main():
     obj = sys.argv[1]
+    global FUN
+    f32 = "--f32" in sys.argv          # the FP32 twin (K1f) in rollout_kernels_f32.o
+    if f32:
+        FUN = FUN.replace("kernelId", "kernelIf")
     txt = subprocess.run(["cuobjdump", "-sass", "-fun", FUN, obj], capture_output=True, text=True).stdout
     ins = []
     for ln in txt.splitlines():
@@ -35,6 +39,8 @@ def main():
     for lo, hi in loops:
         body = [i for i in ins if lo <= i[0] <= hi]
         fp = sum(1 for i in body if i[1].split(".")[0] in FP64)
+        if f32:
+            fp = sum(1 for i in body if i[1].split(".")[0] in ("FFMA", "FMUL", "FADD"))
         if fp >= 400 and (best is None or hi - lo < best[1] - best[0]):
             best = (lo, hi)
     lo, hi = best
