@@ -324,3 +324,31 @@ def test_calls_on_two_streams_do_not_share_scratch(engine):
     for k, ref in (("a", serial[0]), ("b", serial[1])):
         for f1, c in out[k]:
             assert torch.equal(f1, ref[0]) and torch.equal(c.view(torch.int64), ref[1].view(torch.int64)), k
+
+
+def test_broad_phase_spatial_sort_edge_cases(engine):
+    """The broad phase sorts the obstacle points into Morton order of a grid over their bounding box: degenerate extents
+    (all points identical, all on one line), fewer points than a chunk, shuffled order, and a list beyond the sorter's
+    limit (which keeps the caller's order) all give the oracle's flags and min-clearance."""
+    w = wl.config3_lattice(P=192, M=3000)
+    px, py, pyaw = w["px"], w["py"], w["pyaw"]
+    rng = np.random.default_rng(23)
+    cases = {
+        "identical": np.repeat(w["obstacles"][:1], 2000, axis=0),
+        "vertical line": np.stack([np.full(2500, w["obstacles"][7, 0]), np.linspace(-20.0, 120.0, 2500)], 1),
+        "horizontal line": np.stack([np.linspace(-20.0, 120.0, 2500), np.full(2500, w["obstacles"][9, 1])], 1),
+        "shuffled": w["obstacles"][rng.permutation(3000)],
+        "two far clusters": np.concatenate([w["obstacles"][:1500], w["obstacles"][1500:] + 1.0e6]),
+    }
+    for name, obs in cases.items():
+        ref, clr_ref, _ = c_oracle.collision_check(px, py, pyaw, obs, OFF, RAD, want_clearance=True)
+        got = _np(engine.collision_check_batch(px, py, pyaw, obs, OFF, RAD)).astype(bool)
+        assert np.array_equal(got, ref), name
+        f2, clr = engine.collision_check_batch(px, py, pyaw, obs, OFF, RAD, want_clearance=True)
+        assert np.array_equal(_np(f2).astype(bool), ref) and np.array_equal(_np(clr), clr_ref), name
+    # beyond kSortMaxPoints (131,072): the broad phase runs on the caller's order
+    big = wl.config3_lattice(P=48, M=140000)
+    ref, clr_ref, _ = c_oracle.collision_check(big["px"], big["py"], big["pyaw"], big["obstacles"], OFF, RAD, want_clearance=True)
+    got = _np(engine.collision_check_batch(big["px"], big["py"], big["pyaw"], big["obstacles"], OFF, RAD)).astype(bool)
+    f2, clr = engine.collision_check_batch(big["px"], big["py"], big["pyaw"], big["obstacles"], OFF, RAD, want_clearance=True)
+    assert np.array_equal(got, ref) and np.array_equal(_np(f2).astype(bool), ref) and np.array_equal(_np(clr), clr_ref)
