@@ -1100,7 +1100,11 @@ static int broad_phase_prepare(cudaStream_t st, int M, const double *obs, void *
     double2 *sorted = (double2 *)((char *)area + ((pts_bytes + box_bytes + sizeof(ObsPrep) + 15) & ~(size_t)15));
     B200MP_CUDA(cudaMemsetAsync(*prep, 0, sizeof(ObsPrep), st));
     *obs_eff = (const double2 *)obs;
-    if (M <= kSortMaxPoints && getenv("B200MP_NO_OBS_SORT") == nullptr) {
+    bool sort = M <= kSortMaxPoints;
+#ifdef B200MP_DEV_TUNABLES
+    if (getenv("B200MP_NO_OBS_SORT")) sort = false;   // development A/B (tools/collision_quick.py, tools/cbench.cu)
+#endif
+    if (sort) {
         obstacle_sort_kernel<<<1, 1024, 0, st>>>(M, (const double2 *)obs, sorted);
         B200MP_CUDA(cudaGetLastError());
         *obs_eff = sorted;
@@ -1175,7 +1179,9 @@ static int launch_collision_nc(int device, cudaStream_t st, int P, int n_pts, co
         const int groups = (n_chunks + 31) / 32;
         int gy = groups;
         if ((long long)gy * grid > (1LL << 18)) gy = (int)((1LL << 18) / grid);
-        if (const char *ev = getenv("B200MP_CULL_GY")) gy = atoi(ev);   // development tunable (tools/cbench.cu)
+#ifdef B200MP_DEV_TUNABLES
+        if (const char *ev = getenv("B200MP_CULL_GY")) gy = atoi(ev);   // development A/B (tools/cbench.cu)
+#endif
         gy = gy < 1 ? 1 : (gy > groups ? groups : gy);
         collision_cull_kernel<NC><<<dim3(grid, gy), kColBlock, 0, st>>>((int)items, n_pts, cs, px, py, pcos, psin, pyaw, yaw_stride,
                                                                      M, obs_eff, pts, boxes, prep, free_out, yf);

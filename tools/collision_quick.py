@@ -1,4 +1,4 @@
-"""Kernel times of the config-3 collision paths (flags / min-clearance), broad-phase statistics; B200MP_NO_OBS_SORT=1 keeps the caller's obstacle order."""
+"""Kernel times of the config-3 collision paths (flags / min-clearance), broad-phase statistics; B200MP_NO_OBS_SORT=1 keeps the caller's obstacle order (needs a library built with -DB200MP_DEV_TUNABLES=1)."""
 import ctypes as C, os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
