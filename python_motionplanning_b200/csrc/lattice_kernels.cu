@@ -21,15 +21,16 @@
 
 namespace b200mp {
 
-constexpr int kLatBlock = 64;
+constexpr int kLatBlock = 32;   // 4,096 paths = 128 CTAs (one thread per spiral: the work is a serial chain of sincos)
 
 __global__ void __launch_bounds__(kLatBlock)
 lattice_kernel(int P, int n_samples, const double *__restrict__ k1, const double *__restrict__ k2,
                const double *__restrict__ sf, const double *__restrict__ ego_x, const double *__restrict__ ego_y,
                const double *__restrict__ ego_yaw, int ego_broadcast, double *__restrict__ px, double *__restrict__ py,
-               double *__restrict__ pyaw, double *__restrict__ pcos, double *__restrict__ psin, double *__restrict__ end_xy)
+               double *__restrict__ pyaw, double *__restrict__ pcos, double *__restrict__ psin, double *__restrict__ end_xy,
+               int single_pass)
 {
-    extern __shared__ double stage[];   // [kLatBlock][n_pts + 1]: one row per thread, padded against bank conflicts
+    extern __shared__ double stage[];   // [outputs][kLatBlock][n_pts + 1]: one row per thread and output, padded against bank conflicts
     const int n_pts = n_samples - 1;
     const int row = n_pts + 1;
     const int p = blockIdx.x * kLatBlock + threadIdx.x;
@@ -52,7 +53,57 @@ lattice_kernel(int P, int n_samples, const double *__restrict__ k1, const double
         }
     }
     const double b2 = b / 2, c3 = c / 3, d4 = d / 4;
-    // four passes (x, y, heading, then cos / sin of the heading), each staged and written out coalesced
+    if (single_pass) {
+        // ONE sweep over the samples fills a staging row per requested output (x, y, heading, cos, sin); the multi-pass form
+        // below repeats the whole spiral -- 49 sincos -- for every output and is kept for sample counts whose staging rows
+        // do not fit in shared memory
+        double *outs[5] = {px, py, pyaw, pcos, psin};
+        int slot[5], n_out = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) slot[k] = outs[k] ? n_out++ : -1;
+        const size_t plane = (size_t)kLatBlock * row;
+        if (live) {
+            double s_prev = 0.0, t_prev = 0.0, c_prev = 1.0, n_prev = 0.0, X = 0.0, Y = 0.0;
+            double *mine = stage + threadIdx.x * row;
+            for (int j = 1; j < n_samples; ++j) {
+                const double s = (j == n_samples - 1) ? S : (double)j * step;
+                const double s2 = s * s;
+                const double t = ((0.0 * s + b2 * s2) + c3 * (s2 * s)) + d4 * (s2 * s2);   // thetaf, :109-117
+                double cn, sn;
+                sincos(t, &sn, &cn);
+                const double ds = s - s_prev;
+                X = X + ds * (cn + c_prev) / 2.0;                 // cumulative trapezoid, :172-173
+                Y = Y + ds * (sn + n_prev) / 2.0;
+                const double yaw = t_prev + eyaw;                 // heading of the PREVIOUS sample (:466, length quirk)
+                mine[slot[0] * plane + (j - 1)] = ex + X * ce - Y * se;   // local_planner.py:462-465 (px, py are mandatory)
+                mine[slot[1] * plane + (j - 1)] = ey + X * se + Y * ce;
+                if (slot[2] >= 0) mine[slot[2] * plane + (j - 1)] = yaw;
+                if (slot[3] >= 0) mine[slot[3] * plane + (j - 1)] = cos(yaw);
+                if (slot[4] >= 0) mine[slot[4] * plane + (j - 1)] = sin(yaw);
+                s_prev = s;
+                t_prev = t;
+                c_prev = cn;
+                n_prev = sn;
+            }
+            if (end_xy) {                                         // path end points for select_best (x[-1], y[-1])
+                end_xy[p] = ex + X * ce - Y * se;
+                end_xy[(size_t)P + p] = ey + X * se + Y * ce;
+            }
+        }
+        __syncthreads();
+        const int p0 = blockIdx.x * kLatBlock;
+        const int n_live = min(kLatBlock, P - p0);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            if (slot[k] < 0) continue;
+            for (int i = threadIdx.x; i < n_live * n_pts; i += kLatBlock) {
+                const int r = i / n_pts, jj = i - r * n_pts;
+                outs[k][(size_t)p0 * n_pts + i] = stage[slot[k] * plane + r * row + jj];
+            }
+        }
+        return;
+    }
+    // one pass per output (x, y, heading, then cos / sin of the heading), each staged and written out coalesced
     for (int pass = 0; pass < 5; ++pass) {
         double *out = pass == 0 ? px : pass == 1 ? py : pass == 2 ? pyaw : pass == 3 ? pcos : psin;
         if (!out) continue;                                       // uniform across the grid
@@ -117,11 +168,15 @@ int launch_lattice_f64(int device, cudaStream_t st, int P, int n_samples, const 
         set_error("sample_lattice: ego_x, ego_y and ego_yaw go together");
         return B200MP_E_ARG;
     }
-    const size_t smem = sizeof(double) * kLatBlock * (size_t)n_samples;
+    const size_t plane = sizeof(double) * kLatBlock * (size_t)n_samples;
+    const int n_out = 2 + (pyaw != nullptr) + (pcos != nullptr) + (psin != nullptr);
+    const int single_pass = plane * n_out <= 160 * 1024;          // all staging rows at once (the planner's 50 samples: 64 KB)
+    const size_t smem = single_pass ? plane * n_out : plane;
     if (smem > 48 * 1024)
         B200MP_CUDA(cudaFuncSetAttribute(lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lattice_kernel<<<(P + kLatBlock - 1) / kLatBlock, kLatBlock, smem, st>>>(P, n_samples, k1, k2, sf, ego_x, ego_y, ego_yaw,
-                                                                           ego_broadcast, px, py, pyaw, pcos, psin, end_xy);
+                                                                           ego_broadcast, px, py, pyaw, pcos, psin, end_xy,
+                                                                           single_pass);
     B200MP_CUDA(cudaGetLastError());
     return 0;
 }
