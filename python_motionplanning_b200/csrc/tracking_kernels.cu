@@ -12,13 +12,18 @@
 // and then walks forward summing segment lengths until the look-ahead distance is reached.  Here:
 //   * a prepare kernel evaluates, once per waypoint set, everything that does not depend on the vehicle:
 //     segment lengths (same closed form as the host's norm, so the walk adds the same doubles), their
-//     running sum (a search key only), segment headings, and the largest radius of the 8-waypoint "fine"
-//     and 256-waypoint "coarse" chunks about their first waypoints;
+//     running sum (a search key only), segment headings, and one record per chunk of 8 ("fine"), 32 ("mid") and
+//     256 ("coarse") consecutive waypoints: the chord from the chunk's first to its last waypoint and the largest
+//     distance `eps` of any of its waypoints from that chord;
 //   * the nearest-waypoint search is exact but sub-linear: the distance to the previous update's nearest
-//     waypoint (or to the coarse chunk heads) is an upper bound UB on the minimum; a chunk whose first
-//     waypoint is farther than UB + (chunk radius) cannot contain the minimum (triangle inequality, with
-//     1e-12 relative slack for rounding); coarse chunks are culled first, the fine chunks of a surviving
-//     coarse chunk form one 32-bit mask, and the surviving waypoints are compared on the squared distance
+//     waypoint (or to the coarse chunks' first waypoints) is an upper bound UB on the minimum; every waypoint of a
+//     chunk is at least dist(vehicle, chord) - eps away, so a chunk with dist(vehicle, chord) > UB + eps cannot
+//     contain the minimum (rounding slack folded into eps and the comparison).  A vehicle that runs beside its
+//     path at a lateral offset d sees the distance grow only quadratically along the path (sqrt(d^2 + s^2)), so the
+//     former test "first waypoint of the chunk farther than UB + chunk radius" kept 2 sqrt(2 d r) / ds waypoints alive
+//     (a dozen fine chunks at d = 0.3 m); the chord test keeps the one or two chunks around the foot point whatever d
+//     is.  Coarse chunks are culled first, then the 8 mid chunks of a survivor, then the 4 fine chunks of a surviving
+//     mid chunk (one 32-bit mask per coarse chunk), and the surviving waypoints are compared on the squared distance
 //     in the host's rounding sequence (sqrt_rn is monotone).  The reference's "first strict minimum of the
 //     rounded norms" is reproduced by a branch-free scan plus an exact replay when any two squares came
 //     within 1e-15 of each other (ties, duplicate waypoints);
@@ -37,7 +42,45 @@ namespace b200mp {
 
 constexpr int kTrackBlock = 64;
 constexpr int kFine = 8;             // waypoints per fine chunk
-constexpr int kCoarse = 32 * kFine;  // one coarse chunk = 32 fine chunks = one 32-bit candidate mask
+constexpr int kMid = 4 * kFine;      // one mid chunk = 4 fine chunks
+constexpr int kCoarse = 8 * kMid;    // one coarse chunk = 8 mid chunks = 32 fine chunks = one 32-bit candidate mask
+
+// One chunk of consecutive waypoints [i0, i1] for the nearest-waypoint search: the chord a + t u (t in [0, 1]) from its
+// first to its last waypoint, 1/|u|^2 (0 for a degenerate or non-finite chord: the "chord" is then the point a), and
+// eps >= the distance of every waypoint of the chunk from the chord (+inf when the chunk holds a non-finite coordinate:
+// such a chunk is never culled).  48 bytes = three 128-bit loads.
+struct alignas(16) ChunkRec {
+    double ax, ay, ux, uy, inv_l2, eps;
+};
+
+// squared distance from (x, y) to the chord of a record, as the device evaluates it (prepare and search share it)
+__device__ __forceinline__ double chord_dist2(double ax, double ay, double ux, double uy, double inv_l2, double x, double y)
+{
+    const double vx = x - ax, vy = y - ay;
+    double t = (vx * ux + vy * uy) * inv_l2;
+    t = fmin(fmax(t, 0.0), 1.0);         // NaN -> 0
+    const double dx = vx - t * ux, dy = vy - t * uy;
+    return dx * dx + dy * dy;
+}
+
+__device__ __forceinline__ void track_prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// false only when no waypoint of the chunk can be within ub of (x, y).  With d the true distance from the vehicle to the
+// chord and s the evaluated one: |s - d| <= ~1e-15 (d + |u|) (the clamped foot point stays ON the chord, so a rounding of t
+// can only lengthen the distance; the remaining operations are relatively accurate on operands bounded by d + |u|).  The
+// relative part is covered by the factor below, the |u| part by the 1e-11 max|w_j - a| >= 1e-11 |u| added to eps by the
+// prepare kernel.  NaN anywhere compares false: the chunk is searched.
+__device__ __forceinline__ bool chunk_may_hold(const ChunkRec *__restrict__ rec, double x, double y, double ub)
+{
+    const double2 *__restrict__ p = reinterpret_cast<const double2 *>(rec);
+    const double2 a = p[0], u = p[1], e = p[2];
+    const double d2 = chord_dist2(a.x, a.y, u.x, u.y, e.x, x, y);
+    const double reach = ub + e.y;
+    return !(d2 > reach * reach * (1.0 + 1.0e-11));
+}
 constexpr double kPi = 3.141592653589793;
 
 struct TrackDev {
@@ -46,9 +89,9 @@ struct TrackDev {
     const double *state0, *ctrl0;
     const double2 *wp;
     const int *wp_count;
-    const double *seg, *head, *cum, *rmax, *clean;
-    const double2 *heads;
-    int heads_stride;
+    const double *seg, *head, *cum, *clean;
+    const ChunkRec *recs;   // [n_sets][recs_stride]: fine, mid, coarse chunk records of each waypoint set
+    int recs_stride;
     double *traj, *log, *state_end, *ctrl_end;
     int *target_idx;
     const double *mu_table;   // friction table of parameter set 0 (vehicle_rhs.cuh), used by the no-log kernel
@@ -67,7 +110,7 @@ __device__ __forceinline__ double host_sq(double v0, double v1, int mode)
 // numpy's float remainder for a positive divisor (np.float64.__mod__)
 __device__ __forceinline__ double py_mod(double a, double b)
 {
-    double m = fmod(a, b);
+    double m = fabs(a) < b ? a : fmod(a, b);   // |a| < b: fmod returns a itself
     if (m != 0.0) {
         if (m < 0.0) m = __dadd_rn(m, b);
     } else {
@@ -79,18 +122,48 @@ __device__ __forceinline__ double py_mod(double a, double b)
 __global__ void __launch_bounds__(256)
 track_prepare_kernel(int w_max, const double2 *__restrict__ wp, const int *__restrict__ wp_count, int norm_mode,
                      double *__restrict__ seg, double *__restrict__ head, double *__restrict__ cum,
-                     double *__restrict__ rmax, double *__restrict__ clean, double2 *__restrict__ heads, int heads_stride)
+                     double *__restrict__ clean, ChunkRec *__restrict__ recs, int recs_stride)
 {
     const int set = blockIdx.x;
     const int W = wp_count[set];
     const double2 *w = wp + (size_t)set * w_max;
-    // chunk heads gathered into one compact array per set (fine heads first, then coarse): the search reads 32
-    // consecutive heads from 4 cache lines instead of 32 lines 128 bytes apart
-    double2 *fh = heads + (size_t)set * heads_stride, *chd = fh + (w_max + kFine - 1) / kFine;
-    for (int i = threadIdx.x; i * kFine < W; i += blockDim.x) fh[i] = w[i * kFine];
-    for (int i = threadIdx.x; i * kCoarse < W; i += blockDim.x) chd[i] = w[i * kCoarse];
+    // chunk records of the three levels, one compact array per set (fine, then mid, then coarse)
+    const int n_fine = (w_max + kFine - 1) / kFine, n_mid = (w_max + kMid - 1) / kMid, n_coarse = (w_max + kCoarse - 1) / kCoarse;
+    ChunkRec *rset = recs + (size_t)set * recs_stride;
+    for (int c = threadIdx.x; c < n_fine + n_mid + n_coarse; c += blockDim.x) {
+        const int size = c < n_fine ? kFine : (c < n_fine + n_mid ? kMid : kCoarse);
+        const int idx = c < n_fine ? c : (c < n_fine + n_mid ? c - n_fine : c - n_fine - n_mid);
+        const int i0 = idx * size;
+        ChunkRec r;
+        r.ax = r.ay = r.ux = r.uy = r.inv_l2 = 0.0;
+        r.eps = INFINITY;
+        if (i0 < W) {
+            const int i1 = min(W, i0 + size) - 1;
+            const double2 a = w[i0], b = w[i1];
+            const double ux = b.x - a.x, uy = b.y - a.y;
+            const double l2 = ux * ux + uy * uy;
+            const bool chord = l2 > 0.0 && l2 < INFINITY;
+            r.ax = a.x;
+            r.ay = a.y;
+            r.ux = chord ? ux : 0.0;
+            r.uy = chord ? uy : 0.0;
+            r.inv_l2 = chord ? 1.0 / l2 : 0.0;
+            double dev = 0.0, far = 0.0;
+            bool finite = true;
+            for (int j = i0; j <= i1; ++j) {
+                const double2 q = w[j];
+                finite = finite && fabs(q.x) < INFINITY && fabs(q.y) < INFINITY;
+                dev = fmax(dev, sqrt(chord_dist2(r.ax, r.ay, r.ux, r.uy, r.inv_l2, q.x, q.y)));
+                const double fx = q.x - a.x, fy = q.y - a.y;
+                far = fmax(far, sqrt(fx * fx + fy * fy));
+            }
+            // rounding of dev itself and of the search's evaluation (see chunk_may_hold): 1e-11 of the chunk's extent
+            const double eps = dev * (1.0 + 1.0e-9) + 1.0e-11 * far + 1.0e-300;
+            r.eps = (finite && eps < INFINITY) ? eps : INFINITY;
+        }
+        rset[c] = r;
+    }
     double *sg = seg + (size_t)set * w_max, *hd = head + (size_t)set * w_max, *cm = cum + (size_t)set * w_max;
-    double r = 0.0, rc = 0.0;
     int ok = 1;
     for (int i = threadIdx.x; i < W; i += blockDim.x) {
         const double2 p = w[i];
@@ -104,45 +177,43 @@ track_prepare_kernel(int w_max, const double2 *__restrict__ wp, const int *__res
         const double2 a = (i < W - 1) ? w[i + 1] : w[0];     // :105-116, the last waypoint wraps to the first
         const double2 b = (i < W - 1) ? p : w[W - 1];
         hd[i] = atan2(a.y - b.y, a.x - b.x);
-        const double2 cf = w[i - (i % kFine)], cc = w[i - (i % kCoarse)];
-        const double fx = p.x - cf.x, fy = p.y - cf.y, gx = p.x - cc.x, gy = p.y - cc.y;
-        r = fmax(r, sqrt(fx * fx + fy * fy));                // NaN waypoints drop out (they never win a minimum)
-        rc = fmax(rc, sqrt(gx * gx + gy * gy));
     }
-    __shared__ double sr[256], src[256];
     __shared__ int sok;
+    __shared__ double part[256];
     if (threadIdx.x == 0) sok = 1;
-    sr[threadIdx.x] = r;
-    src[threadIdx.x] = rc;
-    __syncthreads();
+    __syncthreads();   // also orders the sg[] stores above before the reads below (same block)
     if (!ok) atomicAnd(&sok, 0);
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            sr[threadIdx.x] = fmax(sr[threadIdx.x], sr[threadIdx.x + s]);
-            src[threadIdx.x] = fmax(src[threadIdx.x], src[threadIdx.x + s]);
-        }
-        __syncthreads();
-    }
+    // running arc length: only a SEARCH KEY for the look-ahead walk (the walk's own sums are re-derived from it with an
+    // error bound that holds for any order of summation, see lookahead_index); a set with a NaN/Inf segment walks
+    // sequentially.  Blocked scan: each thread sums a contiguous run, thread 0 scans the 256 partial sums.
+    const int run = (W + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int j0 = min(W, (int)threadIdx.x * run), j1 = min(W, j0 + run);
+    double acc = 0.0;
+    for (int i = j0; i < j1; ++i) acc += sg[i];
+    part[threadIdx.x] = acc;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        rmax[2 * set] = sr[0] * (1.0 + 1.0e-12) + 1.0e-300;        // fine chunks about their first waypoint
-        rmax[2 * set + 1] = src[0] * (1.0 + 1.0e-12) + 1.0e-300;   // coarse chunks about theirs
-        // running arc length: only a SEARCH KEY for the look-ahead walk (the walk's own sums are re-derived
-        // from it with an error bound, see lookahead_index); a set with a NaN/Inf segment walks sequentially
-        double acc = 0.0;
-        for (int i = 0; i < W; ++i) {
-            acc += sg[i];
-            cm[i] = acc;
+        double off = 0.0;
+        for (int t = 0; t < (int)blockDim.x; ++t) {
+            const double v = part[t];
+            part[t] = off;
+            off += v;
         }
         clean[set] = sok ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    acc = part[threadIdx.x];
+    for (int i = j0; i < j1; ++i) {
+        acc += sg[i];
+        cm[i] = acc;
     }
 }
 
 struct SetView {
-    const double2 *__restrict__ fh, *__restrict__ ch;   // compact fine / coarse chunk heads
+    const ChunkRec *__restrict__ fine, *__restrict__ mid, *__restrict__ coarse;   // chunk records of the three levels
     const double2 *__restrict__ w;
     const double *__restrict__ sg, *__restrict__ cm;
     int W;
-    double rfine, rcoarse;
     bool clean;
 };
 
@@ -191,7 +262,7 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
     const double2 *__restrict__ w = sv.w;
     const int W = sv.W;
     const int n_coarse = (W + kCoarse - 1) / kCoarse;
-    // upper bound on the minimum distance: any waypoint will do; the coarse chunk heads when there is no hint
+    // upper bound on the minimum distance: any waypoint will do; the coarse chunks' first waypoints when there is no hint
     double qub = INFINITY;
     if (hint >= 0 && hint < W) {
         const double2 p = w[hint];
@@ -199,63 +270,97 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
         qub = dx * dx + dy * dy;
     }
     if (!(qub < INFINITY)) {
+        // first update of a vehicle: the nearest of the coarse chunks' first waypoints, then of that chunk's mid and fine
+        // chunks' first waypoints -- any waypoint is a valid bound, a near one keeps the candidate set small
+        int cbest = 0;
         for (int c = 0; c < n_coarse; ++c) {
-            const double2 p = sv.ch[c];
-            qub = fmin(qub, (p.x - x) * (p.x - x) + (p.y - y) * (p.y - y));
+            const double px = sv.coarse[c].ax, py = sv.coarse[c].ay;
+            const double q = (px - x) * (px - x) + (py - y) * (py - y);
+            if (q < qub) {
+                qub = q;
+                cbest = c;
+            }
+        }
+        const int nm0 = min(8, (W - cbest * kCoarse + kMid - 1) / kMid);
+        int mbest = 0;
+        for (int m = 0; m < nm0; ++m) {
+            const double px = sv.mid[cbest * 8 + m].ax, py = sv.mid[cbest * 8 + m].ay;
+            const double q = (px - x) * (px - x) + (py - y) * (py - y);
+            if (q < qub) {
+                qub = q;
+                mbest = m;
+            }
+        }
+        const int nf0 = min(4, (W - cbest * kCoarse - mbest * kMid + kFine - 1) / kFine);
+        for (int f = 0; f < nf0; ++f) {
+            const double px = sv.fine[cbest * 32 + mbest * 4 + f].ax, py = sv.fine[cbest * 32 + mbest * 4 + f].ay;
+            qub = fmin(qub, (px - x) * (px - x) + (py - y) * (py - y));
         }
     }
-    const double ub = sqrt(qub) * (1.0 + 1.0e-12);
-    const double reach_c = (ub + sv.rcoarse) * (ub + sv.rcoarse) * (1.0 + 1.0e-12);
-    const double reach = (ub + sv.rfine) * (ub + sv.rfine) * (1.0 + 1.0e-12);
+    const double ub = sqrt(qub) * (1.0 + 1.0e-12);   // +inf / NaN: nothing is culled
 
     // The reference updates on `dist < min_dist` with dist = sqrt_rn(q).  sqrt_rn is monotone, so a square that is
     // larger than the running minimum by more than a few ulp never updates and one that is smaller by more than a
     // few ulp always does (the rounded roots differ); the scan below is branch-free on that basis and only notes
     // whether any square ever fell inside the +-1e-15 band around the running minimum, in which case (rare: an
-    // exact or near tie) the chunks are re-scanned comparing rounded roots one by one.  A chunk whose first
-    // waypoint is farther than ub + (chunk radius) cannot hold the minimum or a tie with it (NaN compares false:
-    // such a chunk is searched).
+    // exact or near tie) the chunks are re-scanned comparing rounded roots one by one.  A chunk whose chord is farther
+    // than ub + eps cannot hold the minimum or a tie with it (chunk_may_hold).
     double qbest = INFINITY;
     int ibest = 0;
     bool near_tie = false;
-    for (int g = 0; g < n_coarse; ++g) {
-        {
-            const double2 p = sv.ch[g];
-            const double dx = p.x - x, dy = p.y - y;
-            if (dx * dx + dy * dy > reach_c) continue;
-        }
-        const int base = g * kCoarse;
-        const int gn = min(32, (W - base + kFine - 1) / kFine);
-        unsigned mask = 0;
-#pragma unroll 8
-        for (int c = 0; c < gn; ++c) {
-            const double2 p = sv.fh[g * 32 + c];
-            const double dx = p.x - x, dy = p.y - y;
-            mask |= (dx * dx + dy * dy > reach ? 0u : 1u) << c;
-        }
-        while (mask) {
-            const int i0 = base + (__ffs(mask) - 1) * kFine;
-            mask &= mask - 1;
+    // The tests of one level are written without branches (an index past the end is clamped onto the last valid record
+    // and its bit masked off), so that the loads of a whole batch are in flight together instead of one round trip each.
+    for (int g0 = 0; g0 < n_coarse; g0 += 8) {
+        unsigned cmask = 0;
 #pragma unroll
-            for (int k = 0; k < kFine; ++k) {
-                const int i = min(i0 + k, W - 1);               // the last chunk may be short: re-reading W-1 is harmless
-                const double2 v = w[i];
-                const double q = host_sq(__dsub_rn(v.x, x), __dsub_rn(v.y, y), mode);
-                const bool better = q < qbest * (1.0 - 1.0e-15);
-                near_tie |= !better && q <= qbest * (1.0 + 1.0e-15) && q < INFINITY && i0 + k < W;
-                qbest = better ? q : qbest;
-                ibest = better ? i : ibest;
+        for (int k = 0; k < 8; ++k) {
+            const bool hold = chunk_may_hold(sv.coarse + min(g0 + k, n_coarse - 1), x, y, ub);
+            cmask |= (hold && g0 + k < n_coarse ? 1u : 0u) << k;
+        }
+        while (cmask) {
+            const int g = g0 + __ffs(cmask) - 1;
+            cmask &= cmask - 1;
+            const int base = g * kCoarse;
+            const int nm = min(8, (W - base + kMid - 1) / kMid);
+            unsigned mmask = 0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const bool hold = chunk_may_hold(sv.mid + g * 8 + min(m, nm - 1), x, y, ub);
+                mmask |= (hold && m < nm ? 1u : 0u) << m;
+            }
+            unsigned mask = 0;
+            while (mmask) {
+                const int m = __ffs(mmask) - 1;
+                mmask &= mmask - 1;
+                const int nf = min(4, (W - base - m * kMid + kFine - 1) / kFine);
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const bool hold = chunk_may_hold(sv.fine + g * 32 + m * 4 + min(f, nf - 1), x, y, ub);
+                    mask |= (hold && f < nf ? 1u : 0u) << (m * 4 + f);
+                }
+            }
+            while (mask) {
+                const int i0 = base + (__ffs(mask) - 1) * kFine;
+                mask &= mask - 1;
+#pragma unroll
+                for (int k = 0; k < kFine; ++k) {
+                    const int i = min(i0 + k, W - 1);               // the last chunk may be short: re-reading W-1 is harmless
+                    const double2 v = w[i];
+                    const double q = host_sq(__dsub_rn(v.x, x), __dsub_rn(v.y, y), mode);
+                    const bool better = q < qbest * (1.0 - 1.0e-15);
+                    near_tie |= !better && q <= qbest * (1.0 + 1.0e-15) && q < INFINITY && i0 + k < W;
+                    qbest = better ? q : qbest;
+                    ibest = better ? i : ibest;
+                }
             }
         }
     }
-    if (near_tie) {   // exact replay of the reference's comparison sequence over the same chunks
+    if (near_tie) {   // exact replay of the reference's comparison sequence over (a superset of) the same chunks
         qbest = INFINITY;
         ibest = 0;
         double dbest = INFINITY;
         for (int c = 0; c * kFine < W; ++c) {
-            const double2 pc = w[(c * kFine / kCoarse) * kCoarse], p = w[c * kFine];
-            if ((pc.x - x) * (pc.x - x) + (pc.y - y) * (pc.y - y) > reach_c) continue;
-            if ((p.x - x) * (p.x - x) + (p.y - y) * (p.y - y) > reach) continue;
+            if (!chunk_may_hold(sv.fine + c, x, y, ub)) continue;
             const int i1 = min(W, (c + 1) * kFine);
             for (int i = c * kFine; i < i1; ++i) {
                 const double2 v = w[i];
@@ -315,8 +420,11 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
     MuTableView T;
     T.c = s_mu;
     T.B2 = a.mu_B2;
-    if (TAB) {
-        for (int i = threadIdx.x; i < kMuTableDoubles; i += kTrackBlock) s_mu[i] = a.mu_table[i];
+    if (TAB) {   // 16 bytes per load, as the rollout kernel stages it
+        const double2 *src = reinterpret_cast<const double2 *>(a.mu_table);
+        double2 *dst = reinterpret_cast<double2 *>(s_mu);
+#pragma unroll 8
+        for (int i = threadIdx.x; i < kMuTableDoubles / 2; i += kTrackBlock) dst[i] = src[i];
         __syncthreads();
     }
     const size_t V = (size_t)a.V;
@@ -348,13 +456,12 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
             const int W = a.wp_count[set];
             SetView sv;
             sv.w = w;
-            sv.fh = a.heads + (size_t)set * a.heads_stride;
-            sv.ch = sv.fh + (a.w_max + kFine - 1) / kFine;
+            sv.fine = a.recs + (size_t)set * a.recs_stride;
+            sv.mid = sv.fine + (a.w_max + kFine - 1) / kFine;
+            sv.coarse = sv.mid + (a.w_max + kMid - 1) / kMid;
             sv.sg = a.seg + (size_t)set * a.w_max;
             sv.cm = a.cum + (size_t)set * a.w_max;
             sv.W = W;
-            sv.rfine = a.rmax[2 * set];
-            sv.rcoarse = a.rmax[2 * set + 1];
             sv.clean = a.clean[set] != 0.0;
             int nearest = -1, la_prev = -1;
 
@@ -398,6 +505,16 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
                     if (W > 0) {
                         ce = lookahead_index(sv, px, py, a.lookahead, a.norm_mode, nearest, la_prev, &nearest);
                         la_prev = ce;
+                        {   // the next update reads a few waypoints further along both indices: start the following cache
+                            // lines of every table it walks towards L1 now, ctrl_every steps ahead of their use
+                            const int in = min(nearest + 8, W - 1), ic = min(ce + 8, W - 1);
+                            track_prefetch_l1(w + in);
+                            track_prefetch_l1(sv.cm + min(nearest + 16, W - 1));
+                            track_prefetch_l1(sv.fine + min(nearest / kFine + 2, (W - 1) / kFine));
+                            track_prefetch_l1(w + ic);
+                            track_prefetch_l1(sv.cm + min(ce + 16, W - 1));
+                            track_prefetch_l1(hd + min(ce + 16, W - 1));
+                        }
                         double sn, cs;
                         sincos(yaw, &sn, &cs);
                         const double2 t = w[ce];
@@ -529,9 +646,10 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
         return 0;
     }
     const size_t per = (size_t)g.n_sets * (size_t)(g.w_max > 0 ? g.w_max : 1);
-    const int heads_stride = (g.w_max + kFine - 1) / kFine + (g.w_max + kCoarse - 1) / kCoarse + 1;
+    const int recs_stride = (g.w_max + kFine - 1) / kFine + (g.w_max + kMid - 1) / kMid + (g.w_max + kCoarse - 1) / kCoarse + 1;
     void *scratch = nullptr;
-    const size_t tables_bytes = (sizeof(double) * (3 * per + 4 * (size_t)g.n_sets + 2) + sizeof(double2) * (size_t)g.n_sets * (size_t)heads_stride + 15) & ~(size_t)15;
+    const size_t recs_off = (sizeof(double) * (3 * per + (size_t)g.n_sets) + 15) & ~(size_t)15;   // records are 16-byte aligned
+    const size_t tables_bytes = (recs_off + sizeof(ChunkRec) * (size_t)g.n_sets * (size_t)recs_stride + 15) & ~(size_t)15;
     int rc = ensure_scratch(device, st, tables_bytes + sizeof(int2) * (size_t)g.V, &scratch);
     if (rc) return rc;
     void *hint_area = (char *)scratch + tables_bytes;   // search hints handed between the time slices of a launch
@@ -564,10 +682,9 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     a.seg = (double *)scratch;
     a.head = (double *)scratch + per;
     a.cum = (double *)scratch + 2 * per;
-    a.rmax = (double *)scratch + 3 * per;
-    a.clean = (double *)scratch + 3 * per + 2 * (size_t)g.n_sets;
-    a.heads = (const double2 *)((double *)scratch + ((3 * per + 4 * (size_t)g.n_sets + 1) & ~(size_t)1));   // 16-byte aligned
-    a.heads_stride = heads_stride;
+    a.clean = (double *)scratch + 3 * per;
+    a.recs = (const ChunkRec *)((char *)scratch + recs_off);
+    a.recs_stride = recs_stride;
     a.traj = g.traj;
     a.log = g.log;
     a.state_end = g.state_end;
@@ -575,8 +692,7 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     a.target_idx = g.target_idx;
     a.hint = nullptr;
     track_prepare_kernel<<<g.n_sets, 256, 0, st>>>(g.w_max, a.wp, g.wp_count, g.norm_mode, (double *)a.seg, (double *)a.head,
-                                                   (double *)a.cum, (double *)a.rmax, (double *)a.clean,
-                                                   (double2 *)a.heads, heads_stride);
+                                                   (double *)a.cum, (double *)a.clean, (ChunkRec *)a.recs, recs_stride);
     B200MP_CUDA(cudaGetLastError());
     const DevParams<double> P0 = derive_params<double>(ds.set0);
     const long long grid = (long long)g.n_sets * a.blocks_per_set;
