@@ -40,7 +40,24 @@
 
 namespace b200mp {
 
-constexpr int kTrackBlock = 64;
+#ifndef B200MP_TRACK_BLOCK
+#define B200MP_TRACK_BLOCK 128   /* measured: 64 / 128 / 256 threads with the rendezvous 2.54 / 2.51 / 2.61 ms (65,536 vehicles x 500 steps) */
+#endif
+#ifndef B200MP_TRACK_SYNC
+#define B200MP_TRACK_SYNC 1
+#endif
+constexpr int kTrackBlock = B200MP_TRACK_BLOCK;
+// CTA-wide rendezvous in front of every control update (arrival-counting barrier: the threads of a ragged last block that
+// own no vehicle arrive from their own loop).  The controller's code (~25 KB hot) and the RK4 step loop (17 KB) do not fit
+// the 32 KB instruction cache of an SM together; warps that drift apart keep both sets in flight (ncu: instruction-cache
+// hit rate 88 %, `no_instruction` 14 % of the samples of a 500-step launch), warps that update together do not.
+constexpr bool kTrackSync = B200MP_TRACK_SYNC != 0;
+__device__ __forceinline__ void track_cta_rendezvous()
+{
+    // barrier.sync WITHOUT .aligned (bar.sync is the aligned form): threads of one warp arrive from two different loops when
+    // the last block of a set is ragged, which the aligned form does not allow (it hangs)
+    if (kTrackSync) asm volatile("barrier.sync 0;" ::: "memory");
+}
 constexpr int kFine = 8;             // waypoints per fine chunk
 constexpr int kMid = 4 * kFine;      // one mid chunk = 4 fine chunks
 constexpr int kCoarse = 8 * kMid;    // one coarse chunk = 8 mid chunks = 32 fine chunks = one 32-bit candidate mask
@@ -254,6 +271,98 @@ __device__ __forceinline__ int first_reaching(const double *__restrict__ cm, int
     return a;
 }
 
+// Upper bound on the squared minimum distance for a vehicle's first update (no hint yet): the nearest of the coarse chunks'
+// first waypoints, then of that chunk's mid and fine chunks' first waypoints -- any waypoint is a valid bound, a near one
+// keeps the candidate set small.  Out of line: runs once per vehicle, and the controller's hot code has to share the SM's
+// 32 KB instruction cache with the RK4 step loop.
+__device__ __noinline__ double first_update_bound(const SetView &sv, double x, double y)
+{
+    const int W = sv.W;
+    const int n_coarse = (W + kCoarse - 1) / kCoarse;
+    double qub = INFINITY;
+    int cbest = 0;
+    for (int c = 0; c < n_coarse; ++c) {
+        const double px = sv.coarse[c].ax, py = sv.coarse[c].ay;
+        const double q = (px - x) * (px - x) + (py - y) * (py - y);
+        if (q < qub) {
+            qub = q;
+            cbest = c;
+        }
+    }
+    const int nm0 = min(8, (W - cbest * kCoarse + kMid - 1) / kMid);
+    int mbest = 0;
+    for (int m = 0; m < nm0; ++m) {
+        const double px = sv.mid[cbest * 8 + m].ax, py = sv.mid[cbest * 8 + m].ay;
+        const double q = (px - x) * (px - x) + (py - y) * (py - y);
+        if (q < qub) {
+            qub = q;
+            mbest = m;
+        }
+    }
+    const int nf0 = min(4, (W - cbest * kCoarse - mbest * kMid + kFine - 1) / kFine);
+    for (int f = 0; f < nf0; ++f) {
+        const double px = sv.fine[cbest * 32 + mbest * 4 + f].ax, py = sv.fine[cbest * 32 + mbest * 4 + f].ay;
+        qub = fmin(qub, (px - x) * (px - x) + (py - y) * (py - y));
+    }
+    return qub;
+}
+
+// Tests up to eight consecutive chunk records (count >= 1): bit k of the result = record k may hold the nearest waypoint.
+// No branches (an index past the end is clamped onto the last valid record and its bit masked off), so the 24 loads of a
+// batch are in flight together; one copy of the code serves the three levels.
+__device__ __noinline__ unsigned chunk_test8(const ChunkRec *__restrict__ rec, int count, double x, double y, double ub)
+{
+    unsigned mask = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const bool hold = chunk_may_hold(rec + min(k, count - 1), x, y, ub);
+        mask |= (hold && k < count ? 1u : 0u) << k;
+    }
+    return mask;
+}
+
+// Exact replay of the reference's comparison sequence (first strict minimum of the ROUNDED norms) over a superset of the
+// chunks the fast scan visited; reached only when two squared distances came within 1e-15 of each other.  Out of line.
+__device__ __noinline__ int near_tie_replay(const SetView &sv, double x, double y, double ub, int mode, double *qbest_out)
+{
+    const double2 *__restrict__ w = sv.w;
+    const int W = sv.W;
+    double qbest = INFINITY, dbest = INFINITY;
+    int ibest = 0;
+    for (int c = 0; c * kFine < W; ++c) {
+        if (!chunk_may_hold(sv.fine + c, x, y, ub)) continue;
+        const int i1 = min(W, (c + 1) * kFine);
+        for (int i = c * kFine; i < i1; ++i) {
+            const double2 v = w[i];
+            const double q = host_sq(__dsub_rn(v.x, x), __dsub_rn(v.y, y), mode);
+            if (q < qbest) {
+                const double d = __dsqrt_rn(q);
+                if (d < dbest) {
+                    dbest = d;
+                    qbest = q;
+                    ibest = i;
+                }
+            }
+        }
+    }
+    *qbest_out = qbest;
+    return ibest;
+}
+
+// The reference's look-ahead walk itself (stanley_controller.py:68-75), one addition per waypoint: only when the running-sum
+// search of lookahead_index cannot decide the index within its rounding bound, or the set has a NaN/Inf segment.  Out of line.
+__device__ __noinline__ int lookahead_walk(const double *__restrict__ sg, int W, int min_idx, double min_dist, double lookahead)
+{
+    double total = min_dist;
+    int la = min_idx;
+    for (int i = min_idx + 1; i < W; ++i) {
+        if (total >= lookahead) break;
+        total = __dadd_rn(total, sg[i]);
+        la = i;
+    }
+    return la;
+}
+
 // get_lookahead_index (stanley_controller.py:56-76): exact nearest waypoint, then the look-ahead walk.
 // hint = a waypoint index near the vehicle (the previous update's nearest index) or -1.
 __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, double y, double lookahead, int mode, int hint,
@@ -269,34 +378,7 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
         const double dx = p.x - x, dy = p.y - y;
         qub = dx * dx + dy * dy;
     }
-    if (!(qub < INFINITY)) {
-        // first update of a vehicle: the nearest of the coarse chunks' first waypoints, then of that chunk's mid and fine
-        // chunks' first waypoints -- any waypoint is a valid bound, a near one keeps the candidate set small
-        int cbest = 0;
-        for (int c = 0; c < n_coarse; ++c) {
-            const double px = sv.coarse[c].ax, py = sv.coarse[c].ay;
-            const double q = (px - x) * (px - x) + (py - y) * (py - y);
-            if (q < qub) {
-                qub = q;
-                cbest = c;
-            }
-        }
-        const int nm0 = min(8, (W - cbest * kCoarse + kMid - 1) / kMid);
-        int mbest = 0;
-        for (int m = 0; m < nm0; ++m) {
-            const double px = sv.mid[cbest * 8 + m].ax, py = sv.mid[cbest * 8 + m].ay;
-            const double q = (px - x) * (px - x) + (py - y) * (py - y);
-            if (q < qub) {
-                qub = q;
-                mbest = m;
-            }
-        }
-        const int nf0 = min(4, (W - cbest * kCoarse - mbest * kMid + kFine - 1) / kFine);
-        for (int f = 0; f < nf0; ++f) {
-            const double px = sv.fine[cbest * 32 + mbest * 4 + f].ax, py = sv.fine[cbest * 32 + mbest * 4 + f].ay;
-            qub = fmin(qub, (px - x) * (px - x) + (py - y) * (py - y));
-        }
-    }
+    if (!(qub < INFINITY)) qub = first_update_bound(sv, x, y);
     const double ub = sqrt(qub) * (1.0 + 1.0e-12);   // +inf / NaN: nothing is culled
 
     // The reference updates on `dist < min_dist` with dist = sqrt_rn(q).  sqrt_rn is monotone, so a square that is
@@ -308,36 +390,22 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
     double qbest = INFINITY;
     int ibest = 0;
     bool near_tie = false;
-    // The tests of one level are written without branches (an index past the end is clamped onto the last valid record
-    // and its bit masked off), so that the loads of a whole batch are in flight together instead of one round trip each.
     for (int g0 = 0; g0 < n_coarse; g0 += 8) {
-        unsigned cmask = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const bool hold = chunk_may_hold(sv.coarse + min(g0 + k, n_coarse - 1), x, y, ub);
-            cmask |= (hold && g0 + k < n_coarse ? 1u : 0u) << k;
-        }
+        unsigned cmask = chunk_test8(sv.coarse + g0, min(8, n_coarse - g0), x, y, ub);
         while (cmask) {
             const int g = g0 + __ffs(cmask) - 1;
             cmask &= cmask - 1;
             const int base = g * kCoarse;
-            const int nm = min(8, (W - base + kMid - 1) / kMid);
-            unsigned mmask = 0;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const bool hold = chunk_may_hold(sv.mid + g * 8 + min(m, nm - 1), x, y, ub);
-                mmask |= (hold && m < nm ? 1u : 0u) << m;
-            }
+            unsigned mmask = chunk_test8(sv.mid + g * 8, min(8, (W - base + kMid - 1) / kMid), x, y, ub);
             unsigned mask = 0;
             while (mmask) {
                 const int m = __ffs(mmask) - 1;
                 mmask &= mmask - 1;
-                const int nf = min(4, (W - base - m * kMid + kFine - 1) / kFine);
-#pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    const bool hold = chunk_may_hold(sv.fine + g * 32 + m * 4 + min(f, nf - 1), x, y, ub);
-                    mask |= (hold && f < nf ? 1u : 0u) << (m * 4 + f);
-                }
+                // two neighbouring mid chunks usually survive together: their fine chunks go through one batch of eight
+                const int m2 = (mmask & (1u << (m + 1))) ? m + 1 : m;
+                mmask &= ~(1u << m2);
+                const int nf = min((m2 - m + 1) * 4, (W - base - m * kMid + kFine - 1) / kFine);
+                mask |= chunk_test8(sv.fine + g * 32 + m * 4, nf, x, y, ub) << (m * 4);
             }
             while (mask) {
                 const int i0 = base + (__ffs(mask) - 1) * kFine;
@@ -355,27 +423,7 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
             }
         }
     }
-    if (near_tie) {   // exact replay of the reference's comparison sequence over (a superset of) the same chunks
-        qbest = INFINITY;
-        ibest = 0;
-        double dbest = INFINITY;
-        for (int c = 0; c * kFine < W; ++c) {
-            if (!chunk_may_hold(sv.fine + c, x, y, ub)) continue;
-            const int i1 = min(W, (c + 1) * kFine);
-            for (int i = c * kFine; i < i1; ++i) {
-                const double2 v = w[i];
-                const double q = host_sq(__dsub_rn(v.x, x), __dsub_rn(v.y, y), mode);
-                if (q < qbest) {
-                    const double d = __dsqrt_rn(q);
-                    if (d < dbest) {
-                        dbest = d;
-                        qbest = q;
-                        ibest = i;
-                    }
-                }
-            }
-        }
-    }
+    if (near_tie) ibest = near_tie_replay(sv, x, y, ub, mode, &qbest);   // rare: an exact or near tie
     const int min_idx = (qbest < INFINITY) ? ibest : 0;
     const double min_dist = (qbest < INFINITY) ? __dsqrt_rn(qbest) : INFINITY;
     *nearest = min_idx;
@@ -393,14 +441,7 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
                            ? lo : first_reaching(sv.cm, lo, W, min_dist, cm0, lookahead + err, -1);
         if (lo == hi) return min(lo, W - 1);
     }
-    double total = min_dist;
-    int la = min_idx;
-    for (int i = min_idx + 1; i < W; ++i) {
-        if (total >= lookahead) break;
-        total = __dadd_rn(total, sv.sg[i]);
-        la = i;
-    }
-    return la;
+    return lookahead_walk(sv.sg, W, min_idx, min_dist, lookahead);
 }
 
 // The launch is cut into (vehicle block, time chunk) items claimed by persistent CTAs through a ticket, exactly as the
@@ -417,6 +458,12 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
     __shared__ int s_item;
     extern __shared__ __align__(16) unsigned char s_dyn[];   // the friction table (dynamic: 48 KB and more)
     double *s_mu = reinterpret_cast<double *>(s_dyn);
+    // Controller state of each vehicle between two control updates (steering-filter state, speed-error integral, previous
+    // speed, the two search hints): parked in shared memory while the RK4 steps run.  The step loop's schedule is paid for
+    // in live registers (profiles/r02_k1_instruction_diet.md: capping K1 at 224 of its 246 costs 20 %); carried in
+    // registers, this state and the per-set table pointers took ~30 of them and the same step ran 7-15 % slower here
+    // than in the rollout kernel.  volatile: the values must really leave the register file.
+    volatile double *s_ctl = reinterpret_cast<volatile double *>(s_dyn) + (TAB ? kMuTableDoubles : 0) + threadIdx.x;
     MuTableView T;
     T.c = s_mu;
     T.B2 = a.mu_B2;
@@ -451,40 +498,38 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
         const int local = (blk - set * a.blocks_per_set) * kTrackBlock + threadIdx.x;
         const int r = set * a.vps + local;
         if (local < a.vps && r < a.V) {
-            const double2 *w = a.wp + (size_t)set * a.w_max;
-            const double *hd = a.head + (size_t)set * a.w_max;
             const int W = a.wp_count[set];
-            SetView sv;
-            sv.w = w;
-            sv.fine = a.recs + (size_t)set * a.recs_stride;
-            sv.mid = sv.fine + (a.w_max + kFine - 1) / kFine;
-            sv.coarse = sv.mid + (a.w_max + kMid - 1) / kMid;
-            sv.sg = a.seg + (size_t)set * a.w_max;
-            sv.cm = a.cum + (size_t)set * a.w_max;
-            sv.W = W;
-            sv.clean = a.clean[set] != 0.0;
-            int nearest = -1, la_prev = -1;
-
-            double y[10], ax, ay, x_del, e_int, prev_v;
+            {
+                double x_del, e_int, prev_v;
+                int nearest = -1, la_prev = -1;
+                if (!SLICED || chunk_idx == 0) {
+                    x_del = a.ctrl0[r];
+                    e_int = a.ctrl0[V + r];
+                    prev_v = a.ctrl0[2 * V + r];
+                } else {   // carried state, written by another SM: read through L2
+                    x_del = __ldcg(a.ctrl_end + r);
+                    e_int = __ldcg(a.ctrl_end + V + r);
+                    prev_v = __ldcg(a.ctrl_end + 2 * V + r);
+                    const int2 h = __ldcg(a.hint + r);   // search hints only: the indices found do not depend on them
+                    nearest = h.x;
+                    la_prev = h.y;
+                }
+                s_ctl[0] = x_del;
+                s_ctl[kTrackBlock] = e_int;
+                s_ctl[2 * kTrackBlock] = prev_v;
+                s_ctl[3 * kTrackBlock] = __hiloint2double(la_prev, nearest);
+            }
+            double y[10], ax, ay;
             if (!SLICED || chunk_idx == 0) {
 #pragma unroll
                 for (int c = 0; c < 10; ++c) y[c] = a.state0[c * V + r];
                 ax = a.state0[10 * V + r];
                 ay = a.state0[11 * V + r];
-                x_del = a.ctrl0[r];
-                e_int = a.ctrl0[V + r];
-                prev_v = a.ctrl0[2 * V + r];
-            } else {   // carried state, written by another SM: read through L2
+            } else {
 #pragma unroll
                 for (int c = 0; c < 10; ++c) y[c] = __ldcg(a.state_end + c * V + r);
                 ax = __ldcg(a.state_end + 10 * V + r);
                 ay = __ldcg(a.state_end + 11 * V + r);
-                x_del = __ldcg(a.ctrl_end + r);
-                e_int = __ldcg(a.ctrl_end + V + r);
-                prev_v = __ldcg(a.ctrl_end + 2 * V + r);
-                const int2 h = __ldcg(a.hint + r);   // search hints only: the indices found do not depend on them
-                nearest = h.x;
-                la_prev = h.y;
             }
             double delta = 0.0, tau = 0.0, cte = 0.0;
             WheelCtrl<double> c;
@@ -498,13 +543,29 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
 
             int n = n_begin;
             while (n < n_stop) {
+                track_cta_rendezvous();
                 {   // ---- controllers (drive.py:128-138) on the current state
                     const double v = y[0], yaw = y[7], px = y[8], py = y[9];
+                    double x_del = s_ctl[0], e_int = s_ctl[kTrackBlock], prev_v = s_ctl[2 * kTrackBlock];
                     int ce = 0;
                     double raw;
                     if (W > 0) {
+                        const double hints = s_ctl[3 * kTrackBlock];
+                        int nearest = __double2loint(hints);
+                        const int la_prev = __double2hiint(hints);
+                        const double2 *w = a.wp + (size_t)set * a.w_max;
+                        const double *hd = a.head + (size_t)set * a.w_max;
+                        SetView sv;
+                        sv.w = w;
+                        sv.fine = a.recs + (size_t)set * a.recs_stride;
+                        sv.mid = sv.fine + (a.w_max + kFine - 1) / kFine;
+                        sv.coarse = sv.mid + (a.w_max + kMid - 1) / kMid;
+                        sv.sg = a.seg + (size_t)set * a.w_max;
+                        sv.cm = a.cum + (size_t)set * a.w_max;
+                        sv.W = W;
+                        sv.clean = a.clean[set] != 0.0;
                         ce = lookahead_index(sv, px, py, a.lookahead, a.norm_mode, nearest, la_prev, &nearest);
-                        la_prev = ce;
+                        s_ctl[3 * kTrackBlock] = __hiloint2double(ce, nearest);
                         {   // the next update reads a few waypoints further along both indices: start the following cache
                             // lines of every table it walks towards L1 now, ctrl_every steps ahead of their use
                             const int in = min(nearest + 8, W - 1), ic = min(ce + 8, W - 1);
@@ -546,6 +607,9 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
                     set_steer<double, true>(c, &delta);
                     c.tq[0] = c.tq[1] = c.tq[2] = c.tq[3] = tau * P0.inv_Jw;
                     if (a.target_idx) a.target_idx[(size_t)(n / a.ctrl_every) * V + r] = ce;
+                    s_ctl[0] = x_del;
+                    s_ctl[kTrackBlock] = e_int;
+                    s_ctl[2 * kTrackBlock] = prev_v;
                 }
                 const int n_end = min(n_stop, n + a.ctrl_every);
 #pragma unroll 1
@@ -585,10 +649,15 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
             for (int k = 0; k < 10; ++k) a.state_end[k * V + r] = y[k];
             a.state_end[10 * V + r] = ax;
             a.state_end[11 * V + r] = ay;
-            a.ctrl_end[r] = x_del;
-            a.ctrl_end[V + r] = e_int;
-            a.ctrl_end[2 * V + r] = prev_v;
-            if (SLICED && chunk_idx + 1 < sc.n_chunks) a.hint[r] = make_int2(nearest, la_prev);
+            a.ctrl_end[r] = s_ctl[0];
+            a.ctrl_end[V + r] = s_ctl[kTrackBlock];
+            a.ctrl_end[2 * V + r] = s_ctl[2 * kTrackBlock];
+            if (SLICED && chunk_idx + 1 < sc.n_chunks) {
+                const double hints = s_ctl[3 * kTrackBlock];
+                a.hint[r] = make_int2(__double2loint(hints), __double2hiint(hints));
+            }
+        } else if (kTrackSync) {   // no vehicle: keep the rendezvous count of the block
+            for (int n = n_begin; n < n_stop; n += a.ctrl_every) track_cta_rendezvous();
         }
         if (SLICED && chunk_idx + 1 < sc.n_chunks) {   // publish the carried state of this block
             __threadfence();
@@ -707,7 +776,7 @@ int launch_track_f64(int device, cudaStream_t st, const B200mpTrackArgs &g)
     const size_t smem_tab = sizeof(double) * kMuTableDoubles;
     const bool log = g.log != nullptr;
     const bool tab_used = tab && (!log || g.store_stride > 1);   // a logging launch that stores every step never takes the table
-    const size_t smem = tab_used ? smem_tab : 0;
+    const size_t smem = (tab_used ? smem_tab : 0) + sizeof(double) * 4 * kTrackBlock;   // + the controller-state stash
     // the four (LOG, TAB) combinations
     typedef void (*Kern)(const TrackDev, const DevParams<double>, const SliceSched);
     const Kern kern = log ? (tab_used ? (Kern)track_kernel<true, true> : (Kern)track_kernel<true, false>)

@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what")
     ap.add_argument("--launches", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100, help="track / track_log: steps per launch")
     a = ap.parse_args()
     eng = mp.Engine(0)
     p = mp.VehicleParameters()
@@ -41,7 +42,7 @@ def main():
         st0, wps = wl.tracking_fleet(V=65536, n_sets=16)
         s, w = eng.dev(st0), eng.dev(wps)
         for _ in range(a.launches):
-            eng.track_closed_loop(s, w, wl.DT, 100, 25.0, vehicles_per_set=4096,
+            eng.track_closed_loop(s, w, wl.DT, a.steps, 25.0, vehicles_per_set=4096,
                                   **({"store_stride": 10, "want_log": True} if a.what.endswith("log") else {}))
     elif a.what == "planner":
         # one launch of every planner-side kernel at config-3 size: obstacle_prepare + collision_cull<3> (flags from yaws),
