@@ -12,8 +12,8 @@
 // and then walks forward summing segment lengths until the look-ahead distance is reached.  Here:
 //   * a prepare kernel evaluates, once per waypoint set, everything that does not depend on the vehicle:
 //     segment lengths (same closed form as the host's norm, so the walk adds the same doubles), their
-//     running sum (a search key only), segment headings, and one record per chunk of 8 ("fine"), 32 ("mid") and
-//     256 ("coarse") consecutive waypoints: the chord from the chunk's first to its last waypoint and the largest
+//     running sum (a search key only), segment headings, and one record per chunk of 8 ("fine"), 64 ("mid") and
+//     512 ("coarse") consecutive waypoints: the chord from the chunk's first to its last waypoint and the largest
 //     distance `eps` of any of its waypoints from that chord;
 //   * the nearest-waypoint search is exact but sub-linear: the distance to the previous update's nearest
 //     waypoint (or to the coarse chunks' first waypoints) is an upper bound UB on the minimum; every waypoint of a
@@ -22,8 +22,8 @@
 //     path at a lateral offset d sees the distance grow only quadratically along the path (sqrt(d^2 + s^2)), so the
 //     former test "first waypoint of the chunk farther than UB + chunk radius" kept 2 sqrt(2 d r) / ds waypoints alive
 //     (a dozen fine chunks at d = 0.3 m); the chord test keeps the one or two chunks around the foot point whatever d
-//     is.  Coarse chunks are culled first, then the 8 mid chunks of a survivor, then the 4 fine chunks of a surviving
-//     mid chunk (one 32-bit mask per coarse chunk), and the surviving waypoints are compared on the squared distance
+//     is.  Coarse chunks are culled first, then the 8 mid chunks of a survivor, then the 8 fine chunks of a surviving
+//     mid chunk, and the surviving waypoints are compared on the squared distance
 //     in the host's rounding sequence (sqrt_rn is monotone).  The reference's "first strict minimum of the
 //     rounded norms" is reproduced by a branch-free scan plus an exact replay when any two squares came
 //     within 1e-15 of each other (ties, duplicate waypoints);
@@ -59,8 +59,8 @@ __device__ __forceinline__ void track_cta_rendezvous()
     if (kTrackSync) asm volatile("barrier.sync 0;" ::: "memory");
 }
 constexpr int kFine = 8;             // waypoints per fine chunk
-constexpr int kMid = 4 * kFine;      // one mid chunk = 4 fine chunks
-constexpr int kCoarse = 8 * kMid;    // one coarse chunk = 8 mid chunks = 32 fine chunks = one 32-bit candidate mask
+constexpr int kMid = 8 * kFine;      // one mid chunk = 8 fine chunks
+constexpr int kCoarse = 8 * kMid;    // one coarse chunk = 8 mid chunks: every level is tested eight records at a time
 
 // One chunk of consecutive waypoints [i0, i1] for the nearest-waypoint search: the chord a + t u (t in [0, 1]) from its
 // first to its last waypoint, 1/|u|^2 (0 for a degenerate or non-finite chord: the "chord" is then the point a), and
@@ -88,8 +88,9 @@ __device__ __forceinline__ void track_prefetch_l1(const void *p)
 // false only when no waypoint of the chunk can be within ub of (x, y).  With d the true distance from the vehicle to the
 // chord and s the evaluated one: |s - d| <= ~1e-15 (d + |u|) (the clamped foot point stays ON the chord, so a rounding of t
 // can only lengthen the distance; the remaining operations are relatively accurate on operands bounded by d + |u|).  The
-// relative part is covered by the factor below, the |u| part by the 1e-11 max|w_j - a| >= 1e-11 |u| added to eps by the
-// prepare kernel.  NaN anywhere compares false: the chunk is searched.
+// relative part is covered by the factor below, the |u| part by the 1e-11 |u| the prepare kernel adds to eps (which also
+// carries 1e-9 of each waypoint's deviation and 1e-11 of its distance from the chunk's first waypoint for the rounding of
+// the deviations themselves).  NaN anywhere compares false: the chunk is searched.
 __device__ __forceinline__ bool chunk_may_hold(const ChunkRec *__restrict__ rec, double x, double y, double ub)
 {
     const double2 *__restrict__ p = reinterpret_cast<const double2 *>(rec);
@@ -144,7 +145,10 @@ track_prepare_kernel(int w_max, const double2 *__restrict__ wp, const int *__res
     const int set = blockIdx.x;
     const int W = wp_count[set];
     const double2 *w = wp + (size_t)set * w_max;
-    // chunk records of the three levels, one compact array per set (fine, then mid, then coarse)
+    // chunk records of the three levels, one compact array per set (fine, then mid, then coarse).  Three passes: the chords
+    // (one thread per record), then every waypoint's distance from the chord of its fine, mid and coarse chunk folded into
+    // the record with an atomic max (a coarse chunk has 512 waypoints: one thread per record took 50 us per launch), then
+    // the slack terms.
     const int n_fine = (w_max + kFine - 1) / kFine, n_mid = (w_max + kMid - 1) / kMid, n_coarse = (w_max + kCoarse - 1) / kCoarse;
     ChunkRec *rset = recs + (size_t)set * recs_stride;
     for (int c = threadIdx.x; c < n_fine + n_mid + n_coarse; c += blockDim.x) {
@@ -153,7 +157,7 @@ track_prepare_kernel(int w_max, const double2 *__restrict__ wp, const int *__res
         const int i0 = idx * size;
         ChunkRec r;
         r.ax = r.ay = r.ux = r.uy = r.inv_l2 = 0.0;
-        r.eps = INFINITY;
+        r.eps = i0 < W ? 0.0 : INFINITY;   // records past the end are never read
         if (i0 < W) {
             const int i1 = min(W, i0 + size) - 1;
             const double2 a = w[i0], b = w[i1];
@@ -165,20 +169,31 @@ track_prepare_kernel(int w_max, const double2 *__restrict__ wp, const int *__res
             r.ux = chord ? ux : 0.0;
             r.uy = chord ? uy : 0.0;
             r.inv_l2 = chord ? 1.0 / l2 : 0.0;
-            double dev = 0.0, far = 0.0;
-            bool finite = true;
-            for (int j = i0; j <= i1; ++j) {
-                const double2 q = w[j];
-                finite = finite && fabs(q.x) < INFINITY && fabs(q.y) < INFINITY;
-                dev = fmax(dev, sqrt(chord_dist2(r.ax, r.ay, r.ux, r.uy, r.inv_l2, q.x, q.y)));
-                const double fx = q.x - a.x, fy = q.y - a.y;
-                far = fmax(far, sqrt(fx * fx + fy * fy));
-            }
-            // rounding of dev itself and of the search's evaluation (see chunk_may_hold): 1e-11 of the chunk's extent
-            const double eps = dev * (1.0 + 1.0e-9) + 1.0e-11 * far + 1.0e-300;
-            r.eps = (finite && eps < INFINITY) ? eps : INFINITY;
         }
         rset[c] = r;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+        const double2 q = w[j];
+        const bool finite = fabs(q.x) < INFINITY && fabs(q.y) < INFINITY;
+#pragma unroll
+        for (int lvl = 0; lvl < 3; ++lvl) {
+            ChunkRec *r = rset + (lvl == 0 ? j / kFine : (lvl == 1 ? n_fine + j / kMid : n_fine + n_mid + j / kCoarse));
+            const double dev = sqrt(chord_dist2(r->ax, r->ay, r->ux, r->uy, r->inv_l2, q.x, q.y));
+            const double fx = q.x - r->ax, fy = q.y - r->ay;
+            // rounding of dev itself (see chunk_may_hold): 1e-11 of this waypoint's distance from the chunk's first one
+            double e = dev * (1.0 + 1.0e-9) + 1.0e-11 * sqrt(fx * fx + fy * fy);
+            if (!(finite && e < INFINITY)) e = INFINITY;   // a chunk with a non-finite coordinate is never culled
+            atomicMax(reinterpret_cast<unsigned long long *>(&r->eps), (unsigned long long)__double_as_longlong(e));   // e >= 0
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n_fine + n_mid + n_coarse; c += blockDim.x) {
+        // the search's own evaluation error, proportional to the chord length (chunk_may_hold)
+        ChunkRec *r = rset + c;
+        const double len = sqrt(r->ux * r->ux + r->uy * r->uy);
+        const double eps = r->eps + 1.0e-11 * len + 1.0e-300;
+        r->eps = eps < INFINITY ? eps : INFINITY;
     }
     double *sg = seg + (size_t)set * w_max, *hd = head + (size_t)set * w_max, *cm = cum + (size_t)set * w_max;
     int ok = 1;
@@ -299,9 +314,9 @@ __device__ __noinline__ double first_update_bound(const SetView &sv, double x, d
             mbest = m;
         }
     }
-    const int nf0 = min(4, (W - cbest * kCoarse - mbest * kMid + kFine - 1) / kFine);
+    const int nf0 = min(8, (W - cbest * kCoarse - mbest * kMid + kFine - 1) / kFine);
     for (int f = 0; f < nf0; ++f) {
-        const double px = sv.fine[cbest * 32 + mbest * 4 + f].ax, py = sv.fine[cbest * 32 + mbest * 4 + f].ay;
+        const double px = sv.fine[cbest * 64 + mbest * 8 + f].ax, py = sv.fine[cbest * 64 + mbest * 8 + f].ay;
         qub = fmin(qub, (px - x) * (px - x) + (py - y) * (py - y));
     }
     return qub;
@@ -397,28 +412,24 @@ __device__ __forceinline__ int lookahead_index(const SetView &sv, double x, doub
             cmask &= cmask - 1;
             const int base = g * kCoarse;
             unsigned mmask = chunk_test8(sv.mid + g * 8, min(8, (W - base + kMid - 1) / kMid), x, y, ub);
-            unsigned mask = 0;
             while (mmask) {
                 const int m = __ffs(mmask) - 1;
                 mmask &= mmask - 1;
-                // two neighbouring mid chunks usually survive together: their fine chunks go through one batch of eight
-                const int m2 = (mmask & (1u << (m + 1))) ? m + 1 : m;
-                mmask &= ~(1u << m2);
-                const int nf = min((m2 - m + 1) * 4, (W - base - m * kMid + kFine - 1) / kFine);
-                mask |= chunk_test8(sv.fine + g * 32 + m * 4, nf, x, y, ub) << (m * 4);
-            }
-            while (mask) {
-                const int i0 = base + (__ffs(mask) - 1) * kFine;
-                mask &= mask - 1;
+                const int mbase = base + m * kMid;
+                unsigned mask = chunk_test8(sv.fine + g * 64 + m * 8, min(8, (W - mbase + kFine - 1) / kFine), x, y, ub);
+                while (mask) {
+                    const int i0 = mbase + (__ffs(mask) - 1) * kFine;
+                    mask &= mask - 1;
 #pragma unroll
-                for (int k = 0; k < kFine; ++k) {
-                    const int i = min(i0 + k, W - 1);               // the last chunk may be short: re-reading W-1 is harmless
-                    const double2 v = w[i];
-                    const double q = host_sq(__dsub_rn(v.x, x), __dsub_rn(v.y, y), mode);
-                    const bool better = q < qbest * (1.0 - 1.0e-15);
-                    near_tie |= !better && q <= qbest * (1.0 + 1.0e-15) && q < INFINITY && i0 + k < W;
-                    qbest = better ? q : qbest;
-                    ibest = better ? i : ibest;
+                    for (int k = 0; k < kFine; ++k) {
+                        const int i = min(i0 + k, W - 1);               // the last chunk may be short: re-reading W-1 is harmless
+                        const double2 v = w[i];
+                        const double q = host_sq(__dsub_rn(v.x, x), __dsub_rn(v.y, y), mode);
+                        const bool better = q < qbest * (1.0 - 1.0e-15);
+                        near_tie |= !better && q <= qbest * (1.0 + 1.0e-15) && q < INFINITY && i0 + k < W;
+                        qbest = better ? q : qbest;
+                        ibest = better ? i : ibest;
+                    }
                 }
             }
         }
