@@ -576,6 +576,8 @@ def collision_metrics(eng, wl, np, torch, lit):
     ms_k = variants["shipped_scene_auto"]["ms"]
     ms_clear, _ = dev_ms(lambda: eng.collision_check_batch(px, py, None, obs, w["offsets"], w["radii"], trig=trig, want_clearance=True))
     ms_clear_api, _ = wall_ms(lambda: eng.collision_check_batch(px, py, w["pyaw"], obs, w["offsets"], w["radii"], want_clearance=True), reps=5)
+    ms_clear_api_dev, _ = wall_ms(lambda: eng.collision_check_batch(px, py, w["pyaw"], obs, w["offsets"], w["radii"], want_clearance=True,
+                                                                     clearance_trig="device"), reps=5)
     out["collision"] = {
         "metric": "lattice collision checks/sec", "unit": unit, "workload": f"config3: {P} paths x {n} points x {nc} circles vs {M} obstacle points, bit-exact flags",
         "value": tests / (ms_k * 1e-3), "ms": ms_k, "paths_per_s": P / (ms_k * 1e-3),
@@ -588,7 +590,8 @@ def collision_metrics(eng, wl, np, torch, lit):
         "api_inputs_resident": {"ms": ms_res, "value": tests / (ms_res * 1e-3),
                                 "includes": "kernels + the 4-byte undecided count read back + stream sync"},
         "api_host_trig_all_yaws": {"ms": ms_host_trig, "note": "the former default: numpy cos/sin of 200k yaws on the host + their H2D"},
-        "min_clearance": {"kernel_ms": ms_clear, "value": tests / (ms_clear * 1e-3), "api_ms_host_trig": ms_clear_api},
+        "min_clearance": {"kernel_ms": ms_clear, "value": tests / (ms_clear * 1e-3), "api_ms_host_trig": ms_clear_api,
+                          "api_ms_device_trig": ms_clear_api_dev},
         "variants": variants,
     }
     # ---- roofline of the shipped kernel: 4 FP32 lane-operations per executed test (2 subtractions, 1 multiply, 1 FMA = 5 flop)

@@ -460,7 +460,7 @@ class Engine:
 
     def collision_check_batch(self, px, py, pyaw, obstacles, offsets: Sequence[float], radii: Sequence[float],
                               want_clearance: bool = False, device_trig: bool = False, trig=None, host_trig: bool = False,
-                              mode: Optional[str] = None):
+                              mode: Optional[str] = None, clearance_trig: str = "host"):
         """``free[P]`` (uint8, 1 = collision-free) for P paths at once.
 
         px, py ``[P,n]``; pyaw ``[P,>=n]`` (first n used).  Default: the yaws go to the device
@@ -473,7 +473,20 @@ class Engine:
         the minimum clearance is a double that depends on every centre's last bit); ``device_trig=True`` is the unproven
         device-only path (kept for A/B).  ``mode`` = ``"auto" | "screen" | "fp64"`` for this call (default: the
         process-wide mode).  ``self.last_collision_undecided`` = number of host-resolved path points of the last call.
+
+        ``want_clearance=True`` also returns the minimum clearance ``[P]`` (an extension: the reference returns booleans only).
+        ``clearance_trig="host"`` (default) evaluates every yaw with numpy so that the clearance equals the oracle's double bit
+        for bit; ``clearance_trig="device"`` keeps the yaws on the device: the FLAGS are still the proven bit-exact ones of the
+        yaw kernel, the clearance comes from the device's ``sincos`` and differs from the host-trig value by at most a few
+        1e-16 m (the circle centres move by an ulp) -- 0.7 ms instead of 2.9 ms on config 3.
         """
+        if want_clearance and clearance_trig not in ("host", "device"):
+            raise ValueError("clearance_trig must be 'host' or 'device'")
+        if want_clearance and clearance_trig == "device" and trig is None and not host_trig and not device_trig:
+            free = self.collision_check_batch(px, py, pyaw, obstacles, offsets, radii, mode=mode)
+            _, clr = self.collision_check_batch(px, py, pyaw, obstacles, offsets, radii, want_clearance=True, device_trig=True,
+                                                mode=mode)
+            return free, clr
         pxt, pyt = self.dev(px), self.dev(py)
         if pxt.dim() != 2:
             raise ValueError("px, py must be [P, n_pts]")

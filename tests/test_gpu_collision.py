@@ -65,6 +65,14 @@ def test_collision_cfg3_full_bit_exact(engine):
     ref2, clr_ref, _ = c_oracle.collision_check(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD, want_clearance=True)
     assert np.array_equal(_np(free2).astype(bool), ref) and np.array_equal(ref2, ref)
     assert np.array_equal(_np(clr), clr_ref)                     # same roundings -> identical doubles
+    # clearance with the yaws kept on the device: flags still the proven bit-exact ones, the clearance within a few ulp of a
+    # circle centre (1e-12 m stated; the device's sincos moves a centre by ~2e-16 m)
+    free3, clr3 = engine.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD, want_clearance=True,
+                                               clearance_trig="device")
+    assert np.array_equal(_np(free3).astype(bool), ref)
+    d = np.abs(_np(clr3) - clr_ref)
+    print(f"device-trig clearance: max |diff| {d.max():.2e} m, {np.count_nonzero(d)} of {d.size} paths differ")
+    assert d.max() < 1e-12
     # the default call above sent the YAWS to the device (proven verdicts + host-resolved leftovers); the former default
     # -- numpy cos / sin of every yaw on the host -- and caller-supplied trig give the same flags, bit for bit
     und = engine.last_collision_undecided

@@ -120,6 +120,12 @@ def test_lookahead_index_exact_on_adversarial_waypoints(engine, mode):
     nanwp[[0, 31, 32, 64, 150], :] = np.nan
     cases.append(nanwp)
     cases.append(np.zeros((100, 2)))                                                      # all the same point
+    # longer than one batch of coarse chunks (8 x 512 waypoints), ragged last chunks on every level, and a path that comes
+    # back beside itself 2 cm away: chord culling must keep both branches alive
+    u = np.arange(9003) * 0.01
+    cases.append(np.stack([np.where(u < 45, u, 90 - u), np.where(u < 45, 0.0, 0.02) + 0.3 * np.sin(0.2 * np.minimum(u, 90 - u))], 1))
+    sp = np.linspace(0.5, 12 * np.pi, 4611)
+    cases.append(np.stack([0.4 * sp * np.cos(sp), 0.4 * sp * np.sin(sp)], 1))             # spiral: neighbouring turns 2.5 m apart
     for k, wp in enumerate(cases):
         V = 512
         lo, hi = np.nanmin(wp, 0) - 3.0, np.nanmax(wp, 0) + 3.0
