@@ -636,21 +636,21 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
                         until_store = a.store_stride;
                         if (tp) {
 #pragma unroll
-                            for (int k = 0; k < 10; ++k) tp[k * V] = y[k];
+                            for (int k = 0; k < 10; ++k) __stcs(tp + k * V, y[k]);   // written once: streaming stores, as in the rollout kernel
                             tp += 10 * V;
                         }
                         if (LOG && lp) {   // the DataLog row of drive.py:145-151
-                            lp[0] = __dmul_rn((double)(a.step0 + n), a.dt);
+                            __stcs(lp, __dmul_rn((double)(a.step0 + n), a.dt));
 #pragma unroll
-                            for (int k = 0; k < 10; ++k) lp[(1 + k) * V] = y[k];
+                            for (int k = 0; k < 10; ++k) __stcs(lp + (1 + k) * V, y[k]);
 #pragma unroll
-                            for (int k = 0; k < 10; ++k) lp[(11 + k) * V] = sdot[k];
-                            lp[21 * V] = delta;
+                            for (int k = 0; k < 10; ++k) __stcs(lp + (11 + k) * V, sdot[k]);
+                            __stcs(lp + 21 * V, delta);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) lp[(22 + k) * V] = tau;
+                            for (int k = 0; k < 4; ++k) __stcs(lp + (22 + k) * V, tau);
 #pragma unroll
-                            for (int k = 0; k < 18; ++k) lp[(26 + k) * V] = outs[k];
-                            lp[44 * V] = cte;
+                            for (int k = 0; k < 18; ++k) __stcs(lp + (26 + k) * V, outs[k]);
+                            __stcs(lp + 44 * V, cte);
                             lp += 45 * V;
                         }
                     }

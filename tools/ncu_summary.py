@@ -24,6 +24,7 @@ KEYS = [
     "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum.per_cycle_elapsed",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "sm__icc_request_hit_rate.pct", "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct",
 ]
 STALLS = "smsp__average_warps_issue_stalled_"
 
