@@ -205,3 +205,36 @@ def test_tracking_time_sliced_launch_equals_plain_launches(engine):
                                   vehicles_per_set=len(idx))
         assert np.array_equal(_np(big.target_idx)[:, idx], ref["target_idx"])
         assert rel_err(_np(big.state_end)[:, idx], ref["state_end"]).max() < REL_TOL_F64
+
+
+def test_tracking_sliced_launch_with_ragged_blocks(engine):
+    """Time-sliced launch whose sets do not fill their last 128-thread block (1,000 vehicles per set = 7 full blocks + 104
+    threads, i.e. a partly filled warp): the CTA-wide rendezvous in front of every control update counts arrivals from
+    the threads that own no vehicle as well.  Results must equal plain launches of a few sets each, bit for bit."""
+    _setup(engine)
+    n_sets, vps, N = 40, 1000, 120                      # 320 blocks: more than the resident CTAs -> sliced
+    V = n_sets * vps
+    st0, wps = wl.tracking_fleet(V, n_sets, W=1500)
+    mode = host_norm2_mode()
+    big = engine.track_closed_loop(st0, wps, DT, N, 25.0, vehicles_per_set=vps, norm_mode=mode, want_target_idx=True,
+                                   store_stride=40)
+    parts = []
+    for s0 in range(0, n_sets, 10):                     # 80 blocks per launch: one block per CTA, no ticket
+        lo, hi = s0 * vps, (s0 + 10) * vps
+        parts.append(engine.track_closed_loop(st0[:, lo:hi], wps[s0:s0 + 10], DT, N, 25.0, vehicles_per_set=vps,
+                                              norm_mode=mode, want_target_idx=True, store_stride=40))
+    assert torch.equal(big.state_end, torch.cat([p.state_end for p in parts], dim=1))
+    assert torch.equal(big.ctrl_end, torch.cat([p.ctrl_end for p in parts], dim=1))
+    assert torch.equal(big.traj, torch.cat([p.traj for p in parts], dim=2))
+    assert torch.equal(big.target_idx, torch.cat([p.target_idx for p in parts], dim=1))
+    # a fleet that does not fill its sets at all (V < n_sets * vehicles_per_set) against the oracle
+    par = _setup(engine)
+    Vs = 3 * 70 - 11
+    st1, wp1 = wl.tracking_fleet(3 * 70, 3, W=400)
+    st1 = st1[:, :Vs]
+    c0 = np.zeros((3, Vs))
+    c0[2] = st1[0]
+    ref = c_oracle.track_loop(st1, c0, wp1, None, par, DT, 60, 25.0, c_oracle.track_gains(), mode, vehicles_per_set=70)
+    res = engine.track_closed_loop(st1, wp1, DT, 60, 25.0, vehicles_per_set=70, norm_mode=mode, want_target_idx=True)
+    assert np.array_equal(_np(res.target_idx), ref["target_idx"])
+    assert rel_err(_np(res.state_end), ref["state_end"]).max() < REL_TOL_F64
