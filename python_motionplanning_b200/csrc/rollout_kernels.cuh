@@ -46,6 +46,19 @@ template <typename R> __device__ __forceinline__ void traj_store(R *p, R v)
 #endif
 }
 
+// Development A/B (tools/kbench): a CTA-wide arrival-counting barrier in front of every control segment keeps the warps of
+// a CTA in the same part of the step loop (the closed-loop kernel needs it for its instruction-cache footprint; whether the
+// plain rollout gains from it is what the macro measures -- see profiles/r02_k1_launch_shape.md).
+#ifndef B200MP_ROLLOUT_SYNC
+#define B200MP_ROLLOUT_SYNC 0
+#endif
+__device__ __forceinline__ void rollout_cta_rendezvous()
+{
+#if B200MP_ROLLOUT_SYNC
+    asm volatile("barrier.sync 0;" ::: "memory");
+#endif
+}
+
 // Phase staggering.  The CTAs of a launch start together and do identical work, so the (two) warps that share a scheduler
 // run the same part of an RK4 step at the same time: both want the FP64 pipe in the wheel / polynomial sections and both
 // leave it idle in the serial sections (one wave of 37,888 rollouts x 500 steps runs at 1.93e10 steps/s, eight waves -- whose
@@ -331,6 +344,7 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
             SLICE_PROF_T(t_loop);
             SLICE_PROF_ADD(1, t_loop - t_ready);
             while (!H1 && n < n_end) {
+                rollout_cta_rendezvous();
                 const int seg = (a.step0 + n) / a.hold;
                 int seg_end = (seg + 1) * a.hold - a.step0;
                 if (seg_end > n_end) seg_end = n_end;
@@ -383,6 +397,14 @@ rk4_rollout_kernel(const __grid_constant__ RolloutDev<R> a, const __grid_constan
             __syncthreads();
             SLICE_PROF_ADD(2, clock64() - t_done);
             SLICE_PROF_ADD(5, t_done - t_loop);
+#endif
+#if B200MP_ROLLOUT_SYNC
+        } else if (!H1) {   // no rollout: keep the rendezvous count of the block (one per control segment)
+            for (int n = n_begin; n < n_end;) {
+                rollout_cta_rendezvous();
+                int seg_end = ((a.step0 + n) / a.hold + 1) * a.hold - a.step0;
+                n = seg_end > n_end ? n_end : seg_end;
+            }
 #endif
         }
         if (SLICED && chunk_idx + 1 < sc.n_chunks) {   // publish the carried state of this block

@@ -143,7 +143,7 @@ track_prepare_kernel(int w_max, const double2 *__restrict__ wp, const int *__res
                      double *__restrict__ clean, ChunkRec *__restrict__ recs, int recs_stride)
 {
     const int set = blockIdx.x;
-    const int W = wp_count[set];
+    const int W = max(0, min(wp_count[set], w_max));   // a count beyond the array is clamped, never read out of bounds
     const double2 *w = wp + (size_t)set * w_max;
     // chunk records of the three levels, one compact array per set (fine, then mid, then coarse).  Three passes: the chords
     // (one thread per record), then every waypoint's distance from the chord of its fine, mid and coarse chunk folded into
@@ -509,7 +509,7 @@ track_kernel(const __grid_constant__ TrackDev a, const __grid_constant__ DevPara
         const int local = (blk - set * a.blocks_per_set) * kTrackBlock + threadIdx.x;
         const int r = set * a.vps + local;
         if (local < a.vps && r < a.V) {
-            const int W = a.wp_count[set];
+            const int W = max(0, min(a.wp_count[set], a.w_max));
             {
                 double x_del, e_int, prev_v;
                 int nearest = -1, la_prev = -1;
