@@ -382,6 +382,10 @@ class Engine:
         cnt = self.dev(wp_count if wp_count is not None else [W] * n_sets, torch.int32)
         if cnt.numel() != n_sets:
             raise ValueError("wp_count must have one entry per waypoint set")
+        if wp_count is not None and not isinstance(wp_count, torch.Tensor):   # host data: check it here (the kernel clamps)
+            c = np.asarray(wp_count)
+            if c.size and (c.min() < 0 or c.max() > W):
+                raise ValueError(f"wp_count entries must lie in [0, {W}]")
         vps = int(vehicles_per_set or max(1, -(-V // n_sets)))
         if ctrl0 is None:
             c0 = torch.zeros(3, V, dtype=torch.float64, device=self.tdev)

@@ -153,6 +153,8 @@ def test_tracking_edge_cases(engine):
         engine.track_closed_loop(state0, wp, DT, 10, step0=5)              # launches start on a control update
     with pytest.raises(ValueError):
         engine.track_closed_loop(state0, wp, DT, 10, vehicles_per_set=8)   # sets do not cover the fleet
+    with pytest.raises(ValueError):
+        engine.track_closed_loop(state0, wp, DT, 10, wp_count=[500, 501])  # a count beyond the list
     # custom gains / ctrl_every / ragged set lengths against the oracle
     par = c_oracle.make_params(pn.VehicleParams())
     par[0].D[:] = (1.0,) * 4
