@@ -200,6 +200,7 @@ B200MP_HD double mu_table_eval(const double *row, double t)
 template <typename Row> struct MuRowCacheT {
     int k[4];
     Row r[4];
+    double rinv[4];   // B200MP_CARRY_RCP: 1/vx of each wheel at the previous stage of the step
 };
 typedef MuRowCacheT<MuRow> MuRowCache;
 
@@ -457,6 +458,14 @@ B200MP_HD R wheel_vx(R vxc, R vyc, R cd, R sd)
 #ifndef B200MP_HEADING_FRAME
 #define B200MP_HEADING_FRAME 0
 #endif
+// B200MP_CARRY_RCP (FP64 tabulated step): stages 2-4 refine the previous stage's 1/vx of the same wheel instead of taking a
+// new hardware seed -- vx moves by ~1e-5 relative between stages, so r (1 + e + e^2 + e^3) with e = 1 - vx r is exact to e^4
+// (|e| <= 2^-13 checked, else the step is repeated on the checked path).  12 of the 16 MUFU.RCP64H of a step and their
+// zero-low-word moves go, the reciprocal's part of the stage's dependency chain shrinks from seed + 3 DFMA to 4 DFMA; costs
+// eight live registers across the stages.  Measured: see profiles/r02_k1_launch_shape.md.
+#ifndef B200MP_CARRY_RCP
+#define B200MP_CARRY_RCP 0
+#endif
 #ifndef B200MP_HEADING_FRAME_F32
 #define B200MP_HEADING_FRAME_F32 1   /* K1f is issue-bound: there the 12 instructions per step are time */
 #endif
@@ -488,7 +497,19 @@ B200MP_HD void wheel_forces(const DevParams<R> &P, R D, R vxc, R vyc, R w, R cd,
         vx = vxc * cd + vyc * sd;        // :274-281
         vy = vyc * cd - vxc * sd;
     }
-    const R r = EXT_R ? r_ext : M::rcp(vx);
+    R r;
+    constexpr bool kCarry = B200MP_CARRY_RCP != 0 && TAB && sizeof(R) == 8 && !EXT_R;
+    if (kCarry && RC && !FIRST) {
+        const R y0 = (R)RC->rinv[I];
+        const R e = fma(-vx, y0, (R)1);
+        const R t1 = fma(e, e, e);
+        const R t2 = fma(t1, e, e);
+        r = fma(y0, t2, y0);
+        ok &= M::abs(e) <= (R)0.0001220703125;
+    } else {
+        r = EXT_R ? r_ext : M::rcp(vx);
+    }
+    if (kCarry && RC) RC->rinv[I] = (double)r;
     // (rw*w - vx)/vx instead of rw*w/vx - 1 (:284-287): same value, no cancellation after the divide,
     // and exactly 0 when the rounded product equals vx (the reference's zero-slip equilibrium)
     const R sx = (M::mul_rn(P.rw, w) - vx) * r;
