@@ -139,8 +139,16 @@ constexpr bool kRolloutSpeculative = B200MP_RK4_SPECULATIVE != 0;
 #define B200MP_MU_CACHE_STEPS 0   /* measured: keeping the rows live across steps costs 255 registers and 13 % */
 #endif
 constexpr bool kCacheAcrossSteps = B200MP_MU_CACHE_STEPS != 0;
+// NOTE (measured, profiles/r02_k1_launch_shape.md): __maxnreg__ REPLACES __launch_bounds__, and a kernel compiled without
+// __launch_bounds__(64) is 12 % slower even with a cap of 255 registers -- register-budget experiments must use
+// B200MP_ROLLOUT_MINBLOCKS (__launch_bounds__(block, min blocks per SM)), not B200MP_ROLLOUT_MAXNREG.
+#ifndef B200MP_ROLLOUT_MINBLOCKS
+#define B200MP_ROLLOUT_MINBLOCKS 0
+#endif
 #if B200MP_ROLLOUT_MAXNREG > 0
 #define B200MP_ROLLOUT_BOUNDS __maxnreg__(B200MP_ROLLOUT_MAXNREG)
+#elif B200MP_ROLLOUT_MINBLOCKS > 0
+#define B200MP_ROLLOUT_BOUNDS __launch_bounds__(B200MP_ROLLOUT_BLOCK, B200MP_ROLLOUT_MINBLOCKS)
 #else
 #define B200MP_ROLLOUT_BOUNDS __launch_bounds__(B200MP_ROLLOUT_BLOCK)
 #endif

@@ -466,6 +466,9 @@ B200MP_HD R wheel_vx(R vxc, R vyc, R cd, R sd)
 #ifndef B200MP_CARRY_RCP
 #define B200MP_CARRY_RCP 0
 #endif
+#ifndef B200MP_WHEEL_ORDER
+#define B200MP_WHEEL_ORDER 0
+#endif
 #ifndef B200MP_HEADING_FRAME_F32
 #define B200MP_HEADING_FRAME_F32 1   /* K1f is issue-bound: there the 12 instructions per step are time */
 #endif
@@ -578,10 +581,29 @@ B200MP_HD void planar_rhs(const DevParams<R> &P, const R D[4], const R y8[8], R 
                          wheel_vx<R, 2, REAR0>(vxL, vyR, c.cd[2], c.sd[2]), wheel_vx<R, 3, REAR0>(vxR, vyR, c.cd[3], c.sd[3])};
         rcp4(v4, ri);
     }
-    wheel_forces<R, 0, REAR0, TY1, TAB, FIRST, kBatch>(P, D[TY1 ? 0 : 0], vxL, vyF, y8[3], c.cd[0], c.sd[0], Fz[0], fx[0], fy[0], fxt[0], fyt[0], s[0], T, ok, RC, ri[0]);
-    wheel_forces<R, 1, REAR0, TY1, TAB, FIRST, kBatch>(P, D[TY1 ? 0 : 1], vxR, vyF, y8[4], c.cd[1], c.sd[1], Fz[1], fx[1], fy[1], fxt[1], fyt[1], s[1], T, ok, RC, ri[1]);
-    wheel_forces<R, 2, REAR0, TY1, TAB, FIRST, kBatch>(P, D[TY1 ? 0 : 2], vxL, vyR, y8[5], c.cd[2], c.sd[2], Fz[2], fx[2], fy[2], fxt[2], fyt[2], s[2], T, ok, RC, ri[2]);
-    wheel_forces<R, 3, REAR0, TY1, TAB, FIRST, kBatch>(P, D[TY1 ? 0 : 3], vxR, vyR, y8[6], c.cd[3], c.sd[3], Fz[3], fx[3], fy[3], fxt[3], fyt[3], s[3], T, ok, RC, ri[3]);
+#define B200MP_WHEEL0 wheel_forces<R, 0, REAR0, TY1, TAB, FIRST, kBatch>(P, D[TY1 ? 0 : 0], vxL, vyF, y8[3], c.cd[0], c.sd[0], Fz[0], fx[0], fy[0], fxt[0], fyt[0], s[0], T, ok, RC, ri[0]);
+#define B200MP_WHEEL1 wheel_forces<R, 1, REAR0, TY1, TAB, FIRST, kBatch>(P, D[TY1 ? 0 : 1], vxR, vyF, y8[4], c.cd[1], c.sd[1], Fz[1], fx[1], fy[1], fxt[1], fyt[1], s[1], T, ok, RC, ri[1]);
+#define B200MP_WHEEL2 wheel_forces<R, 2, REAR0, TY1, TAB, FIRST, kBatch>(P, D[TY1 ? 0 : 2], vxL, vyR, y8[5], c.cd[2], c.sd[2], Fz[2], fx[2], fy[2], fxt[2], fyt[2], s[2], T, ok, RC, ri[2]);
+#define B200MP_WHEEL3 wheel_forces<R, 3, REAR0, TY1, TAB, FIRST, kBatch>(P, D[TY1 ? 0 : 3], vxR, vyR, y8[6], c.cd[3], c.sd[3], Fz[3], fx[3], fy[3], fxt[3], fyt[3], s[3], T, ok, RC, ri[3]);
+    // The four wheels are independent; the order they are written in only seeds ptxas's list scheduler (development A/B,
+    // profiles/r02_k1_launch_shape.md: the step's time moves by a few per cent with it, the results do not move at all).
+#if B200MP_WHEEL_ORDER == 1
+    B200MP_WHEEL2 B200MP_WHEEL3 B200MP_WHEEL0 B200MP_WHEEL1
+#elif B200MP_WHEEL_ORDER == 2
+    B200MP_WHEEL0 B200MP_WHEEL2 B200MP_WHEEL1 B200MP_WHEEL3
+#elif B200MP_WHEEL_ORDER == 3
+    B200MP_WHEEL3 B200MP_WHEEL2 B200MP_WHEEL1 B200MP_WHEEL0
+#elif B200MP_WHEEL_ORDER == 4
+    B200MP_WHEEL2 B200MP_WHEEL0 B200MP_WHEEL3 B200MP_WHEEL1
+#elif B200MP_WHEEL_ORDER == 5
+    B200MP_WHEEL1 B200MP_WHEEL0 B200MP_WHEEL3 B200MP_WHEEL2
+#else
+    B200MP_WHEEL0 B200MP_WHEEL1 B200MP_WHEEL2 B200MP_WHEEL3
+#endif
+#undef B200MP_WHEEL0
+#undef B200MP_WHEEL1
+#undef B200MP_WHEEL2
+#undef B200MP_WHEEL3
 
     const R Vwz = V * wz, Uwz = U * wz;
     // pair sums shared between the force balance and the yaw moment (the reference adds left to right, :376-378;
