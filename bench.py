@@ -575,7 +575,9 @@ def collision_metrics(eng, wl, np, torch, lit):
             variants[f"{name}_{mode}"] = {"ms": ms, "value": tests / (ms * 1e-3), "free_fraction": float(fr.float().mean().item())}
     ms_k = variants["shipped_scene_auto"]["ms"]
     ms_clear, _ = dev_ms(lambda: eng.collision_check_batch(px, py, None, obs, w["offsets"], w["radii"], trig=trig, want_clearance=True))
-    ms_clear_api, _ = wall_ms(lambda: eng.collision_check_batch(px, py, w["pyaw"], obs, w["offsets"], w["radii"], want_clearance=True), reps=5)
+    ms_clear_api, _ = wall_ms(lambda: eng.collision_check_batch(px, py, w["pyaw"], obs, w["offsets"], w["radii"], want_clearance=True,
+                                                                 clearance_trig="host"), reps=5)
+    ms_clear_api_auto, _ = wall_ms(lambda: eng.collision_check_batch(px, py, w["pyaw"], obs, w["offsets"], w["radii"], want_clearance=True), reps=5)
     ms_clear_api_dev, _ = wall_ms(lambda: eng.collision_check_batch(px, py, w["pyaw"], obs, w["offsets"], w["radii"], want_clearance=True,
                                                                      clearance_trig="device"), reps=5)
     out["collision"] = {
@@ -591,7 +593,10 @@ def collision_metrics(eng, wl, np, torch, lit):
                                 "includes": "kernels + the 4-byte undecided count read back + stream sync"},
         "api_host_trig_all_yaws": {"ms": ms_host_trig, "note": "the former default: numpy cos/sin of 200k yaws on the host + their H2D"},
         "min_clearance": {"kernel_ms": ms_clear, "value": tests / (ms_clear * 1e-3), "api_ms_host_trig": ms_clear_api,
-                          "api_ms_device_trig": ms_clear_api_dev},
+                          "api_ms_device_trig": ms_clear_api_dev, "api_ms": ms_clear_api_auto,
+                          "api": "default (clearance_trig='auto'): device-trig clearance of every path point, numpy cos/sin and an exact "
+                                 "re-evaluation only for the points that can hold their path's minimum; bit-identical to the oracle",
+                          "candidates_resolved_on_host": getattr(eng, "last_clearance_candidates", None)},
         "variants": variants,
     }
     # ---- roofline of the shipped kernel: 4 FP32 lane-operations per executed test (2 subtractions, 1 multiply, 1 FMA = 5 flop)

@@ -65,6 +65,12 @@ def test_collision_cfg3_full_bit_exact(engine):
     ref2, clr_ref, _ = c_oracle.collision_check(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD, want_clearance=True)
     assert np.array_equal(_np(free2).astype(bool), ref) and np.array_equal(ref2, ref)
     assert np.array_equal(_np(clr), clr_ref)                     # same roundings -> identical doubles
+    # the default call resolved only the candidate points (about one per path) with host trig; every yaw on the host gives
+    # the same doubles
+    assert 0 < engine.last_clearance_candidates <= 2 * len(ref)
+    free_h2, clr_h = engine.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD, want_clearance=True,
+                                                  clearance_trig="host")
+    assert np.array_equal(_np(free_h2).astype(bool), ref) and np.array_equal(_np(clr_h), clr_ref)
     # clearance with the yaws kept on the device: flags still the proven bit-exact ones, the clearance within a few ulp of a
     # circle centre (1e-12 m stated; the device's sincos moves a centre by ~2e-16 m)
     free3, clr3 = engine.collision_check_batch(w["px"], w["py"], w["pyaw"], w["obstacles"], OFF, RAD, want_clearance=True,
